@@ -1,0 +1,213 @@
+"""ctypes binding of libdeltaq_cuda (include/deltaq_cuda.h).
+
+The product loads exactly one library: deltaq_b200/libdeltaq_cuda.so, built in-tree by
+``python -m deltaq_b200.build`` (nvcc, sm_100a).  If it is missing, or no CUDA device is present,
+every entry point raises -- there is no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeltaq_cuda.so")
+
+DQ_OK = 0
+DQ_ERR_INVALID_ARGUMENT = -1
+DQ_ERR_OUT_OF_MEMORY = -2
+DQ_ERR_CUDA = -3
+DQ_ERR_NO_DEVICE = -4
+DQ_ERR_INTERNAL = -5
+
+
+class DqStats(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("rounds", ctypes.c_int32), ("radix_passes", ctypes.c_int32),
+                ("kernel_launches", ctypes.c_int32), ("active_sum", ctypes.c_int64),
+                ("algorithmic_bytes", ctypes.c_int64), ("device_ms", ctypes.c_float),
+                ("pass_ms", ctypes.c_float), ("pass_pairs", ctypes.c_int64),
+                ("search_queries", ctypes.c_int32), ("search_long", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DqDiffStreams(ctypes.Structure):
+    _fields_ = [("ctrl", ctypes.c_void_p), ("ctrl_len", ctypes.c_int64),
+                ("diff", ctypes.c_void_p), ("diff_len", ctypes.c_int64),
+                ("extra", ctypes.c_void_p), ("extra_len", ctypes.c_int64),
+                ("search_visits", ctypes.c_int64)]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"libdeltaq_cuda error {status}: {message}")
+        self.status = status
+
+
+EXPORTS = [
+    "dq_cuda_create", "dq_cuda_destroy", "dq_cuda_last_error", "dq_cuda_get_stats", "dq_cuda_set_timing",
+    "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
+    "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams",
+    "dq_cuda_radix_sort_pairs",
+]
+
+
+class Library:
+    """One loaded copy of the C ABI."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} not found: build it with `python -m deltaq_b200.build` (needs nvcc). "
+                "deltaq_b200 has no CPU fallback.")
+        self.path = path
+        L = ctypes.CDLL(path)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        L.dq_cuda_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        L.dq_cuda_destroy.argtypes = [vp]
+        L.dq_cuda_last_error.argtypes = [vp]
+        L.dq_cuda_last_error.restype = ctypes.c_char_p
+        L.dq_cuda_get_stats.argtypes = [vp, ctypes.POINTER(DqStats)]
+        L.dq_cuda_set_timing.argtypes = [vp, ctypes.c_int]
+        L.dq_cuda_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+        L.dq_cuda_host_free.argtypes = [vp]
+        L.dq_cuda_suffix_sort.argtypes = [vp, vp, i32, vp]
+        L.dq_cuda_suffix_sort_device.argtypes = [vp, vp, i32, vp]
+        L.dq_cuda_bsdiff_search.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
+        L.dq_cuda_bsdiff_search_device.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
+        L.dq_cuda_bsdiff_streams.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(DqDiffStreams)]
+        L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
+        for name in EXPORTS:
+            if name != "dq_cuda_last_error":
+                getattr(L, name).restype = ctypes.c_int
+        self.L = L
+
+
+_default = None
+
+
+def default_library():
+    global _default
+    if _default is None:
+        _default = Library(LIB_PATH)
+    return _default
+
+
+def _addr(a):
+    if a is None:
+        return None
+    return ctypes.c_void_p(a.ctypes.data) if a.size else ctypes.c_void_p(0)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (what the C# provider's MemoryManager<int> would own)."""
+
+    def __init__(self, lib, shape, dtype):
+        self._lib = lib
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape)) if not np.isscalar(shape) else int(shape)
+        nbytes = max(1, count * dtype.itemsize)
+        p = ctypes.c_void_p()
+        rc = lib.L.dq_cuda_host_alloc(ctypes.byref(p), nbytes)
+        if rc != DQ_OK:
+            raise NativeError(rc, lib.L.dq_cuda_last_error(None).decode())
+        self._ptr = p
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            self._lib.L.dq_cuda_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """dq_ctx wrapper: one device, one stream, scratch memory; one call at a time."""
+
+    def __init__(self, device=None, lib=None):
+        self.lib = lib or default_library()
+        self._h = ctypes.c_void_p()
+        if device is None:
+            rc = self.lib.L.dq_cuda_create(ctypes.byref(self._h), None, 0)
+        else:
+            dev = (ctypes.c_int * 1)(int(device))
+            rc = self.lib.L.dq_cuda_create(ctypes.byref(self._h), dev, 1)
+        if rc != DQ_OK:
+            raise NativeError(rc, self.lib.L.dq_cuda_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            self.lib.L.dq_cuda_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != DQ_OK:
+            raise NativeError(rc, self.lib.L.dq_cuda_last_error(self._h).decode())
+
+    def stats(self):
+        st = DqStats()
+        self._check(self.lib.L.dq_cuda_get_stats(self._h, ctypes.byref(st)))
+        return st.as_dict()
+
+    def set_timing(self, on):
+        self._check(self.lib.L.dq_cuda_set_timing(self._h, 1 if on else 0))
+
+    def pinned(self, shape, dtype):
+        return PinnedArray(self.lib, shape, dtype)
+
+    # ---- host-pointer entry points -------------------------------------------------------------
+    def suffix_sort(self, text, sa_out):
+        assert text.dtype == np.uint8 and sa_out.dtype == np.int32
+        assert text.flags.c_contiguous and sa_out.flags.c_contiguous and sa_out.size >= text.size
+        self._check(self.lib.L.dq_cuda_suffix_sort(self._h, _addr(text), text.size, _addr(sa_out)))
+
+    def bsdiff_search(self, old, I, new, scan_begin, count, pos_out, len_out):
+        assert old.dtype == np.uint8 and new.dtype == np.uint8
+        assert pos_out.dtype == np.int32 and len_out.dtype == np.int32
+        if I is not None:
+            assert I.dtype == np.int32 and I.flags.c_contiguous and I.size >= old.size
+        self._check(self.lib.L.dq_cuda_bsdiff_search(self._h, _addr(old), old.size, _addr(I), _addr(new), new.size,
+                                                     scan_begin, count, _addr(pos_out), _addr(len_out)))
+
+    def bsdiff_streams(self, old, new):
+        out = DqDiffStreams()
+        self._check(self.lib.L.dq_cuda_bsdiff_streams(self._h, _addr(old), old.size, _addr(new), new.size,
+                                                      ctypes.byref(out)))
+        return {
+            "ctrl": ctypes.string_at(out.ctrl, out.ctrl_len) if out.ctrl_len else b"",
+            "diff": ctypes.string_at(out.diff, out.diff_len) if out.diff_len else b"",
+            "extra": ctypes.string_at(out.extra, out.extra_len) if out.extra_len else b"",
+            "search_visits": out.search_visits,
+        }
+
+    def radix_sort_pairs(self, keys, vals, key_bits=64):
+        assert keys.dtype == np.uint64 and vals.dtype == np.uint32 and keys.size == vals.size
+        self._check(self.lib.L.dq_cuda_radix_sort_pairs(self._h, _addr(keys), _addr(vals), keys.size, key_bits))
+
+    # ---- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr()) ---------------
+    def suffix_sort_device(self, d_text, n, d_sa_out):
+        self._check(self.lib.L.dq_cuda_suffix_sort_device(self._h, ctypes.c_void_p(d_text), n, ctypes.c_void_p(d_sa_out)))
+
+    def bsdiff_search_device(self, d_old, n, d_I, d_new, m, scan_begin, count, d_pos, d_len):
+        self._check(self.lib.L.dq_cuda_bsdiff_search_device(
+            self._h, ctypes.c_void_p(d_old), n, ctypes.c_void_p(d_I) if d_I else None, ctypes.c_void_p(d_new), m,
+            scan_begin, count, ctypes.c_void_p(d_pos), ctypes.c_void_p(d_len)))

@@ -1,0 +1,527 @@
+// deltaq_cuda.cu -- context, host orchestration and the C ABI of libdeltaq_cuda (include/deltaq_cuda.h).
+//
+// There is no CPU fallback in this library: without a CUDA device dq_cuda_create fails with
+// DQ_ERR_NO_DEVICE.  (The g++ -DDQ_EMU build of this file is the test-side logic emulator, see
+// tests/emu/cuda_emu.h; it is never shipped or loaded by the product package.)
+#include "../../include/deltaq_cuda.h"
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dq_common.cuh"
+#include "dq_radix.cuh"
+#include "dq_suffix.cuh"
+#include "dq_search.cuh"
+#include "dq_diff_host.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct EventPair {
+    cudaEvent_t a, b;
+    uint64_t pairs;
+};
+
+}  // namespace
+
+struct dq_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    dq_stats stats{};
+    bool timing = false;
+
+    // suffix-sort state (device)
+    DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist;
+    uint32_t *h_count = nullptr;  // pinned
+    int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<EventPair> pass_events;
+    size_t pass_events_used = 0;
+
+    // search state (device)
+    DevBuf newtext, s_pos, s_len, s_I, s_isa_tmp, s_aux;
+    int32_t resident_m = -1;
+
+    // diff streams (host)
+    dq::diffhost::Streams streams;
+    std::vector<int32_t> h_pos, h_len, h_sa;
+};
+
+namespace {
+
+using dq::div_up;
+namespace rx = dq::radix;
+namespace sx = dq::suffix;
+
+#define DQ_CK(ctx, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return e_ == cudaErrorMemoryAllocation ? DQ_ERR_OUT_OF_MEMORY : DQ_ERR_CUDA;          \
+        }                                                                                         \
+    } while (0)
+
+#define DQ_TRY(expr)             \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != DQ_OK) return rc_; \
+    } while (0)
+
+int ensure(dq_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return DQ_OK;
+    if (b.p) {
+        DQ_CK(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = std::max<size_t>(bytes, 256);
+    want = (want + 255) & ~(size_t)255;
+    DQ_CK(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return DQ_OK;
+}
+
+int bit_length(uint64_t v)
+{
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+struct SortBufs {
+    uint64_t *kin, *kout;
+    uint32_t *vin, *vout;
+};
+
+// Sorts `count` pairs in (s.kin, s.vin) by the digits of `plan`; histograms for all passes are already
+// in ctx->hist ([npass][256] counters at offset 0).  On return the sorted pairs are in (s.kin, s.vin).
+int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &plan)
+{
+    if (count == 0 || plan.npass == 0) return DQ_OK;
+    uint32_t *ghist = ctx->hist.as<uint32_t>();
+    uint32_t *gbase = ghist + rx::kMaxPasses * rx::kRadix;
+    auto scan = rx::scan_hist_kernel;
+    DQ_LAUNCH(scan, plan.npass, rx::kRadix, 0, ctx->stream, ghist, gbase);
+    ctx->stats.kernel_launches++;
+
+    const uint32_t tiles = (uint32_t)div_up(count, rx::kTile);
+    const bool wide = count >= (1u << 30);
+    const size_t desc_bytes = wide ? 8 : 4;
+    const size_t per_pass = (size_t)tiles * rx::kRadix * desc_bytes;
+    const size_t ticket_bytes = 256;  // [kMaxPasses] tickets, padded
+    const bool one_memset = per_pass * plan.npass <= ((size_t)256 << 20);
+    const size_t lb_bytes = ticket_bytes + (one_memset ? per_pass * plan.npass : per_pass);
+    DQ_TRY(ensure(ctx, ctx->lb, lb_bytes));
+    uint8_t *lbp = ctx->lb.as<uint8_t>();
+    uint32_t *tickets = reinterpret_cast<uint32_t *>(lbp);
+    if (one_memset) DQ_CK(ctx, cudaMemsetAsync(lbp, 0, lb_bytes, ctx->stream));
+
+    for (int p = 0; p < plan.npass; ++p) {
+        uint8_t *region = lbp + ticket_bytes + (one_memset ? per_pass * p : 0);
+        if (!one_memset) {
+            DQ_CK(ctx, cudaMemsetAsync(region, 0, per_pass, ctx->stream));
+            if (p == 0) DQ_CK(ctx, cudaMemsetAsync(lbp, 0, ticket_bytes, ctx->stream));
+        }
+        const uint32_t mask = (1u << plan.bits[p]) - 1u;
+        EventPair *ep = nullptr;
+        if (ctx->timing) {
+            if (ctx->pass_events_used == ctx->pass_events.size()) {
+                EventPair e{};
+                DQ_CK(ctx, cudaEventCreate(&e.a));
+                DQ_CK(ctx, cudaEventCreate(&e.b));
+                ctx->pass_events.push_back(e);
+            }
+            ep = &ctx->pass_events[ctx->pass_events_used++];
+            ep->pairs = count;
+            DQ_CK(ctx, cudaEventRecord(ep->a, ctx->stream));
+        }
+        if (wide) {
+            auto k = rx::onesweep_pass_kernel<uint64_t>;
+            DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
+                      count, plan.shift[p], mask, gbase + p * rx::kRadix, reinterpret_cast<uint64_t *>(region),
+                      tickets + p);
+        } else {
+            auto k = rx::onesweep_pass_kernel<uint32_t>;
+            DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
+                      count, plan.shift[p], mask, gbase + p * rx::kRadix, reinterpret_cast<uint32_t *>(region),
+                      tickets + p);
+        }
+        if (ep) DQ_CK(ctx, cudaEventRecord(ep->b, ctx->stream));
+        ctx->stats.kernel_launches++;
+        ctx->stats.radix_passes++;
+        std::swap(s.kin, s.kout);
+        std::swap(s.vin, s.vout);
+    }
+    DQ_CK(ctx, cudaGetLastError());
+    return DQ_OK;
+}
+
+int zero_hist(dq_ctx *ctx)
+{
+    DQ_TRY(ensure(ctx, ctx->hist, (size_t)2 * rx::kMaxPasses * rx::kRadix * 4 + 256));
+    DQ_CK(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)rx::kMaxPasses * rx::kRadix * 4, ctx->stream));
+    return DQ_OK;
+}
+
+uint32_t producer_grid(const dq_ctx *ctx, uint64_t items)
+{
+    uint64_t blocks = div_up(items, (uint64_t)sx::kPackThreads * sx::kPackItems);
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8));
+}
+
+// rank_compact over the sorted active set; returns the next active count through ctx->h_count
+template <bool ROUND0>
+int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
+             uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a)
+{
+    const uint32_t tiles = (uint32_t)div_up(a, sx::kRankTile);
+    const size_t bytes = 256 + (size_t)tiles * 8;
+    DQ_TRY(ensure(ctx, ctx->lb, bytes));
+    uint8_t *lbp = ctx->lb.as<uint8_t>();
+    DQ_CK(ctx, cudaMemsetAsync(lbp, 0, bytes, ctx->stream));
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(lbp);
+    uint32_t *count = ticket + 1;
+    uint64_t *desc = reinterpret_cast<uint64_t *>(lbp + 256);
+    auto k = sx::rank_compact_kernel<ROUND0>;
+    DQ_LAUNCH(k, tiles, sx::kRankThreads, 0, ctx->stream, keys, sa, slot_in, a, n, ctx->isa.as<uint32_t>(),
+              ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count);
+    ctx->stats.kernel_launches++;
+    DQ_CK(ctx, cudaGetLastError());
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    *next_a = *ctx->h_count;
+    return DQ_OK;
+}
+
+// ctx->text holds n bytes followed by >= 16 zero bytes.  Produces ctx->sa (the suffix array) and ctx->isa.
+int sort_resident(dq_ctx *ctx, uint32_t n)
+{
+    dq_stats &st = ctx->stats;
+    st = dq_stats{};
+    st.n = (int32_t)n;
+    ctx->pass_events_used = 0;
+    if (n == 0) return DQ_OK;
+
+    const size_t n8 = (size_t)n * 8, n4 = (size_t)n * 4;
+    DQ_TRY(ensure(ctx, ctx->keyA, n8));
+    DQ_TRY(ensure(ctx, ctx->keyB, n8));
+    DQ_TRY(ensure(ctx, ctx->valA, n4));
+    DQ_TRY(ensure(ctx, ctx->valB, n4));
+    DQ_TRY(ensure(ctx, ctx->isa, n4));
+    DQ_TRY(ensure(ctx, ctx->sa, n4));
+    DQ_TRY(ensure(ctx, ctx->slotA, n4));
+    DQ_TRY(ensure(ctx, ctx->slotB, n4));
+
+    DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+
+    // ---- round 0: all suffixes by their first 8 bytes
+    rx::PassPlan plan{};
+    rx::plan_add_field(plan, 0, 64);
+    DQ_TRY(zero_hist(ctx));
+    {
+        auto k = sx::pack_keys_kernel;
+        DQ_LAUNCH(k, producer_grid(ctx, n), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream,
+                  ctx->text.as<uint8_t>(), n, ctx->keyA.as<uint64_t>(), ctx->valA.as<uint32_t>(), plan,
+                  ctx->hist.as<uint32_t>());
+        st.kernel_launches++;
+    }
+    SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
+    DQ_TRY(run_passes(ctx, s, n, plan));
+    st.rounds = 1;
+    st.active_sum = n;
+    st.algorithmic_bytes = (int64_t)n * (41 + 24 * plan.npass);
+
+    uint32_t *slot_cur = ctx->slotA.as<uint32_t>(), *slot_nxt = ctx->slotB.as<uint32_t>();
+    uint32_t a = 0;
+    // sorted pairs are in (s.kin, s.vin); (s.kout, s.vout) are free
+    DQ_TRY(run_rank<true>(ctx, s.kin, s.vin, nullptr, n, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_cur, &a));
+
+    // ---- doubling rounds over the unresolved suffixes
+    const int bits_r2 = bit_length(n);                      // ISA[.]+1 in [0, n]
+    const int bits_rank = bit_length(n > 1 ? n - 1 : 1);    // rank in [0, n-1]
+    uint64_t h = 8;
+    while (a > 0) {
+        // active set: sa = s.vout, rank = (uint32*)s.kout, slot = slot_cur.  Keys go to s.kin.
+        rx::PassPlan rp{};
+        rx::plan_add_field(rp, 0, bits_r2);
+        rx::plan_add_field(rp, 32, bits_rank);
+        DQ_TRY(zero_hist(ctx));
+        {
+            auto k = sx::build_keys_kernel;
+            DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream, s.vout,
+                      reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), n, a, h, s.kin, rp,
+                      ctx->hist.as<uint32_t>());
+            st.kernel_launches++;
+        }
+        // sort (s.kin, s.vout) using (s.kout, s.vin) as the alternate
+        std::swap(s.vin, s.vout);
+        DQ_TRY(run_passes(ctx, s, a, rp));
+        st.rounds++;
+        st.active_sum += a;
+        st.algorithmic_bytes += (int64_t)a * (52 + 24 * rp.npass);
+
+        uint32_t next_a = 0;
+        DQ_TRY(run_rank<false>(ctx, s.kin, s.vin, slot_cur, a, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_nxt,
+                               &next_a));
+        std::swap(slot_cur, slot_nxt);
+        if (next_a > a) {
+            ctx->err = "internal: active set grew";
+            return DQ_ERR_INTERNAL;
+        }
+        a = next_a;
+        h *= 2;
+        if (h > ((uint64_t)1 << 40)) {
+            ctx->err = "internal: doubling did not converge";
+            return DQ_ERR_INTERNAL;
+        }
+    }
+    st.algorithmic_bytes += (int64_t)n * 4;
+    DQ_CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    DQ_CK(ctx, cudaEventElapsedTime(&st.device_ms, ctx->ev0, ctx->ev1));
+    if (ctx->timing) {
+        float tot = 0.f;
+        uint64_t pairs = 0;
+        for (size_t i = 0; i < ctx->pass_events_used; ++i) {
+            float ms = 0.f;
+            DQ_CK(ctx, cudaEventElapsedTime(&ms, ctx->pass_events[i].a, ctx->pass_events[i].b));
+            tot += ms;
+            pairs += ctx->pass_events[i].pairs;
+        }
+        st.pass_ms = tot;
+        st.pass_pairs = (int64_t)pairs;
+    }
+    return DQ_OK;
+}
+
+int upload_text(dq_ctx *ctx, DevBuf &buf, const uint8_t *src, uint32_t n, cudaMemcpyKind kind)
+{
+    DQ_TRY(ensure(ctx, buf, (size_t)n + 32));
+    if (n) DQ_CK(ctx, cudaMemcpyAsync(buf.p, src, n, kind, ctx->stream));
+    DQ_CK(ctx, cudaMemsetAsync(buf.as<uint8_t>() + n, 0, 32, ctx->stream));
+    return DQ_OK;
+}
+
+int check_args(dq_ctx *ctx, bool ok, const char *what)
+{
+    if (!ok) {
+        ctx->err = what;
+        return DQ_ERR_INVALID_ARGUMENT;
+    }
+    return DQ_OK;
+}
+
+#include "dq_search_host.inl"
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
+{
+    if (!out) return DQ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (ndev > 1) {
+        g_create_error = "one device per context: use one process/context per GPU";
+        return DQ_ERR_INVALID_ARGUMENT;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); libdeltaq_cuda has no CPU fallback";
+        return DQ_ERR_NO_DEVICE;
+    }
+    dq_ctx *ctx = new (std::nothrow) dq_ctx();
+    if (!ctx) return DQ_ERR_OUT_OF_MEMORY;
+    int dev = 0;
+    if (devices && ndev == 1)
+        dev = devices[0];
+    else
+        cudaGetDevice(&dev);
+    ctx->device = dev;
+    auto fail = [&](const char *what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return DQ_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+        return fail("cudaDeviceGetAttribute", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaHostAlloc((void **)&ctx->h_count, 64, cudaHostAllocDefault)) != cudaSuccess)
+        return fail("cudaHostAlloc", e);
+    if ((e = cudaFuncSetAttribute(rx::onesweep_pass_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(rx::onesweep_pass_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    *out = ctx;
+    return DQ_OK;
+}
+
+int dq_cuda_destroy(dq_ctx *ctx)
+{
+    if (!ctx) return DQ_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
+                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->newtext, &ctx->s_pos,
+                      &ctx->s_len, &ctx->s_I, &ctx->s_isa_tmp, &ctx->s_aux};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (auto &e : ctx->pass_events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DQ_OK;
+}
+
+const char *dq_cuda_last_error(dq_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dq_cuda_get_stats(dq_ctx *ctx, dq_stats *out)
+{
+    if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    *out = ctx->stats;
+    return DQ_OK;
+}
+
+int dq_cuda_set_timing(dq_ctx *ctx, int on)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->timing = on != 0;
+    return DQ_OK;
+}
+
+int dq_cuda_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return DQ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+        return DQ_ERR_OUT_OF_MEMORY;
+    }
+    return DQ_OK;
+}
+
+int dq_cuda_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+    return DQ_OK;
+}
+
+int dq_cuda_suffix_sort(dq_ctx *ctx, const uint8_t *text, int32_t n, int32_t *sa_out)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, n >= 0 && (n == 0 || (text && sa_out)), "dq_cuda_suffix_sort: null buffer or negative length"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    ctx->resident_n = -1;
+    DQ_TRY(upload_text(ctx, ctx->text, text, (uint32_t)n, cudaMemcpyHostToDevice));
+    DQ_TRY(sort_resident(ctx, (uint32_t)n));
+    if (n) DQ_CK(ctx, cudaMemcpyAsync(sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->resident_n = n;
+    return DQ_OK;
+}
+
+int dq_cuda_suffix_sort_device(dq_ctx *ctx, const uint8_t *d_text, int32_t n, int32_t *d_sa_out)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, n >= 0 && (n == 0 || (d_text && d_sa_out)), "dq_cuda_suffix_sort_device: null buffer or negative length"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    ctx->resident_n = -1;
+    DQ_TRY(upload_text(ctx, ctx->text, d_text, (uint32_t)n, cudaMemcpyDeviceToDevice));
+    DQ_TRY(sort_resident(ctx, (uint32_t)n));
+    if (n) DQ_CK(ctx, cudaMemcpyAsync(d_sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->resident_n = n;
+    return DQ_OK;
+}
+
+int dq_cuda_radix_sort_pairs(dq_ctx *ctx, uint64_t *keys, uint32_t *vals, int32_t count, int32_t key_bits)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, count >= 0 && key_bits >= 0 && key_bits <= 64 && (count == 0 || (keys && vals)),
+                      "dq_cuda_radix_sort_pairs: bad arguments"));
+    if (count == 0 || key_bits == 0) return DQ_OK;
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    ctx->resident_n = -1;
+    ctx->stats = dq_stats{};
+    ctx->pass_events_used = 0;
+    const size_t c8 = (size_t)count * 8, c4 = (size_t)count * 4;
+    DQ_TRY(ensure(ctx, ctx->keyA, c8));
+    DQ_TRY(ensure(ctx, ctx->keyB, c8));
+    DQ_TRY(ensure(ctx, ctx->valA, c4));
+    DQ_TRY(ensure(ctx, ctx->valB, c4));
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->keyA.p, keys, c8, cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->valA.p, vals, c4, cudaMemcpyHostToDevice, ctx->stream));
+    rx::PassPlan plan{};
+    rx::plan_add_field(plan, 0, key_bits);
+    DQ_TRY(zero_hist(ctx));
+    {
+        auto k = sx::hist_only_kernel;
+        DQ_LAUNCH(k, producer_grid(ctx, (uint64_t)count), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream,
+                  ctx->keyA.as<uint64_t>(), (uint32_t)count, plan, ctx->hist.as<uint32_t>());
+    }
+    SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
+    DQ_TRY(run_passes(ctx, s, (uint32_t)count, plan));
+    DQ_CK(ctx, cudaMemcpyAsync(keys, s.kin, c8, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaMemcpyAsync(vals, s.vin, c4, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+int dq_cuda_bsdiff_search(dq_ctx *ctx, const uint8_t *, int32_t, const int32_t *, const uint8_t *, int32_t, int32_t,
+                          int32_t, int32_t *, int32_t *)
+{
+    if (ctx) ctx->err = "not implemented";
+    return DQ_ERR_INTERNAL;
+}
+int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *, int32_t, const int32_t *, const uint8_t *, int32_t,
+                                 int32_t, int32_t, int32_t *, int32_t *)
+{
+    if (ctx) ctx->err = "not implemented";
+    return DQ_ERR_INTERNAL;
+}
+int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *, int32_t, const uint8_t *, int32_t, dq_diff_streams *)
+{
+    if (ctx) ctx->err = "not implemented";
+    return DQ_ERR_INTERNAL;
+}
+}

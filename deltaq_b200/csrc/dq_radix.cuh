@@ -1,0 +1,242 @@
+// dq_radix.cuh -- onesweep-style least-significant-digit radix sort of (uint64 key, uint32 value) pairs.
+//
+// One kernel launch per digit.  Digit histograms for ALL passes are accumulated up front by the kernel
+// that produces the keys (pack_keys / build_keys in dq_suffix.cuh), so a pass reads each pair once and
+// writes it once: 24 algorithmic bytes per pair per pass.  Tile digit offsets come from a decoupled
+// look-back over per-tile digit counts (one descriptor per tile per digit), tile order comes from an
+// atomic ticket so that a tile only ever waits on tiles that already started.
+//
+// Replaces (by result, not by method) the comparison sorts of the reference's suffix sorters:
+//   /root/reference/src/DeltaQ.SuffixSorting.LibDivSufSort/SsSort.cs:23 (sssort),
+//   /root/reference/src/DeltaQ.SuffixSorting.LibDivSufSort/TrSort.cs:19 (trsort).
+#pragma once
+#include "dq_common.cuh"
+
+namespace dq {
+namespace radix {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kMaxPasses = 8;
+
+constexpr int kThreads = 256;  // == kRadix: thread d owns digit d in the look-back
+constexpr int kItems = 16;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTile = kThreads * kItems;
+
+struct PassPlan {
+    int npass;
+    int shift[kMaxPasses];
+    int bits[kMaxPasses];
+};
+
+// cover key bits [lo, lo+nbits) with digits of <= 8 bits, as evenly as possible
+inline void plan_add_field(PassPlan &p, int lo, int nbits)
+{
+    if (nbits <= 0) return;
+    int nd = (nbits + kRadixBits - 1) / kRadixBits;
+    int base = nbits / nd, extra = nbits % nd;
+    for (int i = 0; i < nd; ++i) {
+        int b = base + (i < extra ? 1 : 0);
+        p.shift[p.npass] = lo;
+        p.bits[p.npass] = b;
+        p.npass++;
+        lo += b;
+    }
+}
+
+// ---- digit histograms, accumulated by the key producers ------------------------------------------------
+// sh: shared [npass][kRadix] counters, zeroed by the caller block
+__device__ __forceinline__ void hist_accumulate(uint32_t *sh, const PassPlan &plan, uint64_t key)
+{
+#pragma unroll
+    for (int p = 0; p < kMaxPasses; ++p) {
+        if (p < plan.npass) {
+            uint32_t d = (uint32_t)(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+            atomicAdd(&sh[p * kRadix + d], 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void hist_flush(const uint32_t *sh, int npass, uint32_t *ghist)
+{
+    for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) {
+        uint32_t c = sh[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// exclusive scan of each pass's 256 counters: ghist[p][d] -> gbase[p][d].  grid = npass, block = 256.
+__global__ void __launch_bounds__(kRadix) scan_hist_kernel(const uint32_t *__restrict__ ghist,
+                                                          uint32_t *__restrict__ gbase)
+{
+    __shared__ uint32_t warp_tot[kRadix / 32];
+    const unsigned d = threadIdx.x;
+    const uint32_t c = ghist[blockIdx.x * kRadix + d];
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane_id() >= (unsigned)o) incl += t;
+    }
+    if (lane_id() == 31) warp_tot[warp_id()] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (unsigned w = 0; w < warp_id(); ++w) woff += warp_tot[w];
+    gbase[blockIdx.x * kRadix + d] = woff + incl - c;
+}
+
+// ---- look-back descriptors -----------------------------------------------------------------------------
+template <typename DescT> struct Desc;
+template <> struct Desc<uint32_t> {
+    static constexpr int kValBits = 30;
+};
+template <> struct Desc<uint64_t> {
+    static constexpr int kValBits = 62;
+};
+constexpr unsigned kStatusAggregate = 1, kStatusInclusive = 2;
+
+// One LSD pass.  grid = #tiles, block = kThreads, dynamic smem = pass_smem_bytes().
+//   lb          [#tiles][kRadix] descriptors, zero before the launch
+//   tile_ticket one counter, zero before the launch
+//   gbase       [kRadix] exclusive digit offsets of this pass over the whole input
+constexpr size_t pass_smem_bytes()
+{
+    return (size_t)kTile * 8 + (size_t)kTile * 4 + (size_t)kWarps * kRadix * 4 + 2 * kRadix * 4 + 64;
+}
+
+template <typename DescT>
+__global__ void __launch_bounds__(kThreads)
+onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                     uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t count, int shift,
+                     uint32_t mask, const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
+                     uint32_t *__restrict__ tile_ticket)
+{
+    DQ_DYN_SMEM(smem);
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *svals = reinterpret_cast<uint32_t *>(smem + (size_t)kTile * 8);
+    uint32_t *whist = svals + kTile;          // [kWarps][kRadix]
+    uint32_t *sdig = whist + kWarps * kRadix; // [kRadix] first slot of each digit inside the tile
+    uint32_t *sout = sdig + kRadix;           // [kRadix] global slot of tile item i with digit d is sout[d] + i
+    uint32_t *smisc = sout + kRadix;
+
+    const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+
+    if (tid == 0) smisc[0] = atomicAdd(tile_ticket, 1u);
+    for (int i = tid; i < kWarps * kRadix; i += kThreads) whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = smisc[0];
+    const uint32_t tile_base = tile * (uint32_t)kTile;
+    const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
+
+    // ---- load, warp-striped: item j of lane l in warp w is tile_base + w*512 + j*32 + l
+    uint64_t key[kItems];
+    uint32_t val[kItems];
+    uint32_t rank[kItems];
+    const uint32_t wbase = warp * (32 * kItems) + lane;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        uint32_t li = wbase + j * 32;
+        key[j] = li < tile_count ? ld_stream(kin + tile_base + li) : ~0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        uint32_t li = wbase + j * 32;
+        val[j] = li < tile_count ? ld_stream(vin + tile_base + li) : 0u;
+    }
+
+    // ---- stable rank of each item among the items of its warp with the same digit
+    uint32_t *wh = whist + warp * kRadix;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const bool valid = wbase + j * 32 < tile_count;
+        const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+        const unsigned vmask = __ballot_sync(kFullMask, valid);
+        const unsigned peers = __match_any_sync(kFullMask, d) & vmask;
+        int leader = valid ? (__ffs(peers) - 1) : (int)lane;
+        uint32_t before = 0;
+        if (valid && (int)lane == leader) {
+            before = wh[d];
+            wh[d] = before + __popc(peers);
+        }
+        before = __shfl_sync(kFullMask, before, leader);
+        rank[j] = before + __popc(peers & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- thread d: digit d's count in this tile, per-warp exclusive offsets, look-back
+    {
+        const unsigned d = tid;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            uint32_t c = whist[w * kRadix + d];
+            whist[w * kRadix + d] = sum;
+            sum += c;
+        }
+        constexpr int VB = Desc<DescT>::kValBits;
+        constexpr DescT kValMask = ((DescT)1 << VB) - 1;
+        DescT *my = lb + (size_t)tile * kRadix + d;
+        if (tile > 0) st_release(my, ((DescT)kStatusAggregate << VB) | (DescT)sum);
+
+        // exclusive scan of the 256 digit counts -> first slot of each digit inside the tile
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) smisc[1 + warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (unsigned w = 0; w < warp; ++w) woff += smisc[1 + w];
+        const uint32_t first = woff + incl - sum;
+
+        DescT excl = 0;
+        if (tile > 0) {
+            uint32_t t = tile - 1;
+            for (;;) {
+                DescT v = ld_acquire(lb + (size_t)t * kRadix + d);
+                unsigned st = (unsigned)(v >> VB);
+                if (st == 0) {
+                    DQ_SPIN_HINT();
+                    continue;
+                }
+                excl += v & kValMask;
+                if (st == kStatusInclusive) break;
+                --t;
+            }
+        }
+        st_release(my, ((DescT)kStatusInclusive << VB) | (excl + (DescT)sum));
+        sdig[d] = first;
+        sout[d] = gbase[d] + (uint32_t)excl - first;
+    }
+    __syncthreads();
+
+    // ---- stage the tile in digit order, then stream it out in coalesced runs
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        if (wbase + j * 32 < tile_count) {
+            const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+            const uint32_t r = sdig[d] + wh[d] + rank[j];
+            skeys[r] = key[j];
+            svals[r] = val[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t i = tid + j * kThreads;
+        if (i < tile_count) {
+            const uint64_t k = skeys[i];
+            const uint32_t d = (uint32_t)(k >> shift) & mask;
+            const uint32_t dst = sout[d] + i;
+            kout[dst] = k;
+            vout[dst] = svals[i];
+        }
+    }
+}
+
+}  // namespace radix
+}  // namespace dq

@@ -1,0 +1,119 @@
+/*
+ * deltaq_cuda.h -- C ABI of libdeltaq_cuda, the B200 (sm_100a) suffix sorter and bsdiff match engine.
+ *
+ * The reference (jzebedee/deltaq, /root/reference) is 100 % managed C# and has NO native interface: the
+ * plug-in point for this path is the managed interface
+ *     DeltaQ.SuffixSorting.ISuffixSort        src/DeltaQ.SuffixSorting.Abstractions/ISuffixSort.cs:9-28
+ * and the match search is the private method
+ *     DeltaQ.BsDiff.Diff.Search               src/DeltaQ.BsDiff/Diff.cs:267-298
+ * A new provider `DeltaQ.SuffixSorting.Cuda.CudaSuffixSort : ISuffixSort` (csharp/) binds
+ * the entry points below through LibraryImport/P-Invoke; the same ABI is driven from Python ctypes
+ * (deltaq_b200/_native.py) for every test and benchmark in this repository.
+ *
+ * Conventions: plain pointers and sizes; every function returns a status (0 = DQ_OK, negative = error
+ * class) and never throws; the text of the last error of a context is dq_cuda_last_error(ctx).  A context
+ * owns one device, one stream and its scratch memory; it serves one call at a time (calls on one context
+ * are serialised by an internal lock); contexts are independent.
+ */
+#ifndef DELTAQ_CUDA_H
+#define DELTAQ_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dq_ctx dq_ctx;
+
+enum {
+    DQ_OK = 0,
+    DQ_ERR_INVALID_ARGUMENT = -1, /* maps to ArgumentException / ArgumentNullException */
+    DQ_ERR_OUT_OF_MEMORY = -2,    /* maps to OutOfMemoryException */
+    DQ_ERR_CUDA = -3,             /* maps to InvalidOperationException(dq_cuda_last_error) */
+    DQ_ERR_NO_DEVICE = -4,        /* no CUDA device: there is NO CPU fallback */
+    DQ_ERR_INTERNAL = -5
+};
+
+/* Per-call statistics of the most recent dq_cuda_suffix_sort* / dq_cuda_bsdiff_search* on the context. */
+typedef struct dq_stats {
+    int32_t n;                 /* input length of the last sort */
+    int32_t rounds;            /* doubling rounds run, round 0 included */
+    int32_t radix_passes;      /* onesweep pass launches */
+    int32_t kernel_launches;   /* all kernel launches of the call */
+    int64_t active_sum;        /* sum over rounds of suffixes entering the round */
+    int64_t algorithmic_bytes; /* SURVEY.md section 8(d) formula, summed over rounds (+4n output) */
+    float   device_ms;         /* CUDA-event time of the device work of the last call (no host copies) */
+    float   pass_ms;           /* CUDA-event time spent inside onesweep pass launches (0 unless timing on) */
+    int64_t pass_pairs;        /* pairs moved by those launches (sum of per-launch counts) */
+    int32_t search_queries;    /* positions answered by the last search */
+    int32_t search_long;       /* of those, answered by the long-match resolver */
+} dq_stats;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+/* devices/ndev: CUDA ordinals to use; NULL/0 = current device.  This build drives one device per context
+ * (ndev must be <= 1); multi-GPU runs use one process and one context per GPU. */
+int dq_cuda_create(dq_ctx **out, const int *devices, int ndev);
+int dq_cuda_destroy(dq_ctx *ctx);
+const char *dq_cuda_last_error(dq_ctx *ctx); /* ctx may be NULL: last error of a failed dq_cuda_create */
+int dq_cuda_get_stats(dq_ctx *ctx, dq_stats *out);
+/* when on, onesweep launches are bracketed by CUDA events (serialises nothing, costs two records/launch) */
+int dq_cuda_set_timing(dq_ctx *ctx, int on);
+
+/* Pinned host buffers (the provider's IMemoryOwner<int> can sit on these: no staging copy on D2H). */
+int dq_cuda_host_alloc(void **out, size_t bytes);
+int dq_cuda_host_free(void *p);
+
+/* ---- ISuffixSort.Sort ------------------------------------------------------------------------------
+ * Replaces ISuffixSort.Sort(ReadOnlySpan<byte> text, Span<int> suffixes) (ISuffixSort.cs:27; reference
+ * implementations LibDivSufSort.cs:21-31, SAIS.cs:25-42).  text and sa_out are HOST pointers; writes
+ * exactly sa_out[0..n) (Diff.Create relies on I[n] staying 0: Diff.cs:78,90); n == 0 is a no-op; sa_out
+ * need not be zeroed.  The "lengths must match" ArgumentException of LibDivSufSort.cs:23-31 is raised by
+ * the managed/Python wrapper, which owns both lengths.  The text, the suffix array and its inverse stay
+ * resident on the device for a following dq_cuda_bsdiff_search with I_or_null == NULL. */
+int dq_cuda_suffix_sort(dq_ctx *ctx, const uint8_t *text, int32_t n, int32_t *sa_out);
+
+/* Same, with DEVICE pointers; runs on the context's stream and returns after the stream is idle. */
+int dq_cuda_suffix_sort_device(dq_ctx *ctx, const uint8_t *d_text, int32_t n, int32_t *d_sa_out);
+
+/* ---- Diff.Search -----------------------------------------------------------------------------------
+ * Replaces the per-position calls  len = Search(I, oldData, newData[scan..], 0, oldData.Length, out pos)
+ * of Diff.Create (Diff.cs:106, Search at :267-298) for scan in [scan_begin, scan_begin+count):
+ * pos_out[k], len_out[k] are bit-identical to what the reference computes at scan = scan_begin + k,
+ * including the I[n] == 0 leaf quirk.  I_or_null: the (n+1)-entry buffer of Diff.cs:78 (entry n is
+ * ignored and treated as 0), or NULL to use the suffix array left on the device by the last
+ * dq_cuda_suffix_sort of the same `old`.  All pointers are HOST pointers. */
+int dq_cuda_bsdiff_search(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I_or_null,
+                          const uint8_t *new_, int32_t m, int32_t scan_begin, int32_t count,
+                          int32_t *pos_out, int32_t *len_out);
+
+/* Same with DEVICE pointers (d_I_or_null: n entries are read). */
+int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *d_old, int32_t n, const int32_t *d_I_or_null,
+                                 const uint8_t *d_new, int32_t m, int32_t scan_begin, int32_t count,
+                                 int32_t *d_pos_out, int32_t *d_len_out);
+
+/* ---- Diff.Create, hot path + consumer ---------------------------------------------------------------
+ * Mirror of Diff.Create (Diff.cs:27-242) up to the compression boundary: suffix sort and match search on
+ * the device, then the reference's greedy scan/extend/emit loop (Diff.cs:100-223, textually unchanged
+ * except that Search() is an array read) on the host.  Returns the three UNCOMPRESSED streams the
+ * reference feeds to its bzip2 encoders.  Buffers are owned by the context and valid until the next call
+ * on it. */
+typedef struct dq_diff_streams {
+    const uint8_t *ctrl;  int64_t ctrl_len;   /* packed-long triples, SpanExtensions.cs:7-30 */
+    const uint8_t *diff;  int64_t diff_len;
+    const uint8_t *extra; int64_t extra_len;
+    int64_t search_visits;                    /* scan positions the greedy loop evaluated */
+} dq_diff_streams;
+int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
+                           dq_diff_streams *out);
+
+/* ---- building block, exported for tests and reuse ----------------------------------------------------
+ * Stable LSD radix sort of (uint64 key, uint32 value) pairs on key bits [0, key_bits), host pointers. */
+int dq_cuda_radix_sort_pairs(dq_ctx *ctx, uint64_t *keys, uint32_t *vals, int32_t count, int32_t key_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DELTAQ_CUDA_H */

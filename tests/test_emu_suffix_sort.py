@@ -1,0 +1,73 @@
+"""Host logic + kernel indexing of the suffix sorter on the CPU logic emulator (tests/emu; NOT the product,
+NOT a fallback -- see tests/emu/cuda_emu.h).  The same C ABI, the same Python wrappers."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import (REF_RANDOM_SIZES, SHRUGGY, adversarial_texts, asset_names, load_asset, load_golden_sa,
+                      random_bytes)
+
+
+@pytest.fixture(scope="module")
+def sorter():
+    from deltaq_b200 import CudaSuffixSort
+    import emu
+    s = CudaSuffixSort(_lib=emu.library())
+    yield s
+    s.dispose()
+
+
+def _sort(sorter, t):
+    with sorter.sort(t) as owner:
+        return owner.memory.copy()
+
+
+@pytest.mark.parametrize("name", asset_names())
+def test_fixture_file(sorter, name):
+    t = load_asset(name)
+    assert np.array_equal(_sort(sorter, t), load_golden_sa(name))
+
+
+@pytest.mark.parametrize("size", REF_RANDOM_SIZES)
+def test_random_buffer(sorter, size):
+    t = random_bytes(size)
+    sa = np.full(size + 1, -7, dtype=np.int32)
+    sorter.sort(t, sa[:size])
+    assert sa[size] == -7
+    assert np.array_equal(sa[:size], oracle.sais(t))
+
+
+@pytest.mark.parametrize("name", sorted(adversarial_texts()))
+def test_adversarial(sorter, name):
+    t = adversarial_texts()[name]
+    assert np.array_equal(_sort(sorter, t), oracle.sais(t))
+
+
+def test_shruggy_and_errors(sorter):
+    t = np.frombuffer(SHRUGGY, dtype=np.uint8)
+    assert np.array_equal(_sort(sorter, t), oracle.sais(t))
+    with pytest.raises(ValueError, match="same length"):
+        sorter.sort(random_bytes(10), np.zeros(9, dtype=np.int32))
+    with pytest.raises(TypeError):
+        sorter.sort(None)
+
+
+def test_multi_tile_low_entropy(sorter):
+    # several radix tiles and rank tiles, many doubling rounds, partial last tiles
+    rng = np.random.default_rng(11)
+    for n, sigma in [(20_000, 2), (9_000, 3), (4097, 2), (8193, 256)]:
+        t = rng.integers(0, sigma, n, dtype=np.uint8)
+        assert np.array_equal(_sort(sorter, t), oracle.sais(t))
+
+
+def test_radix_sort_pairs(sorter):
+    rng = np.random.default_rng(3)
+    for count, bits in [(1, 64), (4095, 64), (4097, 13), (30_000, 64), (10_000, 3)]:
+        keys = rng.integers(0, 2 ** 63, count, dtype=np.uint64)
+        if bits < 64:
+            keys &= np.uint64((1 << bits) - 1)
+        vals = np.arange(count, dtype=np.uint32)
+        k2, v2 = keys.copy(), vals.copy()
+        sorter.context.radix_sort_pairs(k2, v2, bits)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
