@@ -1,0 +1,159 @@
+"""Host-side mirror of DeltaQ.BsDiff.Diff / Patch for the accelerated path.
+
+``Diff.create(old, new, output, suffix_sort)`` mirrors ``Diff.Create(ReadOnlySpan<byte> oldData,
+ReadOnlySpan<byte> newData, Stream output, ISuffixSort suffixSort)``
+(/root/reference/src/DeltaQ.BsDiff/Diff.cs:27-242): same argument checks and error classes, same BSDIFF40
+container (Diff.cs:54-70, :226-241, Constants.cs:5-12).  The suffix sort (Diff.cs:90) and every
+``Search`` call (Diff.cs:106) run on the GPU; the greedy scan/emit loop (Diff.cs:100-223) runs on the
+host inside libdeltaq_cuda (csrc/dq_diff_host.h), consuming the bulk (pos, len) table.
+
+The three streams are compressed with Python's ``bz2`` (libbz2).  The reference uses SharpZipLib 1.4.2
+(un-vendored third party); compressed bytes are not claimed identical to it -- the uncompressed
+ctrl/diff/extra streams and the header fields are (tests/test_bsdiff_gpu.py).
+
+``Patch.apply`` mirrors Patch.Apply (Patch.cs:25-168); it is not on the hot path and exists for the
+reference's round-trip tests (BsDiffTests.cs:30-78).
+"""
+import bz2
+import io
+
+import numpy as np
+
+from .suffix_sort import CudaSuffixSort, as_bytes_array
+
+HEADER_SIZE = 32                      # Constants.cs:7
+SIGNATURE = 0x3034464649445342        # "BSDIFF40", Constants.cs:12
+
+
+def write_packed_long(y):
+    """SpanExtensions.WritePackedLong (SpanExtensions.cs:7-30): sign-magnitude, little-endian."""
+    u = -y if y < 0 else y
+    b = bytearray(u.to_bytes(8, "little"))
+    if y < 0:
+        b[7] |= 0x80
+    return bytes(b)
+
+
+def read_packed_long(b):
+    """SpanExtensions.ReadPackedLong (SpanExtensions.cs:32-44)."""
+    y = int.from_bytes(b[:7], "little") | ((b[7] & 0x7F) << 56)
+    return -y if b[7] & 0x80 else y
+
+
+def create_streams(old, new, suffix_sort):
+    """Uncompressed ctrl / diff / extra streams of Diff.Create for (old, new): GPU sort + GPU search +
+    host greedy loop.  ``suffix_sort`` must be a CudaSuffixSort."""
+    o = as_bytes_array(old, "oldData")
+    w = as_bytes_array(new, "newData")
+    if not isinstance(suffix_sort, CudaSuffixSort):
+        raise TypeError("create_streams needs a CudaSuffixSort")
+    return suffix_sort.context.bsdiff_streams(o, w)
+
+
+def search_all(old, new, suffix_sort, I=None, scan_begin=0, count=None):
+    """(pos, len) of Diff.Search at every scan position in [scan_begin, scan_begin+count).  I: the (n+1)-entry
+    buffer of Diff.cs:78, or None to sort `old` with suffix_sort first."""
+    o = as_bytes_array(old, "oldData")
+    w = as_bytes_array(new, "newData")
+    ctx = suffix_sort.context
+    if count is None:
+        count = w.size - scan_begin
+    if I is None:
+        I = np.zeros(o.size + 1, dtype=np.int32)
+        suffix_sort.sort(o, I[:o.size])
+        I_arg = None        # the suffix array is still resident on the device
+    else:
+        I_arg = np.ascontiguousarray(I, dtype=np.int32)
+        if I_arg.size != o.size + 1:
+            raise ValueError("I must have oldData.Length + 1 entries (Diff.cs:78)")
+    pos = np.empty(count, dtype=np.int32)
+    ln = np.empty(count, dtype=np.int32)
+    ctx.bsdiff_search(o, I_arg, w, scan_begin, count, pos, ln)
+    return pos, ln
+
+
+class Diff:
+    @staticmethod
+    def create(old_data, new_data, output, suffix_sort):
+        # argument checks: Diff.cs:29-52
+        if output is None:
+            raise TypeError("output must not be None")          # ArgumentNullException(nameof(output))
+        if suffix_sort is None:
+            raise TypeError("suffixSort must not be None")      # ArgumentNullException(nameof(suffixSort))
+        if not (hasattr(output, "seekable") and output.seekable()):
+            raise ValueError("Output stream must be seekable.")  # ArgumentException
+        if not (hasattr(output, "writable") and output.writable()):
+            raise ValueError("Output stream must be writable.")
+        o = as_bytes_array(old_data, "oldData")
+        w = as_bytes_array(new_data, "newData")
+
+        header = bytearray(HEADER_SIZE)
+        header[0:8] = write_packed_long(SIGNATURE)
+        header[24:32] = write_packed_long(w.size)
+        start = output.tell()
+        output.write(bytes(header))
+
+        streams = create_streams(o, w, suffix_sort)
+        ctrl = bz2.compress(streams["ctrl"])
+        diff = bz2.compress(streams["diff"])
+        extra = bz2.compress(streams["extra"])
+
+        output.write(ctrl)
+        header[8:16] = write_packed_long(len(ctrl))
+        output.write(diff)
+        header[16:24] = write_packed_long(len(diff))
+        output.write(extra)
+        end = output.tell()
+        output.seek(start)
+        output.write(bytes(header))
+        output.seek(end)
+
+
+class Patch:
+    @staticmethod
+    def apply(old_data, patch, output):
+        """Patch.Apply(ReadOnlyMemory<byte> input, ReadOnlyMemory<byte> diff, Stream output), Patch.cs:25-36."""
+        o = as_bytes_array(old_data, "input")
+        p = bytes(patch)
+        header = p[:HEADER_SIZE]
+        if len(header) < HEADER_SIZE or read_packed_long(header[0:8]) != SIGNATURE:
+            raise RuntimeError("Corrupt patch")                 # InvalidOperationException, Patch.cs:68-70
+        ctrl_len = read_packed_long(header[8:16])
+        diff_len = read_packed_long(header[16:24])
+        new_size = read_packed_long(header[24:32])
+        if ctrl_len < 0 or diff_len < 0 or new_size < 0:
+            raise RuntimeError("Corrupt patch")
+        ctrl = bz2.decompress(p[HEADER_SIZE:HEADER_SIZE + ctrl_len])
+        diff = bz2.decompress(p[HEADER_SIZE + ctrl_len:HEADER_SIZE + ctrl_len + diff_len])
+        extra = bz2.decompress(p[HEADER_SIZE + ctrl_len + diff_len:])
+        out = apply_streams(o, ctrl, diff, extra, new_size)
+        output.write(out)
+        if hasattr(output, "flush"):
+            output.flush()
+
+
+def apply_streams(old, ctrl, diff, extra, new_size):
+    """Patch.ApplyInternal (Patch.cs:95-168) on uncompressed streams."""
+    o = as_bytes_array(old, "input")
+    d = np.frombuffer(diff, dtype=np.uint8)
+    out = io.BytesIO()
+    old_pos = cp = dp = ep = 0
+    while out.tell() < new_size:
+        add = read_packed_long(ctrl[cp:cp + 8])
+        copy = read_packed_long(ctrl[cp + 8:cp + 16])
+        seek = read_packed_long(ctrl[cp + 16:cp + 24])
+        cp += 24
+        if out.tell() + add > new_size:
+            raise RuntimeError("Corrupt patch")
+        seg_old = o[old_pos:old_pos + add]
+        if seg_old.size != add or dp + add > d.size:
+            raise RuntimeError("Corrupt patch")
+        out.write((d[dp:dp + add] + seg_old).astype(np.uint8).tobytes())
+        dp += add
+        old_pos += add
+        if out.tell() + copy > new_size:
+            raise RuntimeError("Corrupt patch")
+        out.write(extra[ep:ep + copy])
+        ep += copy
+        old_pos += seek
+    return out.getvalue()

@@ -32,6 +32,11 @@ struct EventPair {
     uint64_t pairs;
 };
 
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
 }  // namespace
 
 struct dq_ctx {
@@ -52,12 +57,12 @@ struct dq_ctx {
     size_t pass_events_used = 0;
 
     // search state (device)
-    DevBuf newtext, s_pos, s_len, s_I, s_isa_tmp, s_aux;
-    int32_t resident_m = -1;
+    DevBuf newtext, s_pos, s_len, lcp, min1, min2, headp, headl;
+    bool lcp_valid = false;  // lcp/min1/min2 describe the resident (text, sa)
 
     // diff streams (host)
     dq::diffhost::Streams streams;
-    std::vector<int32_t> h_pos, h_len, h_sa;
+    PinBuf h_pos, h_len;
 };
 
 namespace {
@@ -218,6 +223,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     st = dq_stats{};
     st.n = (int32_t)n;
     ctx->pass_events_used = 0;
+    ctx->lcp_valid = false;
     if (n == 0) return DQ_OK;
 
     const size_t n8 = (size_t)n * 8, n4 = (size_t)n * 4;
@@ -389,7 +395,7 @@ int dq_cuda_destroy(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->newtext, &ctx->s_pos,
-                      &ctx->s_len, &ctx->s_I, &ctx->s_isa_tmp, &ctx->s_aux};
+                      &ctx->s_len, &ctx->lcp, &ctx->min1, &ctx->min2, &ctx->headp, &ctx->headl};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->pass_events) {
@@ -397,6 +403,8 @@ int dq_cuda_destroy(dq_ctx *ctx)
         cudaEventDestroy(e.b);
     }
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->h_pos.p) cudaFreeHost(ctx->h_pos.p);
+    if (ctx->h_len.p) cudaFreeHost(ctx->h_len.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -507,21 +515,52 @@ int dq_cuda_radix_sort_pairs(dq_ctx *ctx, uint64_t *keys, uint32_t *vals, int32_
 }  // extern "C"
 
 extern "C" {
-int dq_cuda_bsdiff_search(dq_ctx *ctx, const uint8_t *, int32_t, const int32_t *, const uint8_t *, int32_t, int32_t,
-                          int32_t, int32_t *, int32_t *)
+
+int dq_cuda_bsdiff_search(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I_or_null, const uint8_t *new_,
+                          int32_t m, int32_t scan_begin, int32_t count, int32_t *pos_out, int32_t *len_out)
 {
-    if (ctx) ctx->err = "not implemented";
-    return DQ_ERR_INTERNAL;
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return search_common(ctx, old_, n, I_or_null, new_, m, scan_begin, count, pos_out, len_out, false);
 }
-int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *, int32_t, const int32_t *, const uint8_t *, int32_t,
-                                 int32_t, int32_t, int32_t *, int32_t *)
+
+int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *d_old, int32_t n, const int32_t *d_I_or_null,
+                                 const uint8_t *d_new, int32_t m, int32_t scan_begin, int32_t count,
+                                 int32_t *d_pos_out, int32_t *d_len_out)
 {
-    if (ctx) ctx->err = "not implemented";
-    return DQ_ERR_INTERNAL;
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return search_common(ctx, d_old, n, d_I_or_null, d_new, m, scan_begin, count, d_pos_out, d_len_out, true);
 }
-int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *, int32_t, const uint8_t *, int32_t, dq_diff_streams *)
+
+int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
+                           dq_diff_streams *out)
 {
-    if (ctx) ctx->err = "not implemented";
-    return DQ_ERR_INTERNAL;
+    if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || new_), "bsdiff_streams: bad arguments"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    // Diff.cs:90 -- suffixSort.Sort(oldData, I[..^1]); the suffix array stays on the device
+    ctx->resident_n = -1;
+    DQ_TRY(upload_text(ctx, ctx->text, old_, (uint32_t)n, cudaMemcpyHostToDevice));
+    DQ_TRY(sort_resident(ctx, (uint32_t)n));
+    ctx->resident_n = n;
+    // Diff.cs:106 for every scan position
+    DQ_TRY(ensure_pinned(ctx, ctx->h_pos, (size_t)m * 4 + 4));
+    DQ_TRY(ensure_pinned(ctx, ctx->h_len, (size_t)m * 4 + 4));
+    DQ_TRY(search_common(ctx, old_, n, nullptr, new_, m, 0, m, static_cast<int32_t *>(ctx->h_pos.p),
+                         static_cast<int32_t *>(ctx->h_len.p), false));
+    // Diff.cs:100-223 on the host
+    dq::diffhost::greedy_emit(old_, n, new_, m, static_cast<const int32_t *>(ctx->h_pos.p),
+                              static_cast<const int32_t *>(ctx->h_len.p), ctx->streams);
+    out->ctrl = ctx->streams.ctrl.data();
+    out->ctrl_len = (int64_t)ctx->streams.ctrl.size();
+    out->diff = ctx->streams.diff.data();
+    out->diff_len = (int64_t)ctx->streams.diff.size();
+    out->extra = ctx->streams.extra.data();
+    out->extra_len = (int64_t)ctx->streams.extra.size();
+    out->search_visits = ctx->streams.visits;
+    return DQ_OK;
 }
-}
+
+}  // extern "C"

@@ -1,1 +1,139 @@
-// placeholder until the search kernels land
+// dq_search_host.inl -- host orchestration of the bsdiff match search (included inside deltaq_cuda.cu's
+// anonymous namespace).
+
+namespace sr = dq::search;
+
+// LCP array + block minima of the resident (ctx->text, ctx->sa, ctx->isa) of length n
+int build_lcp(dq_ctx *ctx, uint32_t n)
+{
+    if (ctx->lcp_valid || n == 0) return DQ_OK;
+    const uint32_t chunks = (uint32_t)div_up(n, sr::kChunk), supers = (uint32_t)div_up(n, sr::kSuper);
+    const uint32_t nb1 = (uint32_t)div_up(n, sr::kBlk1), nb2 = (uint32_t)div_up(n, sr::kBlk2);
+    DQ_TRY(ensure(ctx, ctx->lcp, (size_t)n * 4));
+    DQ_TRY(ensure(ctx, ctx->min1, (size_t)nb1 * 4));
+    DQ_TRY(ensure(ctx, ctx->min2, (size_t)nb2 * 4));
+    DQ_TRY(ensure(ctx, ctx->headl, (size_t)chunks * 4));
+    const uint8_t *T = ctx->text.as<uint8_t>();
+    const int32_t *SA = ctx->sa.as<int32_t>();
+    const uint32_t *ISA = ctx->isa.as<uint32_t>();
+    {
+        auto k = sr::lcp_heads_kernel;
+        DQ_LAUNCH(k, (uint32_t)div_up(supers, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+                  ctx->headl.as<uint32_t>());
+    }
+    {
+        auto k = sr::lcp_chain_kernel;
+        DQ_LAUNCH(k, (uint32_t)div_up(chunks, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+                  ctx->headl.as<uint32_t>(), ctx->lcp.as<uint32_t>());
+    }
+    {
+        auto k = sr::block_min_kernel;
+        const uint32_t g1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(nb1, 8), (uint64_t)ctx->sm_count * 16));
+        DQ_LAUNCH(k, g1, 256, 0, ctx->stream, ctx->lcp.as<uint32_t>(), n, (uint32_t)sr::kBlk1, ctx->min1.as<uint32_t>(), nb1);
+        const uint32_t g2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(nb2, 8), (uint64_t)ctx->sm_count * 16));
+        DQ_LAUNCH(k, g2, 256, 0, ctx->stream, ctx->min1.as<uint32_t>(), nb1, (uint32_t)(sr::kBlk2 / sr::kBlk1),
+                  ctx->min2.as<uint32_t>(), nb2);
+    }
+    ctx->stats.kernel_launches += 4;
+    DQ_CK(ctx, cudaGetLastError());
+    ctx->lcp_valid = true;
+    return DQ_OK;
+}
+
+// (ctx->text, ctx->sa, ctx->isa) describe `old` (n bytes); ctx->newtext holds `new` (m bytes, padded).
+// Fills ctx->s_pos / ctx->s_len [0, count).
+int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count)
+{
+    ctx->stats.search_queries = (int32_t)count;
+    if (count == 0) return DQ_OK;
+    DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    DQ_TRY(build_lcp(ctx, n));
+    const uint32_t chunks = (uint32_t)div_up(count, sr::kChunk), supers = (uint32_t)div_up(count, sr::kSuper);
+    DQ_TRY(ensure(ctx, ctx->s_pos, (size_t)count * 4));
+    DQ_TRY(ensure(ctx, ctx->s_len, (size_t)count * 4));
+    DQ_TRY(ensure(ctx, ctx->headp, (size_t)chunks * 4));
+    DQ_TRY(ensure(ctx, ctx->headl, (size_t)std::max<uint64_t>(chunks, div_up(n, sr::kChunk)) * 4));
+    sr::Texts t{ctx->text.as<uint8_t>(), ctx->newtext.as<uint8_t>(), n, m};
+    sr::Index ix{ctx->sa.as<int32_t>(), ctx->isa.as<uint32_t>(), ctx->lcp.as<uint32_t>(), ctx->min1.as<uint32_t>(),
+                 ctx->min2.as<uint32_t>()};
+    {
+        auto k = sr::search_heads_kernel;
+        DQ_LAUNCH(k, (uint32_t)div_up(supers, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
+                  ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>());
+    }
+    {
+        auto k = sr::search_chain_kernel;
+        DQ_LAUNCH(k, (uint32_t)div_up(chunks, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
+                  ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), ctx->s_pos.as<int32_t>(),
+                  ctx->s_len.as<int32_t>());
+    }
+    ctx->stats.kernel_launches += 2;
+    DQ_CK(ctx, cudaGetLastError());
+    DQ_CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    return DQ_OK;
+}
+
+// makes (text, sa, isa) resident from a caller-supplied suffix array
+int adopt_index(dq_ctx *ctx, const uint8_t *old_, uint32_t n, const int32_t *I, cudaMemcpyKind kind)
+{
+    ctx->resident_n = -1;
+    ctx->lcp_valid = false;
+    DQ_TRY(upload_text(ctx, ctx->text, old_, n, kind));
+    DQ_TRY(ensure(ctx, ctx->sa, (size_t)n * 4));
+    DQ_TRY(ensure(ctx, ctx->isa, (size_t)n * 4));
+    if (n) {
+        DQ_CK(ctx, cudaMemcpyAsync(ctx->sa.p, I, (size_t)n * 4, kind, ctx->stream));
+        auto k = sr::invert_sa_kernel;
+        const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n, 256), (uint64_t)ctx->sm_count * 16));
+        DQ_LAUNCH(k, g, 256, 0, ctx->stream, ctx->sa.as<int32_t>(), n, ctx->isa.as<uint32_t>());
+        ctx->stats.kernel_launches++;
+        DQ_CK(ctx, cudaGetLastError());
+    }
+    ctx->resident_n = (int32_t)n;
+    return DQ_OK;
+}
+
+int ensure_pinned(dq_ctx *ctx, PinBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return DQ_OK;
+    if (b.p) {
+        DQ_CK(ctx, cudaFreeHost(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = std::max<size_t>(bytes, 4096);
+    DQ_CK(ctx, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return DQ_OK;
+}
+
+int search_common(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I, const uint8_t *new_, int32_t m,
+                  int32_t scan_begin, int32_t count, int32_t *pos_out, int32_t *len_out, bool device_ptrs)
+{
+    DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && scan_begin >= 0 && count >= 0 && (int64_t)scan_begin + count <= m,
+                      "bsdiff_search: bad lengths or scan range"));
+    DQ_TRY(check_args(ctx, (n == 0 || old_ || !I) && (m == 0 || new_) && (count == 0 || (pos_out && len_out)),
+                      "bsdiff_search: null buffer"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    const cudaMemcpyKind in = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind out = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const int32_t launches_before = ctx->stats.kernel_launches;
+    if (I) {
+        DQ_TRY(check_args(ctx, n == 0 || old_, "bsdiff_search: old is null"));
+        ctx->stats = dq_stats{};
+        DQ_TRY(adopt_index(ctx, old_, (uint32_t)n, I, in));
+    } else {
+        DQ_TRY(check_args(ctx, ctx->resident_n == n,
+                          "bsdiff_search: I is NULL but no suffix array of this length is resident on the device"));
+        ctx->stats.kernel_launches = launches_before;
+    }
+    DQ_TRY(upload_text(ctx, ctx->newtext, new_, (uint32_t)m, in));
+    DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, (uint32_t)scan_begin, (uint32_t)count));
+    if (count) {
+        DQ_CK(ctx, cudaMemcpyAsync(pos_out, ctx->s_pos.p, (size_t)count * 4, out, ctx->stream));
+        DQ_CK(ctx, cudaMemcpyAsync(len_out, ctx->s_len.p, (size_t)count * 4, out, ctx->stream));
+    }
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (count) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_ms, ctx->ev0, ctx->ev1));
+    return DQ_OK;
+}

@@ -48,7 +48,7 @@ typedef struct dq_stats {
     float   pass_ms;           /* CUDA-event time spent inside onesweep pass launches (0 unless timing on) */
     int64_t pass_pairs;        /* pairs moved by those launches (sum of per-launch counts) */
     int32_t search_queries;    /* positions answered by the last search */
-    int32_t search_long;       /* of those, answered by the long-match resolver */
+    float   search_ms;         /* CUDA-event time of the last search's device work (LCP build included when it ran) */
 } dq_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */

@@ -1,0 +1,140 @@
+"""Parity of the CUDA bsdiff match search (and the Diff.Create mirror built on it) with the oracle,
+through the C ABI.  Oracle = literal replay of Diff.Search / Diff.Create's loop (oracle/bsdiff.c)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, random_bytes
+from search_cases import small_random_pairs, structured_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sorter():
+    from deltaq_b200 import CudaSuffixSort
+    s = CudaSuffixSort()
+    yield s
+    s.dispose()
+
+
+def check_pair(sorter, old, new):
+    from deltaq_b200 import bsdiff
+    I = oracle.make_I(oracle.sais(old))
+    rp, rl = oracle.search_all(I, old, new)
+    pos, ln = bsdiff.search_all(old, new, sorter, I=I)
+    assert np.array_equal(ln, rl) and np.array_equal(pos, rp)
+    pos, ln = bsdiff.search_all(old, new, sorter)
+    assert np.array_equal(ln, rl) and np.array_equal(pos, rp)
+    if new.size > 10:
+        b, c = new.size // 3, new.size // 2
+        pos, ln = bsdiff.search_all(old, new, sorter, I=I, scan_begin=b, count=c)
+        assert np.array_equal(ln, rl[b:b + c]) and np.array_equal(pos, rp[b:b + c])
+    got = bsdiff.create_streams(old, new, sorter)
+    ref = oracle.bsdiff_streams(old, new, I)
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], k
+    assert got["search_visits"] == ref["search_calls"]
+
+
+def test_small_random_pairs(sorter):
+    for old, new in small_random_pairs(count=200):
+        check_pair(sorter, old, new)
+
+
+@pytest.mark.parametrize("name", sorted(structured_pairs()))
+def test_structured(sorter, name):
+    old, new = structured_pairs()[name]
+    check_pair(sorter, old, new)
+
+
+def test_golden_bsdiff_cases(sorter):
+    from deltaq_b200 import bsdiff
+    g = np.load(os.path.join(GOLDEN, "bsdiff_cases.npz"))
+    for k in range(int(g["count"])):
+        old, new = g[f"c{k}_old"], g[f"c{k}_new"]
+        got = bsdiff.create_streams(old, new, sorter)
+        for s in ("ctrl", "diff", "extra"):
+            assert got[s] == g[f"c{k}_{s}"].tobytes(), (k, s)
+        pos, ln = bsdiff.search_all(old, new, sorter)
+        visited = g[f"c{k}_trace_len"] >= 0
+        assert np.array_equal(pos[visited], g[f"c{k}_trace_pos"][visited])
+        assert np.array_equal(ln[visited], g[f"c{k}_trace_len"][visited])
+
+
+def test_exe_like_pair_1mib_all_positions(sorter):
+    """Every scan position of a 1 MiB exe-like pair against the literal replay (bounded: the replay is
+    quadratic inside long matches, so compare all positions of a window plus the visited positions)."""
+    from deltaq_b200 import bsdiff, workloads as w
+    old, new = w.c2_exe_pair(1 << 20, (1 << 20) + (1 << 16))
+    I = oracle.make_I(oracle.sais(old))
+    pos, ln = bsdiff.search_all(old, new, sorter, I=I)
+    ref = oracle.bsdiff_streams(old, new, I, trace=True)
+    visited = ref["trace_len"] >= 0
+    assert np.array_equal(pos[visited], ref["trace_pos"][visited])
+    assert np.array_equal(ln[visited], ref["trace_len"][visited])
+    rng = np.random.default_rng(0)
+    for b in rng.integers(0, new.size - 300, 40):
+        rp, rl = oracle.search_all(I, old, new, int(b), 300)
+        assert np.array_equal(pos[b:b + 300], rp) and np.array_equal(ln[b:b + 300], rl)
+    got = bsdiff.create_streams(old, new, sorter)
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], k
+
+
+def test_c2_full_size_streams_identical(sorter):
+    """BASELINE config #2 at full size: 16 MiB -> 17 MiB exe-like pair; the uncompressed ctrl/diff/extra
+    streams equal the oracle's, and applying them reproduces `new` (round trip, BsDiffTests.cs:30-78)."""
+    from deltaq_b200 import bsdiff, workloads as w
+    old, new = w.c2_exe_pair()
+    got = bsdiff.create_streams(old, new, sorter)
+    ref = oracle.bsdiff_streams(old, new)
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], k
+    assert got["search_visits"] == ref["search_calls"]
+    rebuilt = bsdiff.apply_streams(old, got["ctrl"], got["diff"], got["extra"], new.size)
+    assert rebuilt == new.tobytes()
+
+
+@pytest.mark.parametrize("size", [0, 1, 512, 999, 1024, 4096, 0x10000])
+def test_diff_create_roundtrip(sorter, size):
+    # BsDiffTests.cs:30-78 and BsPatchTests.cs:18-38
+    from deltaq_b200.bsdiff import Diff, Patch
+    old = random_bytes(size)
+    for new in (old.copy(), random_bytes(size + 3, seed=9)):
+        out = io.BytesIO()
+        Diff.create(old, new, out, sorter)
+        patch = out.getvalue()
+        assert patch[:8] == b"BSDIFF40"
+        rebuilt = io.BytesIO()
+        Patch.apply(old, patch, rebuilt)
+        assert rebuilt.getvalue() == new.tobytes()
+
+
+def test_diff_create_argument_validation(sorter):
+    # BsDiffTests.cs:80-100
+    from deltaq_b200.bsdiff import Diff
+    with pytest.raises(TypeError):
+        Diff.create(b"", b"", None, sorter)
+    with pytest.raises(TypeError):
+        Diff.create(b"", b"", io.BytesIO(), None)
+
+    class NotSeekable(io.BytesIO):
+        def seekable(self):
+            return False
+
+    with pytest.raises(ValueError):
+        Diff.create(b"", b"", NotSeekable(), sorter)
+
+
+def test_search_without_resident_index_is_an_error(sorter):
+    from deltaq_b200 import _native
+    old, new = random_bytes(100), random_bytes(50, seed=2)
+    sorter.sort(random_bytes(7), np.zeros(7, np.int32))     # resident index has another length
+    pos = np.zeros(50, np.int32)
+    with pytest.raises(_native.NativeError) as ei:
+        sorter.context.bsdiff_search(old, None, new, 0, 50, pos, pos.copy())
+    assert ei.value.status == _native.DQ_ERR_INVALID_ARGUMENT

@@ -1,0 +1,104 @@
+"""bsdiff match search on the CPU logic emulator (tests/emu; NOT the product) against the oracle's literal
+replay of Diff.Search (oracle/bsdiff.c) and its greedy loop."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+from search_cases import small_random_pairs, structured_pairs
+
+
+@pytest.fixture(scope="module")
+def sorter():
+    import emu
+    from deltaq_b200 import CudaSuffixSort
+    s = CudaSuffixSort(_lib=emu.library())
+    yield s
+    s.dispose()
+
+
+def check_pair(sorter, old, new, with_streams=True):
+    from deltaq_b200 import bsdiff
+    I = oracle.make_I(oracle.sais(old))
+    rp, rl = oracle.search_all(I, old, new)
+    pos, ln = bsdiff.search_all(old, new, sorter, I=I)              # caller-supplied I
+    assert np.array_equal(ln, rl) and np.array_equal(pos, rp)
+    pos, ln = bsdiff.search_all(old, new, sorter)                   # I resident from the sort
+    assert np.array_equal(ln, rl) and np.array_equal(pos, rp)
+    if new.size > 10:                                               # sub-range
+        b, c = new.size // 3, new.size // 2
+        pos, ln = bsdiff.search_all(old, new, sorter, I=I, scan_begin=b, count=c)
+        assert np.array_equal(ln, rl[b:b + c]) and np.array_equal(pos, rp[b:b + c])
+    if with_streams:
+        got = bsdiff.create_streams(old, new, sorter)
+        ref = oracle.bsdiff_streams(old, new, I)
+        for k in ("ctrl", "diff", "extra"):
+            assert got[k] == ref[k], k
+        assert got["search_visits"] == ref["search_calls"]
+
+
+def test_small_random_pairs(sorter):
+    for old, new in small_random_pairs():
+        check_pair(sorter, old, new)
+
+
+@pytest.mark.parametrize("name", sorted(structured_pairs()))
+def test_structured(sorter, name):
+    old, new = structured_pairs()[name]
+    check_pair(sorter, old, new)
+
+
+def test_golden_bsdiff_cases(sorter):
+    from deltaq_b200 import bsdiff
+    g = np.load(os.path.join(GOLDEN, "bsdiff_cases.npz"))
+    for k in range(int(g["count"])):
+        old, new = g[f"c{k}_old"], g[f"c{k}_new"]
+        got = bsdiff.create_streams(old, new, sorter)
+        for s in ("ctrl", "diff", "extra"):
+            assert got[s] == g[f"c{k}_{s}"].tobytes(), (k, s)
+        pos, ln = bsdiff.search_all(old, new, sorter)
+        visited = g[f"c{k}_trace_len"] >= 0
+        assert np.array_equal(pos[visited], g[f"c{k}_trace_pos"][visited])
+        assert np.array_equal(ln[visited], g[f"c{k}_trace_len"][visited])
+
+
+@pytest.mark.parametrize("size", [0, 1, 512, 999, 1024, 4096])
+def test_diff_create_roundtrip(sorter, size):
+    # BsDiffTests.cs:30-78: Create then Apply reproduces new
+    import io
+    from conftest import random_bytes
+    from deltaq_b200.bsdiff import Diff, Patch
+    old = random_bytes(size)
+    for new in (old.copy(), random_bytes(size + 3, seed=9)):
+        out = io.BytesIO()
+        Diff.create(old, new, out, sorter)
+        patch = out.getvalue()
+        assert patch[:8] == b"BSDIFF40"
+        rebuilt = io.BytesIO()
+        Patch.apply(old, patch, rebuilt)
+        assert rebuilt.getvalue() == new.tobytes()
+
+
+def test_diff_create_argument_validation(sorter):
+    # BsDiffTests.cs:80-100
+    import io
+    from deltaq_b200.bsdiff import Diff
+    with pytest.raises(TypeError):
+        Diff.create(b"", b"", None, sorter)
+    with pytest.raises(TypeError):
+        Diff.create(b"", b"", io.BytesIO(), None)
+
+    class NotSeekable(io.BytesIO):
+        def seekable(self):
+            return False
+
+    class NotWritable(io.BytesIO):
+        def writable(self):
+            return False
+
+    with pytest.raises(ValueError):
+        Diff.create(b"", b"", NotSeekable(), sorter)
+    with pytest.raises(ValueError):
+        Diff.create(b"", b"", NotWritable(), sorter)
