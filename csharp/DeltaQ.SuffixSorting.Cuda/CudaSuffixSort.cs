@@ -1,0 +1,118 @@
+// DeltaQ.SuffixSorting.Cuda -- ISuffixSort provider backed by libdeltaq_cuda (B200, sm_100a).
+//
+// Source only: this repository's build image has no .NET SDK, so this project is compiled wherever one
+// exists (see INTEGRATION.md).  It implements the reference's plug-in contract unchanged
+// (src/DeltaQ.SuffixSorting.Abstractions/ISuffixSort.cs:9-28) with the same argument checks as the
+// reference's own providers (LibDivSufSort.cs:21-31, SAIS.cs:25-45), and adds the one optional hook the
+// reference lacks (Diff.Search is private static, Diff.cs:267): ISuffixSearch.
+using System;
+using System.Buffers;
+using System.Runtime.InteropServices;
+
+namespace DeltaQ.SuffixSorting.Cuda;
+
+/// <summary>Optional companion of ISuffixSort: bulk evaluation of Diff.Search (Diff.cs:267-298) for every
+/// scan position. Diff.Create probes `suffixSort is ISuffixSearch` and, when present, replaces the call at
+/// Diff.cs:106 by reads of (pos[scan], len[scan]).</summary>
+public interface ISuffixSearch
+{
+    void SearchAll(ReadOnlySpan<int> I, ReadOnlySpan<byte> oldData, ReadOnlySpan<byte> newData,
+                   Span<int> pos, Span<int> len);
+}
+
+internal static unsafe partial class Native
+{
+    private const string Lib = "deltaq_cuda"; // libdeltaq_cuda.so
+
+    [LibraryImport(Lib)] internal static partial int dq_cuda_create(out IntPtr ctx, int* devices, int ndev);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_destroy(IntPtr ctx);
+    [LibraryImport(Lib)] internal static partial IntPtr dq_cuda_last_error(IntPtr ctx);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_host_alloc(out IntPtr p, nuint bytes);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_host_free(IntPtr p);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_suffix_sort(IntPtr ctx, byte* text, int n, int* saOut);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_bsdiff_search(IntPtr ctx, byte* old, int n, int* iOrNull,
+        byte* @new, int m, int scanBegin, int count, int* posOut, int* lenOut);
+
+    internal static void Check(IntPtr ctx, int status)
+    {
+        if (status == 0) return;
+        var msg = Marshal.PtrToStringUTF8(dq_cuda_last_error(ctx)) ?? "libdeltaq_cuda error";
+        throw status switch
+        {
+            -1 => new ArgumentException(msg),
+            -2 => new OutOfMemoryException(msg),
+            _ => new InvalidOperationException(msg), // -3 CUDA, -4 no device (there is no CPU fallback), -5 internal
+        };
+    }
+}
+
+/// <summary>IMemoryOwner&lt;int&gt; over cudaHostAlloc memory: the D2H copy of the suffix array lands in it
+/// directly (no staging copy).</summary>
+internal sealed unsafe class PinnedSuffixOwner : MemoryManager<int>
+{
+    private IntPtr _p;
+    private readonly int _length;
+
+    public PinnedSuffixOwner(int length)
+    {
+        _length = length;
+        Native.Check(IntPtr.Zero, Native.dq_cuda_host_alloc(out _p, (nuint)Math.Max(1, length) * sizeof(int)));
+    }
+
+    public override Span<int> GetSpan() => new((void*)_p, _length);
+    public override MemoryHandle Pin(int elementIndex = 0) => new((int*)_p + elementIndex);
+    public override void Unpin() { }
+
+    protected override void Dispose(bool disposing)
+    {
+        if (_p != IntPtr.Zero) { Native.dq_cuda_host_free(_p); _p = IntPtr.Zero; }
+    }
+}
+
+public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposable
+{
+    private IntPtr _ctx;
+    private readonly object _gate = new();
+
+    public CudaSuffixSort(int device = -1)
+    {
+        int dev = device;
+        Native.Check(IntPtr.Zero, device < 0 ? Native.dq_cuda_create(out _ctx, null, 0)
+                                             : Native.dq_cuda_create(out _ctx, &dev, 1));
+    }
+
+    public IMemoryOwner<int> Sort(ReadOnlySpan<byte> textBuffer)
+    {
+        var owner = new PinnedSuffixOwner(textBuffer.Length);
+        Sort(textBuffer, owner.GetSpan());
+        return owner;
+    }
+
+    public void Sort(ReadOnlySpan<byte> textBuffer, Span<int> suffixBuffer)
+    {
+        if (textBuffer.Length != suffixBuffer.Length)
+            throw new ArgumentException("Text and suffix buffers should have the same length");
+        lock (_gate)
+            fixed (byte* t = textBuffer)
+            fixed (int* sa = suffixBuffer)
+                Native.Check(_ctx, Native.dq_cuda_suffix_sort(_ctx, t, textBuffer.Length, sa));
+    }
+
+    public void SearchAll(ReadOnlySpan<int> I, ReadOnlySpan<byte> oldData, ReadOnlySpan<byte> newData,
+                          Span<int> pos, Span<int> len)
+    {
+        if (I.Length != oldData.Length + 1) throw new ArgumentException("I must have oldData.Length + 1 entries");
+        if (pos.Length != newData.Length || len.Length != newData.Length)
+            throw new ArgumentException("pos/len must have newData.Length entries");
+        lock (_gate)
+            fixed (int* i = I) fixed (byte* o = oldData) fixed (byte* w = newData)
+            fixed (int* p = pos) fixed (int* l = len)
+                Native.Check(_ctx, Native.dq_cuda_bsdiff_search(_ctx, o, oldData.Length, i, w, newData.Length,
+                                                                0, newData.Length, p, l));
+    }
+
+    public void Dispose()
+    {
+        if (_ctx != IntPtr.Zero) { Native.dq_cuda_destroy(_ctx); _ctx = IntPtr.Zero; }
+    }
+}

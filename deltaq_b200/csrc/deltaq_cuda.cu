@@ -57,8 +57,8 @@ struct dq_ctx {
     size_t pass_events_used = 0;
 
     // search state (device)
-    DevBuf newtext, s_pos, s_len, lcp, min1, min2, headp, headl;
-    bool lcp_valid = false;  // lcp/min1/min2 describe the resident (text, sa)
+    DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
+    bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
 
     // diff streams (host)
     dq::diffhost::Streams streams;
@@ -320,9 +320,9 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
 
 int upload_text(dq_ctx *ctx, DevBuf &buf, const uint8_t *src, uint32_t n, cudaMemcpyKind kind)
 {
-    DQ_TRY(ensure(ctx, buf, (size_t)n + 32));
+    DQ_TRY(ensure(ctx, buf, (size_t)n + 64));
     if (n) DQ_CK(ctx, cudaMemcpyAsync(buf.p, src, n, kind, ctx->stream));
-    DQ_CK(ctx, cudaMemsetAsync(buf.as<uint8_t>() + n, 0, 32, ctx->stream));
+    DQ_CK(ctx, cudaMemsetAsync(buf.as<uint8_t>() + n, 0, 64, ctx->stream));
     return DQ_OK;
 }
 
@@ -395,7 +395,7 @@ int dq_cuda_destroy(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->newtext, &ctx->s_pos,
-                      &ctx->s_len, &ctx->lcp, &ctx->min1, &ctx->min2, &ctx->headp, &ctx->headl};
+                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->pass_events) {
@@ -564,3 +564,14 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
 }
 
 }  // extern "C"
+
+#ifdef DQ_EMU
+extern "C" void dq_emu_debug_counters(unsigned long long *out, int reset)
+{
+    auto &d = dq::search::g_dbg;
+    out[0] = d.scratch; out[1] = d.probes; out[2] = d.cmp_bytes; out[3] = d.walk; out[4] = d.walk_max; out[5] = d.anchors;
+    out[6] = d.thr_max[0]; out[7] = d.thr_max[1];
+    for (int k = 0; k < 24; ++k) { out[8 + k] = d.thr_hist[0][k]; out[32 + k] = d.thr_hist[1][k]; }
+    if (reset) d = dq::search::DebugCounters{};
+}
+#endif

@@ -29,7 +29,14 @@ constexpr int kChunk = 64;              // positions per chain
 constexpr int kSuper = kChunk * kChunk; // positions per from-scratch search
 constexpr int kThreads = 128;
 constexpr uint32_t kNone = 0xffffffffu;
-constexpr int kBlk1 = 64, kBlk2 = 4096; // LCP block-minimum levels
+
+#ifdef DQ_EMU
+struct DebugCounters { unsigned long long scratch, probes, cmp_bytes, walk, walk_max, anchors, thr_max[4], thr_hist[4][24]; };
+inline DebugCounters g_dbg;
+#define DQ_DBG(x) x
+#else
+#define DQ_DBG(x)
+#endif
 
 // 8 bytes at an arbitrary address; the buffers are padded so that reading up to 15 bytes past p is safe
 __device__ __forceinline__ uint64_t load64u(const uint8_t *p)
@@ -43,20 +50,91 @@ __device__ __forceinline__ uint64_t load64u(const uint8_t *p)
     return (lo >> sh) | (hi << (64u - sh));
 }
 
-// number of equal leading bytes of a[0..la) and b[0..lb)
+// number of equal leading bytes of a[0..la) and b[0..lb).  Both buffers are readable (zero padded) for 64
+// bytes past their ends.  Short matches leave after one unaligned 8-byte step; long ones run a loop that
+// consumes 32 bytes per iteration with `a` word-aligned and `b` realigned through a carried word.
 __device__ __forceinline__ uint32_t common_prefix(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
 {
     const uint32_t lim = min(la, lb);
-    uint32_t k = 0;
-    while (k < lim) {
-        const uint64_t x = load64u(a + k) ^ load64u(b + k);
-        if (x) {
-            k += (uint32_t)(__ffsll((long long)x) - 1) >> 3;
-            return min(k, lim);
+    if (lim == 0) return 0;
+    DQ_DBG(g_dbg.cmp_bytes += 8;)
+    {
+        const uint64_t x = load64u(a) ^ load64u(b);
+        if (x) return min((uint32_t)(__ffsll((long long)x) - 1) >> 3, lim);
+        if (lim <= 8) return lim;
+    }
+    // the first 8 bytes agree: restart at the first 8-aligned byte of a (1..8 bytes in)
+    uint32_t k = 8u - (uint32_t)(reinterpret_cast<uintptr_t>(a) & 7u);
+    const uint64_t *pa = reinterpret_cast<const uint64_t *>(a + k);
+    const uintptr_t ab = reinterpret_cast<uintptr_t>(b + k);
+    const uint64_t *pb = reinterpret_cast<const uint64_t *>(ab & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(ab & 7u) * 8u;
+    if (sh == 0) {
+        while (k < lim) {
+            DQ_DBG(g_dbg.cmp_bytes += 32;)
+            const uint64_t x0 = __ldg(pa) ^ __ldg(pb), x1 = __ldg(pa + 1) ^ __ldg(pb + 1);
+            const uint64_t x2 = __ldg(pa + 2) ^ __ldg(pb + 2), x3 = __ldg(pa + 3) ^ __ldg(pb + 3);
+            if (x0 | x1 | x2 | x3) {
+                uint32_t off;
+                uint64_t x;
+                if (x0) { off = 0; x = x0; } else if (x1) { off = 8; x = x1; } else if (x2) { off = 16; x = x2; } else { off = 24; x = x3; }
+                return min(k + off + ((uint32_t)(__ffsll((long long)x) - 1) >> 3), lim);
+            }
+            k += 32;
+            pa += 4;
+            pb += 4;
         }
-        k += 8;
+    } else {
+        uint64_t carry = __ldg(pb);
+        const unsigned rs = 64u - sh;
+        while (k < lim) {
+            DQ_DBG(g_dbg.cmp_bytes += 32;)
+            const uint64_t w1 = __ldg(pb + 1), w2 = __ldg(pb + 2), w3 = __ldg(pb + 3), w4 = __ldg(pb + 4);
+            const uint64_t x0 = __ldg(pa) ^ ((carry >> sh) | (w1 << rs));
+            const uint64_t x1 = __ldg(pa + 1) ^ ((w1 >> sh) | (w2 << rs));
+            const uint64_t x2 = __ldg(pa + 2) ^ ((w2 >> sh) | (w3 << rs));
+            const uint64_t x3 = __ldg(pa + 3) ^ ((w3 >> sh) | (w4 << rs));
+            if (x0 | x1 | x2 | x3) {
+                uint32_t off;
+                uint64_t x;
+                if (x0) { off = 0; x = x0; } else if (x1) { off = 8; x = x1; } else if (x2) { off = 16; x = x2; } else { off = 24; x = x3; }
+                return min(k + off + ((uint32_t)(__ffsll((long long)x) - 1) >> 3), lim);
+            }
+            carry = w4;
+            k += 32;
+            pa += 4;
+            pb += 4;
+        }
     }
     return lim;
+}
+
+// warp-cooperative version: all 32 lanes call it with the same arguments and get the same result; each
+// step compares 256 bytes (lane l takes the 8 bytes at k + 8l)
+__device__ __forceinline__ uint32_t common_prefix_warp(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
+{
+    const uint32_t lim = min(la, lb);
+    const uint32_t lane = lane_id();
+    for (uint32_t k = 0; k < lim; k += 256) {
+        const uint32_t off = k + lane * 8u;
+        uint64_t x = 0;
+        if (off < lim) x = load64u(a + off) ^ load64u(b + off);
+        DQ_DBG(g_dbg.cmp_bytes += 8;)
+        const unsigned m = __ballot_sync(kFullMask, x != 0);
+        if (m) {
+            const int first = __ffs((int)m) - 1;
+            const uint64_t xx = __shfl_sync(kFullMask, x, first);
+            return min(k + (uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
+        }
+    }
+    return lim;
+}
+
+template <bool WARP>
+__device__ __forceinline__ uint32_t common_prefix_t(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
+{
+    if (WARP) return common_prefix_warp(a, la, b, lb);
+    return common_prefix(a, la, b, lb);
 }
 
 struct Texts {
@@ -67,10 +145,11 @@ struct Texts {
 
 // lcp of old suffix p with the query at j, given that the first `known` bytes agree; *less = (suffix < query)
 // under Span.SequenceCompareTo: first differing byte, else the shorter one is smaller.
+template <bool WARP = false>
 __device__ __forceinline__ uint32_t match_from(const Texts &t, uint32_t p, uint32_t j, uint32_t known, bool *less)
 {
     const uint32_t la = t.n - p, lq = t.m - j;
-    const uint32_t c = known + common_prefix(t.old_ + p + known, la - known, t.new_ + j + known, lq - known);
+    const uint32_t c = known + common_prefix_t<WARP>(t.old_ + p + known, la - known, t.new_ + j + known, lq - known);
     if (c == la)
         *less = c < lq;
     else if (c == lq)
@@ -80,12 +159,18 @@ __device__ __forceinline__ uint32_t match_from(const Texts &t, uint32_t p, uint3
     return c;
 }
 
+constexpr int kMaxLevels = 6;  // 64^5 > 2^30: enough block-minimum levels for any int32-sized input
+
 struct Index {
     const int32_t *SA;    // n
     const uint32_t *ISA;  // n
-    const uint32_t *LCP;  // n, LCP[0] = 0
-    const uint32_t *min1; // ceil(n/64)   block minima of LCP
-    const uint32_t *min2; // ceil(n/4096)
+    // lv[0] = LCP (n entries, LCP[0] = 0); lv[k] = minima of lv[k-1] over blocks of 64 (size[k] entries)
+    const uint32_t *lv[kMaxLevels];
+    uint32_t size[kMaxLevels];
+    int top;              // highest level in use
+    // 2-byte prefix buckets: ranks [bkt_lo[k], bkt_hi[k]) hold exactly the suffixes (>= 2 bytes long) that
+    // start with the byte pair k
+    const uint32_t *bkt_lo, *bkt_hi;
 };
 
 struct Bracket {
@@ -94,82 +179,166 @@ struct Bracket {
     uint32_t y;  // lcp(query, suffix SA[L])     (valid when L < n)
 };
 
-// binary search from scratch, with Manber-Myers skipping of the bytes both ends are known to share
+// binary search from scratch, with Manber-Myers skipping of the bytes both ends are known to share.  The
+// first two query bytes select a bucket of the suffix array, so ~16 of the ~log2(n) probes are a table read.
+template <bool WARP = false>
 __device__ __forceinline__ Bracket locate_scratch(const Texts &t, const Index &ix, uint32_t j)
 {
-    int64_t lo = -1, hi = t.n;
+    DQ_DBG(g_dbg.scratch++;)
+    const uint32_t n = t.n;
+    int64_t lo = -1, hi = n;
     uint32_t llo = 0, lhi = 0;
+    bool lo_virtual = true, hi_virtual = true;  // bounds not yet compared with the query
+    if (t.m - j >= 2) {
+        const uint32_t k = ((uint32_t)t.new_[j] << 8) | t.new_[j + 1];
+        lo = (int64_t)ix.bkt_lo[k] - 1;
+        hi = ix.bkt_hi[k];
+        llo = lhi = 2;  // every suffix strictly inside shares the byte pair
+    } else {
+        lo_virtual = hi_virtual = false;
+    }
     while (hi - lo > 1) {
+        DQ_DBG(g_dbg.probes++;)
         const uint32_t mid = (uint32_t)((lo + hi) >> 1);
         bool less;
-        const uint32_t c = match_from(t, (uint32_t)ix.SA[mid], j, min(llo, lhi), &less);
+        const uint32_t c = match_from<WARP>(t, (uint32_t)ix.SA[mid], j, min(llo, lhi), &less);
         if (less) {
             lo = mid;
             llo = c;
+            lo_virtual = false;
         } else {
             hi = mid;
             lhi = c;
+            hi_virtual = false;
         }
     }
+    // bucket bounds were never compared: their true lcp with the query is 0 or 1 byte
+    bool dummy;
+    if (lo_virtual) llo = lo >= 0 ? match_from<WARP>(t, (uint32_t)ix.SA[lo], j, 0, &dummy) : 0u;
+    if (hi_virtual) lhi = hi < (int64_t)n ? match_from<WARP>(t, (uint32_t)ix.SA[hi], j, 0, &dummy) : 0u;
     return Bracket{(uint32_t)hi, llo, lhi};
 }
 
-// anchor: rank r whose suffix shares exactly c bytes with the query and is (less ? < : >=) the query
+// first u >= u0 with LCP[u] < c, or n: climbs the block-minimum hierarchy, at most 63 steps per level
+__device__ __forceinline__ uint32_t next_smaller(const Index &ix, uint32_t u0, uint32_t c)
+{
+    int l = 0;
+    uint32_t idx = u0;
+    for (;;) {
+        DQ_DBG(g_dbg.walk++;)
+        if (idx >= ix.size[l]) return ix.size[0];
+        if ((idx & 63u) == 0 && l < ix.top) {  // block aligned: the block starting here, one level up
+            idx >>= 6;
+            ++l;
+            continue;
+        }
+        if (ix.lv[l][idx] < c) break;
+        ++idx;
+    }
+    while (l > 0) {
+        --l;
+        idx <<= 6;
+        const uint32_t *A = ix.lv[l];
+        while (A[idx] >= c) {
+            DQ_DBG(g_dbg.walk++;)
+            ++idx;
+        }
+    }
+    return idx;
+}
+
+// last u <= u0 with LCP[u] < c (c > 0, so u = 0 always qualifies)
+__device__ __forceinline__ uint32_t prev_smaller(const Index &ix, uint32_t u0, uint32_t c)
+{
+    int l = 0;
+    uint32_t idx = u0;
+    for (;;) {
+        const uint32_t *A = ix.lv[l];
+        bool found = false;
+        for (;;) {
+            DQ_DBG(g_dbg.walk++;)
+            if (A[idx] < c) {
+                found = true;
+                break;
+            }
+            if ((idx & 63u) == 0 && l < ix.top) break;
+            --idx;  // cannot underflow: entry 0 of every level is 0 < c
+        }
+        if (found) break;
+        idx = (idx >> 6) - 1;  // the block before this one, one level up
+        ++l;
+    }
+    while (l > 0) {
+        --l;
+        idx = min(idx * 64u + 63u, ix.size[l] - 1u);
+        const uint32_t *A = ix.lv[l];
+        while (A[idx] >= c) {
+            DQ_DBG(g_dbg.walk++;)
+            --idx;
+        }
+    }
+    return idx;
+}
+
+constexpr uint32_t kMinAnchor = 3;  // anchors sharing fewer bytes name intervals so wide that scratch is cheaper
+
+// anchor: rank r whose suffix shares exactly c bytes with the query and is (less ? < : >=) the query.
+// All suffixes sharing >= c bytes with suffix r form one contiguous rank interval (delimited by LCP < c);
+// the query sorts inside it, so L is found by a binary search over that interval only, every probe
+// starting at byte c.
+template <bool WARP = false>
 __device__ __forceinline__ Bracket locate_anchor(const Texts &t, const Index &ix, uint32_t j, uint32_t r, uint32_t c,
                                                  bool less)
 {
     const uint32_t n = t.n;
+    const uint32_t *LCP = ix.lv[0];
+    DQ_DBG(g_dbg.anchors++;)
+    if (c < kMinAnchor) return locate_scratch<WARP>(t, ix, j);
     if (less) {
-        uint32_t lo = r, llo = c, u = r + 1;
-        for (;;) {
-            if (u >= n) return Bracket{n, llo, 0};
-            if ((u & (kBlk2 - 1)) == 0 && u + kBlk2 <= n && ix.min2[u / kBlk2] > llo) {
-                lo = u + kBlk2 - 1;
-                u += kBlk2;
-                continue;
-            }
-            if ((u & (kBlk1 - 1)) == 0 && u + kBlk1 <= n && ix.min1[u / kBlk1] > llo) {
-                lo = u + kBlk1 - 1;
-                u += kBlk1;
-                continue;
-            }
-            const uint32_t g = ix.LCP[u];
-            if (g > llo) {
-                lo = u++;
-                continue;
-            }
-            if (g < llo) return Bracket{u, llo, g};
+        if (r + 1 >= n) return Bracket{n, c, 0};
+        const uint32_t g = LCP[r + 1];
+        if (g < c) return Bracket{r + 1, c, g};
+        const uint32_t e = next_smaller(ix, r + 1, c);  // interval is [.., e)
+        uint32_t lo = r, hi = e, llo = c, lhi = c;
+        bool boundary = true;
+        while (hi - lo > 1) {
+            DQ_DBG(g_dbg.probes++;)
+            const uint32_t mid = lo + ((hi - lo) >> 1);
             bool ls;
-            const uint32_t cc = match_from(t, (uint32_t)ix.SA[u], j, llo, &ls);
-            if (!ls) return Bracket{u, llo, cc};
-            lo = u++;
-            llo = cc;
+            const uint32_t cc = match_from<WARP>(t, (uint32_t)ix.SA[mid], j, min(llo, lhi), &ls);
+            if (ls) {
+                lo = mid;
+                llo = cc;
+            } else {
+                hi = mid;
+                lhi = cc;
+                boundary = false;
+            }
         }
+        return Bracket{hi, llo, boundary ? (e < n ? LCP[e] : 0u) : lhi};
     } else {
-        uint32_t hi = r, lhi = c;
-        for (;;) {
-            if (hi == 0) return Bracket{0, 0, lhi};
-            // LCP[hi-k+1 .. hi] all > lhi  =>  suffixes hi-k .. hi-1 are >= query with the same lcp
-            if ((hi & (kBlk2 - 1)) == kBlk2 - 1 && ix.min2[hi / kBlk2] > lhi) {
-                hi -= kBlk2;
-                continue;
-            }
-            if ((hi & (kBlk1 - 1)) == kBlk1 - 1 && ix.min1[hi / kBlk1] > lhi) {
-                hi -= kBlk1;
-                continue;
-            }
-            const uint32_t g = ix.LCP[hi];
-            if (g > lhi) {
-                --hi;
-                continue;
-            }
-            if (g < lhi) return Bracket{hi, g, lhi};
+        if (r == 0) return Bracket{0, 0, c};
+        const uint32_t g = LCP[r];
+        if (g < c) return Bracket{r, g, c};
+        const uint32_t s = prev_smaller(ix, r, c);  // interval is [s, ..]; suffix s-1 (if any) is < query
+        int64_t lo = (int64_t)s - 1, hi = r;
+        uint32_t llo = c, lhi = c;
+        bool boundary = true;
+        while (hi - lo > 1) {
+            DQ_DBG(g_dbg.probes++;)
+            const uint32_t mid = (uint32_t)(lo + ((hi - lo) >> 1));
             bool ls;
-            const uint32_t cc = match_from(t, (uint32_t)ix.SA[hi - 1], j, lhi, &ls);
-            if (ls) return Bracket{hi, cc, lhi};
-            --hi;
-            lhi = cc;
+            const uint32_t cc = match_from<WARP>(t, (uint32_t)ix.SA[mid], j, min(llo, lhi), &ls);
+            if (ls) {
+                lo = mid;
+                llo = cc;
+                boundary = false;
+            } else {
+                hi = mid;
+                lhi = cc;
+            }
         }
+        return Bracket{(uint32_t)hi, boundary ? LCP[s] : llo, lhi};
     }
 }
 
@@ -179,11 +348,12 @@ struct Carry {
     bool less;
 };
 
+template <bool WARP = false>
 __device__ __forceinline__ Bracket locate_step(const Texts &t, const Index &ix, uint32_t j, const Carry &cy,
                                                uint32_t stride, bool have)
 {
-    if (have && cy.l > stride) return locate_anchor(t, ix, j, ix.ISA[cy.p + stride], cy.l - stride, cy.less);
-    return locate_scratch(t, ix, j);
+    if (have && cy.l > stride) return locate_anchor<WARP>(t, ix, j, ix.ISA[cy.p + stride], cy.l - stride, cy.less);
+    return locate_scratch<WARP>(t, ix, j);
 }
 
 __device__ __forceinline__ Carry carry_of(const Texts &t, const Index &ix, const Bracket &b)
@@ -213,7 +383,7 @@ __device__ __forceinline__ void reference_result(const Texts &t, const Index &ix
             y = x;
         } else {
             pe = (uint32_t)ix.SA[1];
-            const uint32_t g = ix.LCP[1];
+            const uint32_t g = ix.lv[0][1];
             if (g < x)
                 y = g;
             else if (g > x)
@@ -253,13 +423,40 @@ __global__ void __launch_bounds__(256) invert_sa_kernel(const int32_t *__restric
         ISA[SA[r]] = (uint32_t)r;
 }
 
-// LCP array, level A: one thread per kSuper text positions walks the chunk heads with stride kChunk.
+// 2-byte bucket bounds of the suffix array.  Suffix p has the 17-bit key 2*pair+1 (pair = T[p]<<8 | T[p+1]),
+// the one-byte suffix n-1 has 2*(T[n-1]<<8), which puts it in front of its bucket and outside [lo, hi).
+// One thread per pair k: lo[k] = #{key < 2k+1}, hi[k] = #{key < 2k+2}, by binary search over SA.
+__global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint8_t *__restrict__ T, uint32_t n,
+                                                             const int32_t *__restrict__ SA,
+                                                             uint32_t *__restrict__ bkt_lo, uint32_t *__restrict__ bkt_hi)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 65536u) return;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const uint32_t target = 2u * k + 1u + (uint32_t)which;
+        uint32_t lo = 0, hi = n;  // first rank whose key >= target
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            const uint32_t p = (uint32_t)SA[mid];
+            const uint32_t key = (p + 1 < n) ? 2u * (((uint32_t)T[p] << 8) | T[p + 1]) + 1u : 2u * ((uint32_t)T[p] << 8);
+            if (key < target)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        (which ? bkt_hi : bkt_lo)[k] = lo;
+    }
+}
+
+// LCP array, level A: one WARP per kSuper text positions walks the chunk heads with stride kChunk; the byte
+// comparisons are warp-cooperative (a head inside a long repeat costs length/256 steps, not length/8).
 // head_l[i / kChunk] = PLCP[i] for i % kChunk == 0.
 __global__ void __launch_bounds__(kThreads)
 lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
                  const uint32_t *__restrict__ ISA, uint32_t *__restrict__ head_l)
 {
-    const uint64_t sc = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t sc = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t i0 = sc * kSuper;
     if (i0 >= n) return;
     uint32_t l = 0;
@@ -273,9 +470,9 @@ lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
         } else {
             const uint32_t q = (uint32_t)SA[r - 1];
             const uint32_t known = l > (uint32_t)kChunk ? l - kChunk : 0;
-            l = known + common_prefix(T + i + known, n - i - known, T + q + known, n - q - known);
+            l = known + common_prefix_warp(T + i + known, n - i - known, T + q + known, n - q - known);
         }
-        head_l[i / kChunk] = l;
+        if (lane_id() == 0) head_l[i / kChunk] = l;
     }
 }
 
@@ -287,6 +484,8 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t i0 = c * kChunk;
     if (i0 >= n) return;
+    DQ_DBG(unsigned long long b0 = g_dbg.cmp_bytes;)
+    DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes - b0; g_dbg.thr_max[0] = max(g_dbg.thr_max[0], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[0][k]++; } } fin{b0};)
     uint32_t l = head_l[c];
     LCP[ISA[i0]] = l;
     for (int k = 1; k < kChunk; ++k) {
@@ -321,13 +520,14 @@ __global__ void __launch_bounds__(256) block_min_kernel(const uint32_t *__restri
     }
 }
 
-// search, level A: chunk heads of [scan_begin, scan_begin+count), one thread per kSuper positions.
-// head_p / head_l hold the carry of each head (bit 31 of head_l = less).
+// search, level A: chunk heads of [scan_begin, scan_begin+count), one WARP per kSuper positions (uniform
+// control flow, warp-cooperative byte comparisons).  head_p / head_l hold the carry of each head (bit 31 of
+// head_l = less).
 __global__ void __launch_bounds__(kThreads)
 search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint32_t *__restrict__ head_p,
                     uint32_t *__restrict__ head_l)
 {
-    const uint64_t sc = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t sc = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t k0 = sc * kSuper;
     if (k0 >= count || t.n == 0) return;
     Carry cy{0, 0, false};
@@ -336,11 +536,13 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
         const uint64_t kk = k0 + (uint64_t)k * kChunk;
         if (kk >= count) break;
         const uint32_t j = scan_begin + (uint32_t)kk;
-        const Bracket b = locate_step(t, ix, j, cy, kChunk, have);
+        const Bracket b = locate_step<true>(t, ix, j, cy, kChunk, have);
         cy = carry_of(t, ix, b);
         have = true;
-        head_p[kk / kChunk] = cy.p;
-        head_l[kk / kChunk] = cy.l | (cy.less ? 0x80000000u : 0u);
+        if (lane_id() == 0) {
+            head_p[kk / kChunk] = cy.p;
+            head_l[kk / kChunk] = cy.l | (cy.less ? 0x80000000u : 0u);
+        }
     }
 }
 
@@ -352,6 +554,8 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t k0 = c * kChunk;
     if (k0 >= count) return;
+    DQ_DBG(unsigned long long b0 = g_dbg.cmp_bytes + 64 * g_dbg.probes;)
+    DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes + 64 * g_dbg.probes - b0; g_dbg.thr_max[1] = max(g_dbg.thr_max[1], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[1][k]++; } } fin{b0};)
     if (t.n == 0) {
         for (int k = 0; k < kChunk && k0 + k < count; ++k) {
             pos_out[k0 + k] = 0;

@@ -3,22 +3,36 @@
 
 namespace sr = dq::search;
 
+// level sizes of the block-minimum hierarchy over an n-entry LCP array
+int lcp_levels(uint32_t n, uint32_t size[sr::kMaxLevels])
+{
+    int top = 0;
+    size[0] = n;
+    while (size[top] > 64 && top + 1 < sr::kMaxLevels) {
+        size[top + 1] = (uint32_t)div_up(size[top], 64);
+        ++top;
+    }
+    for (int l = top + 1; l < sr::kMaxLevels; ++l) size[l] = 0;
+    return top;
+}
+
 // LCP array + block minima of the resident (ctx->text, ctx->sa, ctx->isa) of length n
 int build_lcp(dq_ctx *ctx, uint32_t n)
 {
     if (ctx->lcp_valid || n == 0) return DQ_OK;
     const uint32_t chunks = (uint32_t)div_up(n, sr::kChunk), supers = (uint32_t)div_up(n, sr::kSuper);
-    const uint32_t nb1 = (uint32_t)div_up(n, sr::kBlk1), nb2 = (uint32_t)div_up(n, sr::kBlk2);
-    DQ_TRY(ensure(ctx, ctx->lcp, (size_t)n * 4));
-    DQ_TRY(ensure(ctx, ctx->min1, (size_t)nb1 * 4));
-    DQ_TRY(ensure(ctx, ctx->min2, (size_t)nb2 * 4));
+    uint32_t size[sr::kMaxLevels];
+    const int top = lcp_levels(n, size);
+    size_t total = 0;
+    for (int l = 0; l <= top; ++l) total += ((size_t)size[l] + 63) & ~(size_t)63;
+    DQ_TRY(ensure(ctx, ctx->lcp, total * 4));
     DQ_TRY(ensure(ctx, ctx->headl, (size_t)chunks * 4));
     const uint8_t *T = ctx->text.as<uint8_t>();
     const int32_t *SA = ctx->sa.as<int32_t>();
     const uint32_t *ISA = ctx->isa.as<uint32_t>();
     {
         auto k = sr::lcp_heads_kernel;
-        DQ_LAUNCH(k, (uint32_t)div_up(supers, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+        DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
                   ctx->headl.as<uint32_t>());
     }
     {
@@ -27,14 +41,20 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
                   ctx->headl.as<uint32_t>(), ctx->lcp.as<uint32_t>());
     }
     {
-        auto k = sr::block_min_kernel;
-        const uint32_t g1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(nb1, 8), (uint64_t)ctx->sm_count * 16));
-        DQ_LAUNCH(k, g1, 256, 0, ctx->stream, ctx->lcp.as<uint32_t>(), n, (uint32_t)sr::kBlk1, ctx->min1.as<uint32_t>(), nb1);
-        const uint32_t g2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(nb2, 8), (uint64_t)ctx->sm_count * 16));
-        DQ_LAUNCH(k, g2, 256, 0, ctx->stream, ctx->min1.as<uint32_t>(), nb1, (uint32_t)(sr::kBlk2 / sr::kBlk1),
-                  ctx->min2.as<uint32_t>(), nb2);
+        DQ_TRY(ensure(ctx, ctx->bkt, (size_t)2 * 65536 * 4));
+        auto k = sr::bucket_bounds_kernel;
+        DQ_LAUNCH(k, 256, 256, 0, ctx->stream, T, n, SA, ctx->bkt.as<uint32_t>(), ctx->bkt.as<uint32_t>() + 65536);
     }
-    ctx->stats.kernel_launches += 4;
+    ctx->stats.kernel_launches += 3;
+    uint32_t *lv = ctx->lcp.as<uint32_t>();
+    for (int l = 1; l <= top; ++l) {
+        uint32_t *nxt = lv + (((size_t)size[l - 1] + 63) & ~(size_t)63);
+        auto k = sr::block_min_kernel;
+        const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(size[l], 8), (uint64_t)ctx->sm_count * 16));
+        DQ_LAUNCH(k, g, 256, 0, ctx->stream, lv, size[l - 1], 64u, nxt, size[l]);
+        ctx->stats.kernel_launches++;
+        lv = nxt;
+    }
     DQ_CK(ctx, cudaGetLastError());
     ctx->lcp_valid = true;
     return DQ_OK;
@@ -54,12 +74,23 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
     DQ_TRY(ensure(ctx, ctx->headp, (size_t)chunks * 4));
     DQ_TRY(ensure(ctx, ctx->headl, (size_t)std::max<uint64_t>(chunks, div_up(n, sr::kChunk)) * 4));
     sr::Texts t{ctx->text.as<uint8_t>(), ctx->newtext.as<uint8_t>(), n, m};
-    sr::Index ix{ctx->sa.as<int32_t>(), ctx->isa.as<uint32_t>(), ctx->lcp.as<uint32_t>(), ctx->min1.as<uint32_t>(),
-                 ctx->min2.as<uint32_t>()};
+    sr::Index ix{};
+    ix.SA = ctx->sa.as<int32_t>();
+    ix.ISA = ctx->isa.as<uint32_t>();
+    ix.top = lcp_levels(n, ix.size);
+    ix.bkt_lo = ctx->bkt.as<uint32_t>();
+    ix.bkt_hi = ctx->bkt.as<uint32_t>() + 65536;
+    {
+        const uint32_t *lv = ctx->lcp.as<uint32_t>();
+        for (int l = 0; l <= ix.top; ++l) {
+            ix.lv[l] = lv;
+            lv += ((size_t)ix.size[l] + 63) & ~(size_t)63;
+        }
+    }
     {
         auto k = sr::search_heads_kernel;
-        DQ_LAUNCH(k, (uint32_t)div_up(supers, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
-                  ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>());
+        DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin,
+                  count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>());
     }
     {
         auto k = sr::search_chain_kernel;
