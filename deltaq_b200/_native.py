@@ -47,7 +47,7 @@ class NativeError(RuntimeError):
 EXPORTS = [
     "dq_cuda_create", "dq_cuda_destroy", "dq_cuda_last_error", "dq_cuda_get_stats", "dq_cuda_set_timing",
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
-    "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams",
+    "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
     "dq_cuda_radix_sort_pairs",
 ]
 
@@ -76,6 +76,7 @@ class Library:
         L.dq_cuda_bsdiff_search.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
         L.dq_cuda_bsdiff_search_device.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
         L.dq_cuda_bsdiff_streams.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(DqDiffStreams)]
+        L.dq_cuda_greedy_emit.argtypes = [vp, vp, i32, vp, i32, vp, vp, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
         for name in EXPORTS:
             if name != "dq_cuda_last_error":
@@ -188,10 +189,20 @@ class Context:
         self._check(self.lib.L.dq_cuda_bsdiff_search(self._h, _addr(old), old.size, _addr(I), _addr(new), new.size,
                                                      scan_begin, count, _addr(pos_out), _addr(len_out)))
 
+    def greedy_emit(self, old, new, pos, ln):
+        out = DqDiffStreams()
+        self._check(self.lib.L.dq_cuda_greedy_emit(self._h, _addr(old), old.size, _addr(new), new.size,
+                                                   _addr(pos), _addr(ln), ctypes.byref(out)))
+        return self._streams(out)
+
     def bsdiff_streams(self, old, new):
         out = DqDiffStreams()
         self._check(self.lib.L.dq_cuda_bsdiff_streams(self._h, _addr(old), old.size, _addr(new), new.size,
                                                       ctypes.byref(out)))
+        return self._streams(out)
+
+    @staticmethod
+    def _streams(out):
         return {
             "ctrl": ctypes.string_at(out.ctrl, out.ctrl_len) if out.ctrl_len else b"",
             "diff": ctypes.string_at(out.diff, out.diff_len) if out.diff_len else b"",

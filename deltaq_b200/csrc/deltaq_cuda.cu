@@ -337,6 +337,8 @@ int check_args(dq_ctx *ctx, bool ok, const char *what)
 
 #include "dq_search_host.inl"
 
+void export_streams(dq_ctx *ctx, dq_diff_streams *out);
+
 }  // namespace
 
 // ======================================================================================================
@@ -553,6 +555,27 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     // Diff.cs:100-223 on the host
     dq::diffhost::greedy_emit(old_, n, new_, m, static_cast<const int32_t *>(ctx->h_pos.p),
                               static_cast<const int32_t *>(ctx->h_len.p), ctx->streams);
+    export_streams(ctx, out);
+    return DQ_OK;
+}
+
+int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
+                        const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out)
+{
+    if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || (new_ && pos_tab && len_tab)),
+                      "greedy_emit: bad arguments"));
+    dq::diffhost::greedy_emit(old_, n, new_, m, pos_tab, len_tab, ctx->streams);
+    export_streams(ctx, out);
+    return DQ_OK;
+}
+
+}  // extern "C"
+
+namespace {
+void export_streams(dq_ctx *ctx, dq_diff_streams *out)
+{
     out->ctrl = ctx->streams.ctrl.data();
     out->ctrl_len = (int64_t)ctx->streams.ctrl.size();
     out->diff = ctx->streams.diff.data();
@@ -560,10 +583,8 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     out->extra = ctx->streams.extra.data();
     out->extra_len = (int64_t)ctx->streams.extra.size();
     out->search_visits = ctx->streams.visits;
-    return DQ_OK;
 }
-
-}  // extern "C"
+}  // namespace
 
 #ifdef DQ_EMU
 extern "C" void dq_emu_debug_counters(unsigned long long *out, int reset)

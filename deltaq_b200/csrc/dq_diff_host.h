@@ -3,9 +3,18 @@
 //     len = Search(I, oldData, newData[scan..], 0, oldData.Length, out pos);          (Diff.cs:106)
 // is the array read  len = len_tab[scan]; pos = pos_tab[scan];  -- the hook SURVEY.md section 8(b) describes.
 // Emits the three UNCOMPRESSED streams (ctrl triples as packed longs, SpanExtensions.cs:7-30).
+//
+// Same statements, faster stepping: the byte-at-a-time loops of the reference are advanced 32 bytes at a time
+// wherever a whole block behaves uniformly (all bytes equal, or the bound check cannot fire), which leaves
+// every variable exactly as the reference's loop would (proofs at each site); anything else falls back to the
+// reference's own single-byte step.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace dq {
 namespace diffhost {
@@ -14,6 +23,31 @@ struct Streams {
     std::vector<uint8_t> ctrl, diff, extra;
     int64_t visits = 0;
 };
+
+// bit k of the result is set iff a[k] == b[k], k in [0, 32)
+inline uint32_t eq_mask32(const uint8_t *a, const uint8_t *b)
+{
+#if defined(__SSE2__)
+    const __m128i a0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a));
+    const __m128i b0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(b));
+    const __m128i a1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + 16));
+    const __m128i b1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(b + 16));
+    return (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a0, b0)) |
+           ((uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a1, b1)) << 16);
+#else
+    uint32_t m = 0;
+    for (int k = 0; k < 32; ++k) m |= (uint32_t)(a[k] == b[k]) << k;
+    return m;
+#endif
+}
+
+inline int32_t count_equal(const uint8_t *a, const uint8_t *b, int32_t len)
+{
+    int32_t cnt = 0, k = 0;
+    for (; k + 32 <= len; k += 32) cnt += __builtin_popcount(eq_mask32(a + k, b + k));
+    for (; k < len; ++k) cnt += (a[k] == b[k]);
+    return cnt;
+}
 
 inline void put_packed_long(std::vector<uint8_t> &out, int64_t y)
 {
@@ -44,8 +78,15 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
             pos = pos_tab[scan];
             out.visits++;
 
-            for (; scsc < scan + len; scsc++)
-                if ((scsc + lastoffset < oldLen) && (oldData[scsc + lastoffset] == newData[scsc])) oldscore++;
+            {
+                // Diff.cs:108-114.  scsc + lastoffset >= lastpos >= 0, so only the upper bound can fire: count
+                // equal bytes over the part of [scsc, scan+len) that stays inside oldData.
+                const int64_t lim = (int64_t)oldLen - lastoffset;  // scsc < lim  <=>  scsc + lastoffset < oldLen
+                const int32_t stop = scan + len;
+                const int32_t inb = (int32_t)(lim < stop ? (lim > scsc ? lim : scsc) : stop);
+                if (inb > scsc) oldscore += count_equal(oldData + lastoffset + scsc, newData + scsc, inb - scsc);
+                if (scsc < stop) scsc = stop;
+            }
 
             if ((len == oldscore && len != 0) || (len > oldscore + 8)) break;
 
@@ -54,12 +95,45 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
 
         if (len != oldscore || scan == newLen) {
             int32_t s = 0, sf = 0, lenf = 0;
-            for (int32_t i = 0; (lastscan + i < scan) && (lastpos + i < oldLen);) {
-                if (oldData[lastpos + i] == newData[lastscan + i]) s++;
-                i++;
-                if (s * 2 - i > sf * 2 - lenf) {
-                    sf = s;
-                    lenf = i;
+            {
+                // Diff.cs:132-145.  Over a block whose bytes all match, s*2-i rises by one per byte, so if it
+                // ends above the running best the last byte of the block is the (strictly improving) final
+                // update, and if not there is no update at all: one step does the whole block.
+                const int32_t span = (scan - lastscan) < (oldLen - lastpos) ? (scan - lastscan) : (oldLen - lastpos);
+                const uint8_t *po = oldData + lastpos, *pn = newData + lastscan;
+                int32_t i = 0;
+                while (i < span) {
+                    if (i + 32 <= span) {
+                        const uint32_t eq = eq_mask32(po + i, pn + i);
+                        if (eq == 0xffffffffu) {
+                            s += 32;
+                            i += 32;
+                            if (s * 2 - i > sf * 2 - lenf) {
+                                sf = s;
+                                lenf = i;
+                            }
+                            continue;
+                        }
+                        if (eq == 0) {  // the score only falls over this block: no update can happen
+                            i += 32;
+                            continue;
+                        }
+                        for (int k = 0; k < 32; ++k) {
+                            s += (int32_t)((eq >> k) & 1u);
+                            i++;
+                            if (s * 2 - i > sf * 2 - lenf) {
+                                sf = s;
+                                lenf = i;
+                            }
+                        }
+                        continue;
+                    }
+                    if (po[i] == pn[i]) s++;
+                    i++;
+                    if (s * 2 - i > sf * 2 - lenf) {
+                        sf = s;
+                        lenf = i;
+                    }
                 }
             }
 
@@ -67,12 +141,43 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
             if (scan < newLen) {
                 s = 0;
                 int32_t sb = 0;
-                for (int32_t i = 1; (scan >= lastscan + i) && (pos >= i); i++) {
+                // Diff.cs:152-164, same block argument as the forward loop (walking backwards)
+                const int32_t span = (scan - lastscan) < pos ? (scan - lastscan) : pos;
+                int32_t i = 1;
+                while (i <= span) {
+                    if (i + 31 <= span) {
+                        // bit k <-> step i + 31 - k (the block is read forwards, the loop walks backwards)
+                        const uint32_t eq = eq_mask32(oldData + pos - i - 31, newData + scan - i - 31);
+                        if (eq == 0xffffffffu) {
+                            s += 32;
+                            i += 31;
+                            if (s * 2 - i > sb * 2 - lenb) {
+                                sb = s;
+                                lenb = i;
+                            }
+                            i++;
+                            continue;
+                        }
+                        if (eq == 0) {
+                            i += 32;
+                            continue;
+                        }
+                        for (int k = 31; k >= 0; --k) {
+                            s += (int32_t)((eq >> k) & 1u);
+                            if (s * 2 - i > sb * 2 - lenb) {
+                                sb = s;
+                                lenb = i;
+                            }
+                            i++;
+                        }
+                        continue;
+                    }
                     if (oldData[pos - i] == newData[scan - i]) s++;
                     if (s * 2 - i > sb * 2 - lenb) {
                         sb = s;
                         lenb = i;
                     }
+                    i++;
                 }
             }
 
@@ -92,7 +197,21 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
                 lenb -= lens;
             }
 
-            for (int32_t i = 0; i < lenf; i++) out.diff.push_back((uint8_t)(newData[lastscan + i] - oldData[lastpos + i]));
+            {
+                // Diff.cs:197-200
+                const size_t at = out.diff.size();
+                out.diff.resize(at + (size_t)(lenf > 0 ? lenf : 0));
+                uint8_t *dst = out.diff.data() + at;
+                const uint8_t *pn = newData + lastscan, *po = oldData + lastpos;
+                int32_t i = 0;
+#if defined(__SSE2__)
+                for (; i + 16 <= lenf; i += 16)
+                    _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + i),
+                                     _mm_sub_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(pn + i)),
+                                                  _mm_loadu_si128(reinterpret_cast<const __m128i *>(po + i))));
+#endif
+                for (; i < lenf; i++) dst[i] = (uint8_t)(pn[i] - po[i]);
+            }
 
             const int32_t extraLength = (scan - lenb) - (lastscan + lenf);
             if (extraLength > 0)

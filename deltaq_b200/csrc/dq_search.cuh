@@ -476,6 +476,16 @@ lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
     }
 }
 
+// number of equal bytes walking backwards from a[-1], b[-1], at most cap
+__device__ __forceinline__ uint32_t common_suffix(const uint8_t *a, const uint8_t *b, uint32_t cap)
+{
+    uint32_t e = 0;
+    while (e < cap && a[-(int)e - 1] == b[-(int)e - 1]) ++e;
+    return e;
+}
+
+constexpr uint32_t kBackMin = 32;  // look at the next head only when it sits inside a repeat at least this long
+
 // LCP array, level B: one thread per chunk, stride 1.  LCP[ISA[i]] = PLCP[i].
 __global__ void __launch_bounds__(kThreads)
 lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
@@ -488,6 +498,19 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
     DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes - b0; g_dbg.thr_max[0] = max(g_dbg.thr_max[0], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[0][k]++; } } fin{b0};)
     uint32_t l = head_l[c];
     LCP[ISA[i0]] = l;
+    // The next head ih shares nl bytes with its rank predecessor qh.  If the `back` bytes before ih and qh
+    // agree too, then for d <= back suffix ih-d shares d+nl bytes with the smaller suffix qh-d, and its own
+    // rank predecessor shares at least as much: a second lower bound, so a repeat that starts inside this
+    // chunk and reaches the next head is not re-compared byte by byte.
+    uint32_t nl = 0, back = 0;
+    const uint64_t ih = i0 + kChunk;
+    if (ih < n) {
+        nl = head_l[c + 1];
+        if (nl >= kBackMin) {
+            const uint32_t qh = (uint32_t)SA[ISA[ih] - 1];  // nl > 0 => the head has a predecessor
+            back = common_suffix(T + ih, T + qh, min((uint32_t)kChunk - 1, qh));
+        }
+    }
     for (int k = 1; k < kChunk; ++k) {
         const uint64_t i64 = i0 + k;
         if (i64 >= n) break;
@@ -497,7 +520,9 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
             l = 0;
         } else {
             const uint32_t q = (uint32_t)SA[r - 1];
-            const uint32_t known = l > 0 ? l - 1 : 0;
+            uint32_t known = l > 0 ? l - 1 : 0;
+            const uint32_t d = (uint32_t)(kChunk - k);
+            if (d <= back) known = max(known, d + nl);
             l = known + common_prefix(T + i + known, n - i - known, T + q + known, n - q - known);
         }
         LCP[r] = l;
@@ -566,13 +591,30 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
     // the head's carry describes the head itself: re-derive its bracket from it (stride 0)
     const uint32_t hl = head_l[c];
     Carry cy{head_p[c], hl & 0x7fffffffu, (hl >> 31) != 0};
+    // The next head matched old suffix np for nl bytes.  If the `back` bytes before the head and before np
+    // agree, the query d <= back positions earlier matches suffix np-d for exactly d+nl bytes on the same
+    // side: a second exact anchor, so a long match that begins inside this chunk and reaches the next head
+    // is never re-compared byte by byte.
+    uint32_t np = 0, nl = 0, back = 0;
+    bool nless = false;
+    if (k0 + kChunk < count) {
+        const uint32_t v = head_l[c + 1];
+        nl = v & 0x7fffffffu;
+        nless = (v >> 31) != 0;
+        np = head_p[c + 1];
+        if (nl >= kBackMin)
+            back = common_suffix(t.new_ + scan_begin + k0 + kChunk, t.old_ + np, min((uint32_t)kChunk - 1, np));
+    }
     for (int k = 0; k < kChunk; ++k) {
         const uint64_t kk = k0 + k;
         if (kk >= count) break;
         const uint32_t j = scan_begin + (uint32_t)kk;
         Bracket b;
+        const uint32_t d = (uint32_t)(kChunk - k);
         if (k == 0)
             b = locate_anchor(t, ix, j, ix.ISA[cy.p], cy.l, cy.less);
+        else if (d <= back && d + nl + 1 > cy.l)
+            b = locate_anchor(t, ix, j, ix.ISA[np - d], d + nl, nless);
         else
             b = locate_step(t, ix, j, cy, 1, true);
         int32_t pos, len;

@@ -109,6 +109,11 @@ typedef struct dq_diff_streams {
 int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                            dq_diff_streams *out);
 
+/* The host consumer alone: Diff.cs:100-223 over a caller-supplied (pos, len) table (m entries each, e.g. from
+ * dq_cuda_bsdiff_search).  Pure host code; no device work. */
+int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
+                        const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out);
+
 /* ---- building block, exported for tests and reuse ----------------------------------------------------
  * Stable LSD radix sort of (uint64 key, uint32 value) pairs on key bits [0, key_bits), host pointers. */
 int dq_cuda_radix_sort_pairs(dq_ctx *ctx, uint64_t *keys, uint32_t *vals, int32_t count, int32_t key_bits);
