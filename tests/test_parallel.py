@@ -1,0 +1,93 @@
+"""N > 1 path: match search sharded by new-range over a replicated suffix array.
+World size 2 over gloo on the CPU (contexts = the logic emulator, tests/emu); the same code runs over NCCL with
+device pointers on GPUs (test_search_sharded_nccl, needs >= 2 GPUs: `gpurun --gpus 2 -- pytest -m gpu ...`)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _pair():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from search_cases import structured_pairs
+    old, new = structured_pairs()["zero_runs_with_islands"]
+    return old, new
+
+
+def _worker(rank, world, port, backend, use_emu, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from deltaq_b200 import CudaSuffixSort
+    from deltaq_b200.parallel import search_sharded
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    if use_emu:
+        import emu
+        sorter = CudaSuffixSort(_lib=emu.library())
+    else:
+        sorter = CudaSuffixSort(device=rank)
+    old, new = _pair()
+    pos, ln = search_sharded(old, new, sorter)
+    q.put((rank, pos, ln))
+    dist.barrier()
+    dist.destroy_process_group()
+    sorter.dispose()
+
+
+def _run(world, backend, use_emu):
+    import torch.multiprocessing as mp
+    import oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, use_emu, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    old, new = _pair()
+    I = oracle.make_I(oracle.sais(old))
+    rp, rl = oracle.search_all(I, old, new)
+    for rank, pos, ln in results:
+        assert np.array_equal(pos, rp) and np.array_equal(ln, rl), rank
+
+
+def test_shard_bounds_cover_everything():
+    from deltaq_b200.parallel import shard_bounds
+    for m in (0, 1, 7, 64, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(m, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == m
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_search_sharded_gloo_world2():
+    import emu
+    emu.build()
+    _run(2, "gloo", True)
+
+
+@pytest.mark.gpu
+def test_search_sharded_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    _run(2, "nccl", False)
