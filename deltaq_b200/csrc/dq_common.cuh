@@ -33,32 +33,36 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << lane_id()) - 1u; }
 
-// ---- release/acquire accessors for the decoupled look-back descriptors ------------------------------------
+// ---- accessors for the decoupled look-back descriptors ------------------------------------------------------
+// A descriptor is ONE 32/64-bit word holding status and value together, and nothing else is communicated
+// through it, so single-word atomicity is all the protocol needs: relaxed gpu-scope accesses (served by L2),
+// no fences.  (acquire/release here compiles to CCTL.IVALL + ERRBAR around every poll -- 35 % of the pass
+// kernel's stall samples in the first version, profiles/r01_onesweep_pass_full.md.)
 #ifdef DQ_EMU
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) { return *p; }
-__device__ __forceinline__ uint64_t ld_acquire(const uint64_t *p) { return *p; }
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v) { *p = v; }
-__device__ __forceinline__ void st_release(uint64_t *p, uint64_t v) { *p = v; }
+__device__ __forceinline__ uint32_t ld_desc(const uint32_t *p) { return *p; }
+__device__ __forceinline__ uint64_t ld_desc(const uint64_t *p) { return *p; }
+__device__ __forceinline__ void st_desc(uint32_t *p, uint32_t v) { *p = v; }
+__device__ __forceinline__ void st_desc(uint64_t *p, uint64_t v) { *p = v; }
 #else
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+__device__ __forceinline__ uint32_t ld_desc(const uint32_t *p)
 {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint64_t ld_acquire(const uint64_t *p)
+__device__ __forceinline__ uint64_t ld_desc(const uint64_t *p)
 {
     uint64_t v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+__device__ __forceinline__ void st_desc(uint32_t *p, uint32_t v)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_release(uint64_t *p, uint64_t v)
+__device__ __forceinline__ void st_desc(uint64_t *p, uint64_t v)
 {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 #endif
 

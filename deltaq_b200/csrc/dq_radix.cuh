@@ -19,8 +19,14 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
 
+#ifndef DQ_PASS_ITEMS
+#define DQ_PASS_ITEMS 16
+#endif
+#ifndef DQ_PASS_MIN_BLOCKS
+#define DQ_PASS_MIN_BLOCKS 4
+#endif
 constexpr int kThreads = 256;  // == kRadix: thread d owns digit d in the look-back
-constexpr int kItems = 16;
+constexpr int kItems = DQ_PASS_ITEMS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = kThreads * kItems;
 
@@ -100,13 +106,150 @@ constexpr unsigned kStatusAggregate = 1, kStatusInclusive = 2;
 //   lb          [#tiles][kRadix] descriptors, zero before the launch
 //   tile_ticket one counter, zero before the launch
 //   gbase       [kRadix] exclusive digit offsets of this pass over the whole input
+//
+// Shared memory: key staging (32 KB) | value staging (16 KB, its first 8 KB double as the per-warp digit
+// counters until the keys are staged) | 2 KB of per-digit tables.  50 KB and <= 64 registers keep 4 CTAs
+// (32 warps) resident per SM, so one CTA's look-back wait and its load latency hide behind the others.
 constexpr size_t pass_smem_bytes()
 {
-    return (size_t)kTile * 8 + (size_t)kTile * 4 + (size_t)kWarps * kRadix * 4 + 2 * kRadix * 4 + 64;
+    return (size_t)kTile * 8 + (size_t)kTile * 4 + 2 * kRadix * 4 + 64;
+}
+static_assert(kWarps * kRadix * 4 <= kTile * 4, "per-warp counters must fit in the value staging area");
+
+template <typename DescT, bool FULL>
+__device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                              uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
+                                              uint32_t tile, uint32_t tile_count, int shift, uint32_t mask,
+                                              const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
+                                              uint64_t *skeys, uint32_t *svals, uint32_t *whist, uint32_t *sdig,
+                                              uint32_t *sout, uint32_t *smisc)
+{
+    const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t tile_base = tile * (uint32_t)kTile;
+
+    // ---- load keys, warp-striped: item j of lane l in warp w is tile_base + w*512 + j*32 + l
+    uint64_t key[kItems];
+    uint32_t rk[kItems / 2];  // two 16-bit ranks per register (ranks are < kTile = 4096)
+    const uint32_t wbase = warp * (32 * kItems) + lane;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t li = wbase + j * 32;
+        key[j] = (FULL || li < tile_count) ? ld_stream(kin + tile_base + li) : ~0ull;
+    }
+
+    // ---- stable rank of each item among the items of its warp with the same digit
+    uint32_t *wh = whist + warp * kRadix;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
+        unsigned peers = __match_any_sync(kFullMask, d);
+        bool valid = true;
+        if (!FULL) {
+            valid = wbase + j * 32 < tile_count;
+            peers &= __ballot_sync(kFullMask, valid);
+        }
+        const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
+        uint32_t before = 0;
+        if (valid && (int)lane == leader) {
+            before = wh[d];
+            wh[d] = before + __popc(peers);
+        }
+        before = __shfl_sync(kFullMask, before, leader);
+        const uint32_t rj = before + __popc(peers & lanemask_lt());
+        if (j & 1)
+            rk[j >> 1] |= rj << 16;
+        else
+            rk[j >> 1] = rj;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- thread d: digit d's count in this tile, per-warp exclusive offsets, publish, look back
+    constexpr int VB = Desc<DescT>::kValBits;
+    constexpr DescT kValMask = ((DescT)1 << VB) - 1;
+    const unsigned d = tid;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = whist[w * kRadix + d];
+        whist[w * kRadix + d] = sum;
+        sum += c;
+    }
+    DescT *my = lb + (size_t)tile * kRadix + d;
+    if (tile > 0) st_desc(my, ((DescT)kStatusAggregate << VB) | (DescT)sum);
+
+    // exclusive scan of the 256 digit counts -> first slot of each digit inside the tile
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) smisc[1 + warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (unsigned w = 0; w < warp; ++w) woff += smisc[1 + w];
+    const uint32_t first = woff + incl - sum;
+    sdig[d] = first;
+    __syncthreads();
+
+    // ---- stage the keys in digit order; the tile-local rank does not depend on the look-back
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        if (FULL || wbase + j * 32 < tile_count) {
+            const uint32_t dj = (uint32_t)(key[j] >> shift) & mask;
+            const uint32_t r = sdig[dj] + wh[dj] + ((rk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+            rk[j >> 1] = (j & 1) ? ((rk[j >> 1] & 0xffffu) | (r << 16)) : ((rk[j >> 1] & 0xffff0000u) | r);
+            skeys[r] = key[j];
+        }
+    }
+    // values are requested now and land while the look-back spins
+    uint32_t val[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t li = wbase + j * 32;
+        val[j] = (FULL || li < tile_count) ? ld_stream(vin + tile_base + li) : 0u;
+    }
+
+    DescT excl = 0;
+    if (tile > 0) {
+        uint32_t t = tile - 1;
+        for (;;) {
+            const DescT v = ld_desc(lb + (size_t)t * kRadix + d);
+            const unsigned st = (unsigned)(v >> VB);
+            if (st == 0) {
+                DQ_SPIN_HINT();
+                continue;
+            }
+            excl += v & kValMask;
+            if (st == kStatusInclusive) break;
+            --t;
+        }
+    }
+    st_desc(my, ((DescT)kStatusInclusive << VB) | (excl + (DescT)sum));
+    sout[d] = gbase[d] + (uint32_t)excl - first;
+    __syncthreads();  // every thread has read its per-warp counters: the value staging area may overwrite them
+
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+        if (FULL || wbase + j * 32 < tile_count) svals[(rk[j >> 1] >> (16 * (j & 1))) & 0xffffu] = val[j];
+    __syncthreads();
+
+    // ---- stream the tile out: item i of the staged order goes to sout[digit] + i (coalesced runs)
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t i = tid + j * kThreads;
+        if (FULL || i < tile_count) {
+            const uint64_t k = skeys[i];
+            const uint32_t dst = sout[(uint32_t)(k >> shift) & mask] + i;
+            kout[dst] = k;
+            vout[dst] = svals[i];
+        }
+    }
 }
 
 template <typename DescT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, DQ_PASS_MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                      uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t count, int shift,
                      uint32_t mask, const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
@@ -115,127 +258,24 @@ onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
     DQ_DYN_SMEM(smem);
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
     uint32_t *svals = reinterpret_cast<uint32_t *>(smem + (size_t)kTile * 8);
-    uint32_t *whist = svals + kTile;          // [kWarps][kRadix]
-    uint32_t *sdig = whist + kWarps * kRadix; // [kRadix] first slot of each digit inside the tile
-    uint32_t *sout = sdig + kRadix;           // [kRadix] global slot of tile item i with digit d is sout[d] + i
+    uint32_t *whist = svals;                 // [kWarps][kRadix], dead once the keys are staged
+    uint32_t *sdig = svals + kTile;          // [kRadix] first slot of each digit inside the tile
+    uint32_t *sout = sdig + kRadix;          // [kRadix] global slot of staged item i with digit d = sout[d] + i
     uint32_t *smisc = sout + kRadix;
 
-    const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-
+    const unsigned tid = threadIdx.x;
     if (tid == 0) smisc[0] = atomicAdd(tile_ticket, 1u);
     for (int i = tid; i < kWarps * kRadix; i += kThreads) whist[i] = 0;
     __syncthreads();
     const uint32_t tile = smisc[0];
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
-
-    // ---- load, warp-striped: item j of lane l in warp w is tile_base + w*512 + j*32 + l
-    uint64_t key[kItems];
-    uint32_t val[kItems];
-    uint32_t rank[kItems];
-    const uint32_t wbase = warp * (32 * kItems) + lane;
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        uint32_t li = wbase + j * 32;
-        key[j] = li < tile_count ? ld_stream(kin + tile_base + li) : ~0ull;
-    }
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        uint32_t li = wbase + j * 32;
-        val[j] = li < tile_count ? ld_stream(vin + tile_base + li) : 0u;
-    }
-
-    // ---- stable rank of each item among the items of its warp with the same digit
-    uint32_t *wh = whist + warp * kRadix;
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        const bool valid = wbase + j * 32 < tile_count;
-        const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
-        const unsigned vmask = __ballot_sync(kFullMask, valid);
-        const unsigned peers = __match_any_sync(kFullMask, d) & vmask;
-        int leader = valid ? (__ffs(peers) - 1) : (int)lane;
-        uint32_t before = 0;
-        if (valid && (int)lane == leader) {
-            before = wh[d];
-            wh[d] = before + __popc(peers);
-        }
-        before = __shfl_sync(kFullMask, before, leader);
-        rank[j] = before + __popc(peers & lanemask_lt());
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- thread d: digit d's count in this tile, per-warp exclusive offsets, look-back
-    {
-        const unsigned d = tid;
-        uint32_t sum = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            uint32_t c = whist[w * kRadix + d];
-            whist[w * kRadix + d] = sum;
-            sum += c;
-        }
-        constexpr int VB = Desc<DescT>::kValBits;
-        constexpr DescT kValMask = ((DescT)1 << VB) - 1;
-        DescT *my = lb + (size_t)tile * kRadix + d;
-        if (tile > 0) st_release(my, ((DescT)kStatusAggregate << VB) | (DescT)sum);
-
-        // exclusive scan of the 256 digit counts -> first slot of each digit inside the tile
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= (unsigned)o) incl += t;
-        }
-        if (lane == 31) smisc[1 + warp] = incl;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (unsigned w = 0; w < warp; ++w) woff += smisc[1 + w];
-        const uint32_t first = woff + incl - sum;
-
-        DescT excl = 0;
-        if (tile > 0) {
-            uint32_t t = tile - 1;
-            for (;;) {
-                DescT v = ld_acquire(lb + (size_t)t * kRadix + d);
-                unsigned st = (unsigned)(v >> VB);
-                if (st == 0) {
-                    DQ_SPIN_HINT();
-                    continue;
-                }
-                excl += v & kValMask;
-                if (st == kStatusInclusive) break;
-                --t;
-            }
-        }
-        st_release(my, ((DescT)kStatusInclusive << VB) | (excl + (DescT)sum));
-        sdig[d] = first;
-        sout[d] = gbase[d] + (uint32_t)excl - first;
-    }
-    __syncthreads();
-
-    // ---- stage the tile in digit order, then stream it out in coalesced runs
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        if (wbase + j * 32 < tile_count) {
-            const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
-            const uint32_t r = sdig[d] + wh[d] + rank[j];
-            skeys[r] = key[j];
-            svals[r] = val[j];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        const uint32_t i = tid + j * kThreads;
-        if (i < tile_count) {
-            const uint64_t k = skeys[i];
-            const uint32_t d = (uint32_t)(k >> shift) & mask;
-            const uint32_t dst = sout[d] + i;
-            kout[dst] = k;
-            vout[dst] = svals[i];
-        }
-    }
+    if (tile_count == (uint32_t)kTile)
+        onesweep_tile<DescT, true>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
+                                   sdig, sout, smisc);
+    else
+        onesweep_tile<DescT, false>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
+                                    sdig, sout, smisc);
 }
 
 }  // namespace radix

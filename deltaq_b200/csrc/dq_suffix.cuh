@@ -242,11 +242,11 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         const uint64_t agg = rk_pack(bmax, bsum);
         uint64_t excl = 0;
         if (tile > 0) {
-            st_release(lb + tile, ((uint64_t)radix::kStatusAggregate << 62) | agg);
+            st_desc(lb + tile, ((uint64_t)radix::kStatusAggregate << 62) | agg);
             uint32_t t = tile - 1;
             uint32_t xm = 0, xs = 0;
             for (;;) {
-                uint64_t v = ld_acquire(lb + t);
+                uint64_t v = ld_desc(lb + t);
                 unsigned st = (unsigned)(v >> 62);
                 if (st == 0) {
                     DQ_SPIN_HINT();
@@ -260,7 +260,7 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             excl = rk_pack(xm, xs);
         }
         const uint64_t incl = rk_pack(max(rk_max(excl), bmax), rk_sum(excl) + bsum);
-        st_release(lb + tile, ((uint64_t)radix::kStatusInclusive << 62) | incl);
+        st_desc(lb + tile, ((uint64_t)radix::kStatusInclusive << 62) | incl);
         s_excl = excl;
         if ((uint64_t)(tile + 1) * kRankTile >= a) *count_out = rk_sum(incl);
     }
