@@ -23,7 +23,7 @@ constexpr int kMaxPasses = 8;
 #define DQ_PASS_ITEMS 16
 #endif
 #ifndef DQ_PASS_MIN_BLOCKS
-#define DQ_PASS_MIN_BLOCKS 4
+#define DQ_PASS_MIN_BLOCKS 3
 #endif
 constexpr int kThreads = 256;  // == kRadix: thread d owns digit d in the look-back
 constexpr int kItems = DQ_PASS_ITEMS;
@@ -107,76 +107,66 @@ constexpr unsigned kStatusAggregate = 1, kStatusInclusive = 2;
 //   tile_ticket one counter, zero before the launch
 //   gbase       [kRadix] exclusive digit offsets of this pass over the whole input
 //
-// Shared memory: key staging (32 KB) | value staging (16 KB, its first 8 KB double as the per-warp digit
-// counters until the keys are staged) | 2 KB of per-digit tables.  50 KB and <= 64 registers keep 4 CTAs
-// (32 warps) resident per SM, so one CTA's look-back wait and its load latency hide behind the others.
+// Order of work inside a tile (what the ncu captures in profiles/ asked for):
+//   1. load keys; count digits per warp with shared-memory atomics ("early counts");
+//   2. thread d publishes digit d's tile count at once, so successors never wait on this tile's ranking;
+//   3. look-back immediately, kLookWindow predecessors per round trip (independent loads), publish inclusive;
+//   4. stable ranking (match_any within the warp, running per-warp counters that already include the tile
+//      and warp offsets) writes every key straight to its slot of the shared staging area;
+//   5. values (requested before the look-back) are staged through the same slots; coalesced write-out.
+constexpr int kLookWindow = 8;
+
 constexpr size_t pass_smem_bytes()
 {
-    return (size_t)kTile * 8 + (size_t)kTile * 4 + 2 * kRadix * 4 + 64;
+    return (size_t)kTile * 8 + (size_t)kTile * 4 + (size_t)kWarps * kRadix * 4 + kRadix * 4 + 64;
 }
-static_assert(kWarps * kRadix * 4 <= kTile * 4, "per-warp counters must fit in the value staging area");
 
 template <typename DescT, bool FULL>
 __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                               uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
                                               uint32_t tile, uint32_t tile_count, int shift, uint32_t mask,
                                               const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
-                                              uint64_t *skeys, uint32_t *svals, uint32_t *whist, uint32_t *sdig,
-                                              uint32_t *sout, uint32_t *smisc)
+                                              uint64_t *skeys, uint32_t *svals, uint32_t *whist, uint32_t *sout,
+                                              uint32_t *smisc)
 {
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint32_t tile_base = tile * (uint32_t)kTile;
 
-    // ---- load keys, warp-striped: item j of lane l in warp w is tile_base + w*512 + j*32 + l
+    // ---- 1. keys, warp-striped: item j of lane l in warp w is tile_base + w*32*kItems + j*32 + l
     uint64_t key[kItems];
-    uint32_t rk[kItems / 2];  // two 16-bit ranks per register (ranks are < kTile = 4096)
     const uint32_t wbase = warp * (32 * kItems) + lane;
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
         const uint32_t li = wbase + j * 32;
         key[j] = (FULL || li < tile_count) ? ld_stream(kin + tile_base + li) : ~0ull;
     }
-
-    // ---- stable rank of each item among the items of its warp with the same digit
     uint32_t *wh = whist + warp * kRadix;
 #pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        const uint32_t d = (uint32_t)(key[j] >> shift) & mask;
-        unsigned peers = __match_any_sync(kFullMask, d);
-        bool valid = true;
-        if (!FULL) {
-            valid = wbase + j * 32 < tile_count;
-            peers &= __ballot_sync(kFullMask, valid);
-        }
-        const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
-        uint32_t before = 0;
-        if (valid && (int)lane == leader) {
-            before = wh[d];
-            wh[d] = before + __popc(peers);
-        }
-        before = __shfl_sync(kFullMask, before, leader);
-        const uint32_t rj = before + __popc(peers & lanemask_lt());
-        if (j & 1)
-            rk[j >> 1] |= rj << 16;
-        else
-            rk[j >> 1] = rj;
-        __syncwarp();
-    }
+    for (int j = 0; j < kItems; ++j)
+        if (FULL || wbase + j * 32 < tile_count) atomicAdd(&wh[(uint32_t)(key[j] >> shift) & mask], 1u);
     __syncthreads();
 
-    // ---- thread d: digit d's count in this tile, per-warp exclusive offsets, publish, look back
+    // ---- 2. thread d: tile count of digit d, published immediately
     constexpr int VB = Desc<DescT>::kValBits;
     constexpr DescT kValMask = ((DescT)1 << VB) - 1;
     const unsigned d = tid;
+    uint32_t cw[kWarps];
     uint32_t sum = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-        const uint32_t c = whist[w * kRadix + d];
-        whist[w * kRadix + d] = sum;
-        sum += c;
+        cw[w] = whist[w * kRadix + d];
+        sum += cw[w];
     }
     DescT *my = lb + (size_t)tile * kRadix + d;
     if (tile > 0) st_desc(my, ((DescT)kStatusAggregate << VB) | (DescT)sum);
+
+    // values are requested now and land during the look-back and the ranking
+    uint32_t val[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t li = wbase + j * 32;
+        val[j] = (FULL || li < tile_count) ? ld_stream(vin + tile_base + li) : 0u;
+    }
 
     // exclusive scan of the 256 digit counts -> first slot of each digit inside the tile
     uint32_t incl = sum;
@@ -187,55 +177,78 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     }
     if (lane == 31) smisc[1 + warp] = incl;
     __syncthreads();
-    uint32_t woff = 0;
-    for (unsigned w = 0; w < warp; ++w) woff += smisc[1 + w];
-    const uint32_t first = woff + incl - sum;
-    sdig[d] = first;
-    __syncthreads();
-
-    // ---- stage the keys in digit order; the tile-local rank does not depend on the look-back
+    uint32_t first = incl - sum;
+    for (unsigned w = 0; w < warp; ++w) first += smisc[1 + w];
+    {   // running counters of the ranking start at (slot of the digit in the tile) + (items of earlier warps)
+        uint32_t run = first;
 #pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        if (FULL || wbase + j * 32 < tile_count) {
-            const uint32_t dj = (uint32_t)(key[j] >> shift) & mask;
-            const uint32_t r = sdig[dj] + wh[dj] + ((rk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
-            rk[j >> 1] = (j & 1) ? ((rk[j >> 1] & 0xffffu) | (r << 16)) : ((rk[j >> 1] & 0xffff0000u) | r);
-            skeys[r] = key[j];
+        for (int w = 0; w < kWarps; ++w) {
+            whist[w * kRadix + d] = run;
+            run += cw[w];
         }
     }
-    // values are requested now and land while the look-back spins
-    uint32_t val[kItems];
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        const uint32_t li = wbase + j * 32;
-        val[j] = (FULL || li < tile_count) ? ld_stream(vin + tile_base + li) : 0u;
-    }
 
+    // ---- 3. look-back: kLookWindow predecessors per round trip
     DescT excl = 0;
     if (tile > 0) {
-        uint32_t t = tile - 1;
-        for (;;) {
-            const DescT v = ld_desc(lb + (size_t)t * kRadix + d);
-            const unsigned st = (unsigned)(v >> VB);
-            if (st == 0) {
-                DQ_SPIN_HINT();
-                continue;
+        int64_t t = (int64_t)tile - 1;
+        bool done = false;
+        while (!done) {
+            DescT v[kLookWindow];
+#pragma unroll
+            for (int i = 0; i < kLookWindow; ++i)
+                v[i] = (t - i >= 0) ? ld_desc(lb + (size_t)(t - i) * kRadix + d) : ((DescT)kStatusInclusive << VB);
+            int used = 0;
+#pragma unroll
+            for (int i = 0; i < kLookWindow; ++i) {
+                if (!done && used == i) {
+                    const unsigned st = (unsigned)(v[i] >> VB);
+                    if (st != 0) {
+                        excl += v[i] & kValMask;
+                        used = i + 1;
+                        if (st == kStatusInclusive) done = true;
+                    }
+                }
             }
-            excl += v & kValMask;
-            if (st == kStatusInclusive) break;
-            --t;
+            t -= used;
+            if (!done && used == 0) DQ_SPIN_HINT();
         }
     }
     st_desc(my, ((DescT)kStatusInclusive << VB) | (excl + (DescT)sum));
     sout[d] = gbase[d] + (uint32_t)excl - first;
-    __syncthreads();  // every thread has read its per-warp counters: the value staging area may overwrite them
+    __syncthreads();
 
+    // ---- 4. stable ranking; keys go straight to their slot
+    uint32_t rk[kItems / 2];  // two 16-bit slots per register (slots are < kTile <= 65536)
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t dj = (uint32_t)(key[j] >> shift) & mask;
+        unsigned peers = __match_any_sync(kFullMask, dj);
+        bool valid = true;
+        if (!FULL) {
+            valid = wbase + j * 32 < tile_count;
+            peers &= __ballot_sync(kFullMask, valid);
+        }
+        const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
+        uint32_t before = 0;
+        if (valid && (int)lane == leader) {
+            before = wh[dj];
+            wh[dj] = before + __popc(peers);
+        }
+        before = __shfl_sync(kFullMask, before, leader);
+        const uint32_t r = before + __popc(peers & lanemask_lt());
+        if (valid) skeys[r] = key[j];
+        if (j & 1)
+            rk[j >> 1] |= r << 16;
+        else
+            rk[j >> 1] = r;
+        __syncwarp();
+    }
+    // ---- 5. values through the same slots, then stream the tile out
 #pragma unroll
     for (int j = 0; j < kItems; ++j)
         if (FULL || wbase + j * 32 < tile_count) svals[(rk[j >> 1] >> (16 * (j & 1))) & 0xffffu] = val[j];
     __syncthreads();
-
-    // ---- stream the tile out: item i of the staged order goes to sout[digit] + i (coalesced runs)
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
         const uint32_t i = tid + j * kThreads;
@@ -258,9 +271,8 @@ onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
     DQ_DYN_SMEM(smem);
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
     uint32_t *svals = reinterpret_cast<uint32_t *>(smem + (size_t)kTile * 8);
-    uint32_t *whist = svals;                 // [kWarps][kRadix], dead once the keys are staged
-    uint32_t *sdig = svals + kTile;          // [kRadix] first slot of each digit inside the tile
-    uint32_t *sout = sdig + kRadix;          // [kRadix] global slot of staged item i with digit d = sout[d] + i
+    uint32_t *whist = svals + kTile;            // [kWarps][kRadix]
+    uint32_t *sout = whist + kWarps * kRadix;   // [kRadix] global slot of staged item i with digit d = sout[d] + i
     uint32_t *smisc = sout + kRadix;
 
     const unsigned tid = threadIdx.x;
@@ -272,10 +284,10 @@ onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
     const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
     if (tile_count == (uint32_t)kTile)
         onesweep_tile<DescT, true>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
-                                   sdig, sout, smisc);
+                                   sout, smisc);
     else
         onesweep_tile<DescT, false>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
-                                    sdig, sout, smisc);
+                                    sout, smisc);
 }
 
 }  // namespace radix
