@@ -46,6 +46,7 @@ class NativeError(RuntimeError):
 
 EXPORTS = [
     "dq_cuda_create", "dq_cuda_destroy", "dq_cuda_last_error", "dq_cuda_get_stats", "dq_cuda_set_timing",
+    "dq_cuda_get_pass_times",
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
     "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
     "dq_cuda_radix_sort_pairs",
@@ -69,6 +70,7 @@ class Library:
         L.dq_cuda_last_error.restype = ctypes.c_char_p
         L.dq_cuda_get_stats.argtypes = [vp, ctypes.POINTER(DqStats)]
         L.dq_cuda_set_timing.argtypes = [vp, ctypes.c_int]
+        L.dq_cuda_get_pass_times.argtypes = [vp, vp, vp, vp, ctypes.c_int]
         L.dq_cuda_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dq_cuda_host_free.argtypes = [vp]
         L.dq_cuda_suffix_sort.argtypes = [vp, vp, i32, vp]
@@ -168,6 +170,18 @@ class Context:
         st = DqStats()
         self._check(self.lib.L.dq_cuda_get_stats(self._h, ctypes.byref(st)))
         return st.as_dict()
+
+    def pass_times(self):
+        """[(ms, pairs, shift)] of every onesweep launch of the last sort (timing must be on)."""
+        cap = 4096
+        ms = np.zeros(cap, dtype=np.float32)
+        pairs = np.zeros(cap, dtype=np.int64)
+        shift = np.zeros(cap, dtype=np.int32)
+        n = self.lib.L.dq_cuda_get_pass_times(self._h, _addr(ms), _addr(pairs), _addr(shift), cap)
+        if n < 0:
+            self._check(n)
+        n = min(n, cap)
+        return [(float(ms[i]), int(pairs[i]), int(shift[i])) for i in range(n)]
 
     def set_timing(self, on):
         self._check(self.lib.L.dq_cuda_set_timing(self._h, 1 if on else 0))

@@ -30,6 +30,8 @@ struct DevBuf {
 struct EventPair {
     cudaEvent_t a, b;
     uint64_t pairs;
+    int shift;
+    float ms;
 };
 
 struct PinBuf {
@@ -118,13 +120,14 @@ struct SortBufs {
 
 // Sorts `count` pairs in (s.kin, s.vin) by the digits of `plan`; histograms for all passes are already
 // in ctx->hist ([npass][256] counters at offset 0).  On return the sorted pairs are in (s.kin, s.vin).
-int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &plan)
+int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &plan, bool locally_ordered)
 {
     if (count == 0 || plan.npass == 0) return DQ_OK;
     uint32_t *ghist = ctx->hist.as<uint32_t>();
     uint32_t *gbase = ghist + rx::kMaxPasses * rx::kRadix;
+    uint32_t *use_match = gbase + rx::kMaxPasses * rx::kRadix;
     auto scan = rx::scan_hist_kernel;
-    DQ_LAUNCH(scan, plan.npass, rx::kRadix, 0, ctx->stream, ghist, gbase);
+    DQ_LAUNCH(scan, plan.npass, rx::kRadix, 0, ctx->stream, ghist, gbase, use_match, count, locally_ordered ? 1 : 0);
     ctx->stats.kernel_launches++;
 
     const uint32_t tiles = (uint32_t)div_up(count, rx::kTile);
@@ -156,18 +159,19 @@ int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &pla
             }
             ep = &ctx->pass_events[ctx->pass_events_used++];
             ep->pairs = count;
+            ep->shift = plan.shift[p];
             DQ_CK(ctx, cudaEventRecord(ep->a, ctx->stream));
         }
         if (wide) {
             auto k = rx::onesweep_pass_kernel<uint64_t>;
             DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
                       count, plan.shift[p], mask, gbase + p * rx::kRadix, reinterpret_cast<uint64_t *>(region),
-                      tickets + p);
+                      tickets + p, use_match + p);
         } else {
             auto k = rx::onesweep_pass_kernel<uint32_t>;
             DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
                       count, plan.shift[p], mask, gbase + p * rx::kRadix, reinterpret_cast<uint32_t *>(region),
-                      tickets + p);
+                      tickets + p, use_match + p);
         }
         if (ep) DQ_CK(ctx, cudaEventRecord(ep->b, ctx->stream));
         ctx->stats.kernel_launches++;
@@ -250,7 +254,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         st.kernel_launches++;
     }
     SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
-    DQ_TRY(run_passes(ctx, s, n, plan));
+    DQ_TRY(run_passes(ctx, s, n, plan, false));
     st.rounds = 1;
     st.active_sum = n;
     st.algorithmic_bytes = (int64_t)n * (41 + 24 * plan.npass);
@@ -279,7 +283,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         }
         // sort (s.kin, s.vout) using (s.kout, s.vin) as the alternate
         std::swap(s.vin, s.vout);
-        DQ_TRY(run_passes(ctx, s, a, rp));
+        DQ_TRY(run_passes(ctx, s, a, rp, true));
         st.rounds++;
         st.active_sum += a;
         st.algorithmic_bytes += (int64_t)a * (52 + 24 * rp.npass);
@@ -309,6 +313,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         for (size_t i = 0; i < ctx->pass_events_used; ++i) {
             float ms = 0.f;
             DQ_CK(ctx, cudaEventElapsedTime(&ms, ctx->pass_events[i].a, ctx->pass_events[i].b));
+            ctx->pass_events[i].ms = ms;
             tot += ms;
             pairs += ctx->pass_events[i].pairs;
         }
@@ -432,6 +437,19 @@ int dq_cuda_set_timing(dq_ctx *ctx, int on)
     return DQ_OK;
 }
 
+int dq_cuda_get_pass_times(dq_ctx *ctx, float *ms, int64_t *pairs, int32_t *shift, int cap)
+{
+    if (!ctx || cap < 0) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const int n = (int)ctx->pass_events_used;
+    for (int i = 0; i < n && i < cap; ++i) {
+        if (ms) ms[i] = ctx->pass_events[i].ms;
+        if (pairs) pairs[i] = (int64_t)ctx->pass_events[i].pairs;
+        if (shift) shift[i] = ctx->pass_events[i].shift;
+    }
+    return n;
+}
+
 int dq_cuda_host_alloc(void **out, size_t bytes)
 {
     if (!out) return DQ_ERR_INVALID_ARGUMENT;
@@ -507,7 +525,7 @@ int dq_cuda_radix_sort_pairs(dq_ctx *ctx, uint64_t *keys, uint32_t *vals, int32_
                   ctx->keyA.as<uint64_t>(), (uint32_t)count, plan, ctx->hist.as<uint32_t>());
     }
     SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
-    DQ_TRY(run_passes(ctx, s, (uint32_t)count, plan));
+    DQ_TRY(run_passes(ctx, s, (uint32_t)count, plan, false));
     DQ_CK(ctx, cudaMemcpyAsync(keys, s.kin, c8, cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CK(ctx, cudaMemcpyAsync(vals, s.vin, c4, cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));

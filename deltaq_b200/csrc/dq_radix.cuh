@@ -73,10 +73,18 @@ __device__ __forceinline__ void hist_flush(const uint32_t *sh, int npass, uint32
 }
 
 // exclusive scan of each pass's 256 counters: ghist[p][d] -> gbase[p][d].  grid = npass, block = 256.
+// Also decides how the pass ranks its items (see match_digit): use_match[p] = 1 when a warp row of 32 items is
+// expected to hold at most kMatchMaxDistinct distinct digits.  force_match: the caller knows the input is
+// locally ordered (doubling rounds: measured faster with MATCH on every pass), skip the estimate.
+constexpr float kMatchMaxDistinct = 16.0f;
+
 __global__ void __launch_bounds__(kRadix) scan_hist_kernel(const uint32_t *__restrict__ ghist,
-                                                          uint32_t *__restrict__ gbase)
+                                                          uint32_t *__restrict__ gbase,
+                                                          uint32_t *__restrict__ use_match, uint32_t total,
+                                                          int force_match)
 {
     __shared__ uint32_t warp_tot[kRadix / 32];
+    __shared__ float warp_exp[kRadix / 32];
     const unsigned d = threadIdx.x;
     const uint32_t c = ghist[blockIdx.x * kRadix + d];
     uint32_t incl = c;
@@ -85,11 +93,46 @@ __global__ void __launch_bounds__(kRadix) scan_hist_kernel(const uint32_t *__res
         uint32_t t = __shfl_up_sync(kFullMask, incl, o);
         if (lane_id() >= (unsigned)o) incl += t;
     }
+    // expected number of distinct digits among 32 independent draws: sum_d 1 - (1 - p_d)^32
+    float e = 0.f;
+    if (c) {
+        float q = 1.f - (float)c / (float)total;
+        q *= q; q *= q; q *= q; q *= q; q *= q;  // ^32
+        e = 1.f - q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(kFullMask, e, o);
     if (lane_id() == 31) warp_tot[warp_id()] = incl;
+    if (lane_id() == 0) warp_exp[warp_id()] = e;
     __syncthreads();
     uint32_t woff = 0;
     for (unsigned w = 0; w < warp_id(); ++w) woff += warp_tot[w];
     gbase[blockIdx.x * kRadix + d] = woff + incl - c;
+    if (d == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < kRadix / 32; ++w) tot += warp_exp[w];
+        use_match[blockIdx.x] = (force_match || tot <= kMatchMaxDistinct) ? 1u : 0u;
+    }
+}
+
+// lanes of the warp whose digit equals this lane's.  MATCH.ANY costs time proportional to the number of
+// DISTINCT digits in the warp row (measured on B200: uniform digits 2.1 TB/s with MATCH vs 2.8 TB/s with
+// ballots; locally ordered digits 3.0-3.4 TB/s with MATCH vs 2.5-2.7 with ballots); one ballot per digit bit
+// costs the same whatever the data.  The choice is made once per pass by scan_hist_kernel.
+template <bool USE_MATCH>
+__device__ __forceinline__ unsigned match_digit(uint32_t d, int nbits)
+{
+    if (USE_MATCH) return __match_any_sync(kFullMask, d);
+    unsigned peers = kFullMask;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+        if (b < nbits) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned bal = __ballot_sync(kFullMask, bit);
+            peers &= bit ? bal : ~bal;
+        }
+    }
+    return peers;
 }
 
 // ---- look-back descriptors -----------------------------------------------------------------------------
@@ -118,7 +161,41 @@ constexpr int kLookWindow = 8;
 
 constexpr size_t pass_smem_bytes()
 {
-    return (size_t)kTile * 8 + (size_t)kTile * 4 + (size_t)kWarps * kRadix * 4 + kRadix * 4 + 64;
+    return (size_t)kTile * 8 + (size_t)kTile * 4 + (size_t)kWarps * kRadix * 4 + kRadix * 4 + 128;
+}
+
+// stable rank of every item of the warp among the tile's items with the same digit; wh[] = the warp's
+// running counters, pre-loaded with (slot of the digit in the tile) + (items of earlier warps)
+template <bool FULL, bool USE_MATCH>
+__device__ __forceinline__ void rank_and_stage(const uint64_t (&key)[kItems], uint32_t (&rk)[kItems / 2], uint32_t *wh,
+                                               uint64_t *skeys, uint32_t wbase, uint32_t tile_count, int shift,
+                                               uint32_t mask, int nbits)
+{
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const uint32_t dj = (uint32_t)(key[j] >> shift) & mask;
+        unsigned peers = match_digit<USE_MATCH>(dj, nbits);
+        bool valid = true;
+        if (!FULL) {
+            valid = wbase + j * 32 < tile_count;
+            peers &= __ballot_sync(kFullMask, valid);
+        }
+        const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
+        uint32_t before = 0;
+        if (valid && (int)lane == leader) {
+            before = wh[dj];
+            wh[dj] = before + __popc(peers);
+        }
+        before = __shfl_sync(kFullMask, before, leader);
+        const uint32_t r = before + __popc(peers & lanemask_lt());
+        if (valid) skeys[r] = key[j];
+        if (j & 1)
+            rk[j >> 1] |= r << 16;
+        else
+            rk[j >> 1] = r;
+        __syncwarp();
+    }
 }
 
 template <typename DescT, bool FULL>
@@ -127,7 +204,7 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
                                               uint32_t tile, uint32_t tile_count, int shift, uint32_t mask,
                                               const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
                                               uint64_t *skeys, uint32_t *svals, uint32_t *whist, uint32_t *sout,
-                                              uint32_t *smisc)
+                                              uint32_t *smisc, bool few_distinct)
 {
     const unsigned tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint32_t tile_base = tile * (uint32_t)kTile;
@@ -159,6 +236,7 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     }
     DescT *my = lb + (size_t)tile * kRadix + d;
     if (tile > 0) st_desc(my, ((DescT)kStatusAggregate << VB) | (DescT)sum);
+    const int nbits = __popc(mask);
 
     // values are requested now and land during the look-back and the ranking
     uint32_t val[kItems];
@@ -220,30 +298,10 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
 
     // ---- 4. stable ranking; keys go straight to their slot
     uint32_t rk[kItems / 2];  // two 16-bit slots per register (slots are < kTile <= 65536)
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        const uint32_t dj = (uint32_t)(key[j] >> shift) & mask;
-        unsigned peers = __match_any_sync(kFullMask, dj);
-        bool valid = true;
-        if (!FULL) {
-            valid = wbase + j * 32 < tile_count;
-            peers &= __ballot_sync(kFullMask, valid);
-        }
-        const int leader = valid ? (__ffs(peers) - 1) : (int)lane;
-        uint32_t before = 0;
-        if (valid && (int)lane == leader) {
-            before = wh[dj];
-            wh[dj] = before + __popc(peers);
-        }
-        before = __shfl_sync(kFullMask, before, leader);
-        const uint32_t r = before + __popc(peers & lanemask_lt());
-        if (valid) skeys[r] = key[j];
-        if (j & 1)
-            rk[j >> 1] |= r << 16;
-        else
-            rk[j >> 1] = r;
-        __syncwarp();
-    }
+    if (few_distinct)
+        rank_and_stage<FULL, true>(key, rk, wh, skeys, wbase, tile_count, shift, mask, nbits);
+    else
+        rank_and_stage<FULL, false>(key, rk, wh, skeys, wbase, tile_count, shift, mask, nbits);
     // ---- 5. values through the same slots, then stream the tile out
 #pragma unroll
     for (int j = 0; j < kItems; ++j)
@@ -266,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, DQ_PASS_MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                      uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t count, int shift,
                      uint32_t mask, const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
-                     uint32_t *__restrict__ tile_ticket)
+                     uint32_t *__restrict__ tile_ticket, const uint32_t *__restrict__ use_match)
 {
     DQ_DYN_SMEM(smem);
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
@@ -276,18 +334,22 @@ onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
     uint32_t *smisc = sout + kRadix;
 
     const unsigned tid = threadIdx.x;
-    if (tid == 0) smisc[0] = atomicAdd(tile_ticket, 1u);
+    if (tid == 0) {
+        smisc[0] = atomicAdd(tile_ticket, 1u);
+        smisc[16] = *use_match;
+    }
     for (int i = tid; i < kWarps * kRadix; i += kThreads) whist[i] = 0;
     __syncthreads();
     const uint32_t tile = smisc[0];
+    const bool few = smisc[16] != 0;
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
     if (tile_count == (uint32_t)kTile)
         onesweep_tile<DescT, true>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
-                                   sout, smisc);
+                                   sout, smisc, few);
     else
         onesweep_tile<DescT, false>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
-                                    sout, smisc);
+                                    sout, smisc, few);
 }
 
 }  // namespace radix

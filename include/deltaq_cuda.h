@@ -62,6 +62,10 @@ int dq_cuda_get_stats(dq_ctx *ctx, dq_stats *out);
 /* when on, onesweep launches are bracketed by CUDA events (serialises nothing, costs two records/launch) */
 int dq_cuda_set_timing(dq_ctx *ctx, int on);
 
+/* Per-launch CUDA-event times of the onesweep passes of the last sort (timing must be on): fills up to `cap`
+ * entries of ms[] / pairs[] / shift[] in launch order and returns the number of launches (or a negative status). */
+int dq_cuda_get_pass_times(dq_ctx *ctx, float *ms, int64_t *pairs, int32_t *shift, int cap);
+
 /* Pinned host buffers (the provider's IMemoryOwner<int> can sit on these: no staging copy on D2H). */
 int dq_cuda_host_alloc(void **out, size_t bytes);
 int dq_cuda_host_free(void *p);

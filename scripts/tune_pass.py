@@ -13,11 +13,12 @@ from deltaq_b200 import _native, build, workloads as w  # noqa: E402
 variants = [(16, 4), (16, 3), (16, 2), (12, 4), (12, 5), (8, 6), (20, 3)]
 if len(sys.argv) > 1:
     variants = [tuple(int(x) for x in v.split("x")) for v in sys.argv[1:]]
+variants = [v if len(v) == 3 else (v[0], v[1], 0) for v in variants]
 texts = {"uniform16M": w.c1_uniform(16 << 20, 9), "c2_old": w.c2_exe_pair()[0]}
 res = {}
-for items, minb in variants:
-    out = os.path.join(ROOT, "gpurun_out", f"libdq_{items}_{minb}.so")
-    cmd = [build.nvcc_path()] + build.NVCC_FLAGS + [f"-DDQ_PASS_ITEMS={items}", f"-DDQ_PASS_MIN_BLOCKS={minb}", "-Xptxas", "-v",
+for items, minb, ballot in variants:
+    out = os.path.join(ROOT, "gpurun_out", f"libdq_{items}_{minb}_{ballot}.so")
+    cmd = [build.nvcc_path()] + build.NVCC_FLAGS + [f"-DDQ_PASS_ITEMS={items}", f"-DDQ_PASS_MIN_BLOCKS={minb}",  "-Xptxas", "-v",
            "-I", build.INCLUDE, "-o", out, os.path.join(build.CSRC, "deltaq_cuda.cu")]
     p = subprocess.run(cmd, capture_output=True, text=True)
     info = [l for l in p.stderr.splitlines() if "onesweep_pass_kernelIj" in l or "spill" in l or "Used" in l]
@@ -39,9 +40,12 @@ for items, minb in variants:
             st = ctx.stats()
             if best is None or st["device_ms"] < best["device_ms"]:
                 best = st
+        if "--passes" in os.environ.get("TUNE_FLAGS", ""):
+            for ms, pairs, shift in ctx.pass_times()[:40]:
+                print(f"      shift={shift:2d} pairs={pairs:9d} {ms*1e3:8.1f} us  {pairs*24/ms/1e6:7.0f} GB/s")
         gbs = best["pass_pairs"] * 24 / best["pass_ms"] / 1e6
-        res[f"{items}x{minb}:{name}"] = dict(device_ms=best["device_ms"], pass_ms=best["pass_ms"], pass_GBps=gbs)
-        print(f"items={items} minb={minb} {name}: device {best['device_ms']:.3f} ms, passes {best['pass_ms']:.3f} ms, {gbs:.0f} GB/s   [{regs}]", flush=True)
+        res[f"{items}x{minb}x{ballot}:{name}"] = dict(device_ms=best["device_ms"], pass_ms=best["pass_ms"], pass_GBps=gbs)
+        print(f"items={items} minb={minb} ballot={ballot} {name}: device {best['device_ms']:.3f} ms, passes {best['pass_ms']:.3f} ms, {gbs:.0f} GB/s   [{regs}]", flush=True)
         pin.free()
     ctx.close()
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_pass.json"), "w"), indent=1)
