@@ -127,7 +127,7 @@ hist_only_kernel(const uint64_t *__restrict__ keys, uint32_t count, radix::PassP
 }
 
 // ---- K4+K5: group heads, new ranks, singleton retirement, compaction -- one pass, decoupled look-back ----
-constexpr int kRankThreads = 256;
+constexpr int kRankThreads = 512;
 constexpr int kRankItems = 8;
 constexpr int kRankTile = kRankThreads * kRankItems;
 constexpr int kRankWarps = kRankThreads / 32;
@@ -140,6 +140,12 @@ __host__ __device__ __forceinline__ uint32_t rk_sum(uint64_t v) { return (uint32
 
 // keys/sa: the sorted active set (a entries).  slot_in == nullptr in round 0 (slot[k] = k).
 // Outputs: ISA, SA, the compacted next active set (sa_out, rank_out, slot_out) and *count_out = its size.
+//
+// Warp-striped: warp w of the tile owns 32*kRankItems consecutive positions, row j of lane l is position
+// base + j*32 + l, so every load and the compacted stores are coalesced.  Head flags and survivor flags live
+// as one ballot per row (uniform registers), which turns both scans into bit arithmetic:
+//   "slot of the last head at or before me" = shfl from the highest head bit at or below my lane,
+//   "survivors before me"                   = popc of the survivor ballot below my lane.
 template <bool ROUND0>
 __global__ void __launch_bounds__(kRankThreads)
 rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sa,
@@ -156,134 +162,137 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     if (tid == 0) s_tile = atomicAdd(tile_ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t k0 = tile * (uint32_t)kRankTile + tid * kRankItems;
+    const uint32_t wbase = tile * (uint32_t)kRankTile + warp * (32u * kRankItems);
 
-    // head[j] for j in [0, kRankItems]: does a group start at k0 + j?  (positions >= a count as heads)
-    uint64_t key[kRankItems + 1];
+    uint64_t key[kRankItems];
     uint32_t s[kRankItems], sl[kRankItems];
-    bool head[kRankItems + 1];
-    uint64_t prev_key = 0;
-    uint32_t prev_sa = 0;
-    if (k0 > 0 && k0 <= a) {
-        prev_key = keys[k0 - 1];
-        if (ROUND0) prev_sa = sa[k0 - 1];
-    }
-#pragma unroll
-    for (int j = 0; j <= kRankItems; ++j) key[j] = (k0 + j < a) ? keys[k0 + j] : 0ull;
+    unsigned hb[kRankItems + 1];  // hb[j] = ballot of "a group starts here" over row j; positions >= a count as heads
+    unsigned vb[kRankItems];      // ballot of k < a
 #pragma unroll
     for (int j = 0; j < kRankItems; ++j) {
-        s[j] = (k0 + j < a) ? sa[k0 + j] : 0u;
-        sl[j] = ROUND0 ? (k0 + j) : ((k0 + j < a) ? slot_in[k0 + j] : 0u);
+        const uint32_t k = wbase + j * 32 + lane;
+        const bool valid = k < a;
+        key[j] = valid ? keys[k] : 0ull;
+        s[j] = valid ? sa[k] : 0u;
+        sl[j] = ROUND0 ? k : (valid ? slot_in[k] : 0u);
     }
 #pragma unroll
-    for (int j = 0; j <= kRankItems; ++j) {
-        const uint32_t k = k0 + j;
-        bool hd;
-        if (k >= a || k == 0) {
-            hd = true;
-        } else {
-            const uint64_t pk = j == 0 ? prev_key : key[j - 1];
-            hd = key[j] != pk;
-            if (ROUND0) {
-                const uint32_t ps = j == 0 ? prev_sa : s[j - 1];
-                hd = hd || (n - ps < 8u);  // the previous suffix is shorter than the key: it stands alone
+    for (int j = 0; j < kRankItems; ++j) {
+        const uint32_t k = wbase + j * 32 + lane;
+        const bool valid = k < a;
+        // previous element: the lane to the left, or (lane 0) a reload of the element before the row
+        uint64_t pk = __shfl_up_sync(kFullMask, key[j], 1);
+        uint32_t ps = __shfl_up_sync(kFullMask, s[j], 1);
+        bool hd = true;
+        if (valid && k > 0) {
+            if (lane == 0) {
+                pk = keys[k - 1];
+                if (ROUND0) ps = sa[k - 1];
             }
+            hd = key[j] != pk;
+            if (ROUND0) hd = hd || (n - ps < 8u);  // the previous suffix is shorter than the key: it stands alone
         }
-        head[j] = hd;
+        hb[j] = __ballot_sync(kFullMask, hd);
+        vb[j] = __ballot_sync(kFullMask, valid);
+    }
+    {   // does a group start right after this warp's last position?
+        const uint32_t k = wbase + 32u * kRankItems;
+        bool hd = true;
+        if (lane == 31 && k < a) {
+            hd = keys[k] != key[kRankItems - 1];
+            if (ROUND0) hd = hd || (n - s[kRankItems - 1] < 8u);
+        }
+        hb[kRankItems] = __shfl_sync(kFullMask, hd ? 1u : 0u, 31);
     }
 
-    // thread-local: running "slot of the last head" and survivor count
-    uint32_t tmax = 0, tsum = 0;
+    // survivor ballots and the warp's aggregates
+    unsigned sb[kRankItems];
+    uint32_t wsum = 0, wmax = 0;
 #pragma unroll
     for (int j = 0; j < kRankItems; ++j) {
-        if (k0 + j < a) {
-            if (head[j]) tmax = sl[j];
-            if (!(head[j] && head[j + 1])) tsum++;
-        }
+        const unsigned next = (hb[j] >> 1) | ((hb[j + 1] & 1u) << 31);  // head flag of the element after each lane
+        sb[j] = vb[j] & ~(hb[j] & next);
+        wsum += __popc(sb[j]);
+        const unsigned hm = hb[j] & vb[j];
+        const uint32_t last = __shfl_sync(kFullMask, sl[j], hm ? 31 - __clz((int)hm) : 0);
+        if (hm) wmax = last;  // slots increase with position: the last head of the last row with one wins
     }
-    // block scan (max, sum)
-    uint32_t imax = tmax, isum = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t m = __shfl_up_sync(kFullMask, imax, o);
-        uint32_t c = __shfl_up_sync(kFullMask, isum, o);
-        if (lane >= (unsigned)o) {
-            imax = max(imax, m);
-            isum += c;
-        }
-    }
-    if (lane == 31) {
-        s_wmax[warp] = imax;
-        s_wsum[warp] = isum;
+    if (lane == 0) {
+        s_wmax[warp] = wmax;
+        s_wsum[warp] = wsum;
     }
     __syncthreads();
-    uint32_t wmax = 0, wsum = 0, bmax = 0, bsum = 0;
+    uint32_t emax = 0, esum = 0, bmax = 0, bsum = 0;
 #pragma unroll
     for (int w = 0; w < kRankWarps; ++w) {
         if ((unsigned)w < warp) {
-            wmax = max(wmax, s_wmax[w]);
-            wsum += s_wsum[w];
+            emax = max(emax, s_wmax[w]);
+            esum += s_wsum[w];
         }
         bmax = max(bmax, s_wmax[w]);
         bsum += s_wsum[w];
     }
-    // exclusive prefix of this thread inside the tile
-    uint32_t emax = __shfl_up_sync(kFullMask, imax, 1);
-    uint32_t esum = __shfl_up_sync(kFullMask, isum, 1);
-    if (lane == 0) {
-        emax = 0;
-        esum = 0;
-    }
-    emax = max(emax, wmax);
-    esum += wsum;
 
-    // tile prefix by decoupled look-back (thread 0)
-    if (tid == 0) {
+    // tile prefix by decoupled look-back: warp 0 inspects 32 predecessors per round trip
+    if (warp == 0) {
         const uint64_t agg = rk_pack(bmax, bsum);
-        uint64_t excl = 0;
+        uint32_t xm = 0, xs = 0;
         if (tile > 0) {
-            st_desc(lb + tile, ((uint64_t)radix::kStatusAggregate << 62) | agg);
-            uint32_t t = tile - 1;
-            uint32_t xm = 0, xs = 0;
+            if (lane == 0) st_desc(lb + tile, ((uint64_t)radix::kStatusAggregate << 62) | agg);
+            int64_t base = (int64_t)tile - 1;
             for (;;) {
-                uint64_t v = ld_desc(lb + t);
-                unsigned st = (unsigned)(v >> 62);
-                if (st == 0) {
+                const int64_t t = base - lane;
+                // before tile 0 there is nothing: a virtual inclusive descriptor of zero ends the walk
+                const uint64_t v = t >= 0 ? ld_desc(lb + t) : ((uint64_t)radix::kStatusInclusive << 62);
+                const unsigned st = (unsigned)(v >> 62);
+                const unsigned ready = __ballot_sync(kFullMask, st != 0);
+                const unsigned incl = __ballot_sync(kFullMask, st == radix::kStatusInclusive);
+                // lanes up to (and including) the nearest inclusive predecessor must all be published
+                const unsigned need = incl ? (0xffffffffu >> (31 - (__ffs((int)incl) - 1))) : 0xffffffffu;
+                if ((ready & need) != need) {
                     DQ_SPIN_HINT();
                     continue;
                 }
-                xm = max(xm, rk_max(v));
-                xs += rk_sum(v);
-                if (st == radix::kStatusInclusive) break;
-                --t;
+                const bool mine = (need >> lane) & 1u;
+                xm = max(xm, __reduce_max_sync(kFullMask, mine ? rk_max(v) : 0u));
+                xs += __reduce_add_sync(kFullMask, mine ? rk_sum(v) : 0u);
+                if (incl) break;
+                base -= 32;
             }
-            excl = rk_pack(xm, xs);
         }
-        const uint64_t incl = rk_pack(max(rk_max(excl), bmax), rk_sum(excl) + bsum);
-        st_desc(lb + tile, ((uint64_t)radix::kStatusInclusive << 62) | incl);
-        s_excl = excl;
-        if ((uint64_t)(tile + 1) * kRankTile >= a) *count_out = rk_sum(incl);
+        if (lane == 0) {
+            const uint64_t excl = rk_pack(xm, xs);
+            const uint64_t inc = rk_pack(max(xm, bmax), xs + bsum);
+            st_desc(lb + tile, ((uint64_t)radix::kStatusInclusive << 62) | inc);
+            s_excl = excl;
+            if ((uint64_t)(tile + 1) * kRankTile >= a) *count_out = rk_sum(inc);
+        }
     }
     __syncthreads();
-    uint32_t run_max = max(emax, rk_max(s_excl));
-    uint32_t out = esum + rk_sum(s_excl);
+    uint32_t carry = max(emax, rk_max(s_excl));  // slot of the last head before this warp's chunk
+    uint32_t out = esum + rk_sum(s_excl);        // survivors before this warp's chunk
 
 #pragma unroll
     for (int j = 0; j < kRankItems; ++j) {
-        if (k0 + j < a) {
-            if (head[j]) run_max = sl[j];
-            const uint32_t nr = run_max;
-            if (head[j] && head[j + 1]) {
+        const unsigned hm = hb[j] & vb[j];
+        const unsigned le = hm & (0xffffffffu >> (31 - lane));  // heads at or below my lane
+        const uint32_t mine = __shfl_sync(kFullMask, sl[j], le ? 31 - __clz((int)le) : 0);
+        const uint32_t nr = le ? mine : carry;
+        const bool valid = (vb[j] >> lane) & 1u;
+        if (valid) {
+            if ((sb[j] >> lane) & 1u) {
+                const uint32_t o = out + __popc(sb[j] & lanemask_lt());
+                if (ROUND0 || nr != (uint32_t)(key[j] >> 32)) ISA[s[j]] = nr;
+                sa_out[o] = s[j];
+                rank_out[o] = nr;
+                slot_out[o] = sl[j];
+            } else {
                 SA[sl[j]] = (int32_t)s[j];
                 ISA[s[j]] = nr;
-            } else {
-                if (ROUND0 || nr != (uint32_t)(key[j] >> 32)) ISA[s[j]] = nr;
-                sa_out[out] = s[j];
-                rank_out[out] = nr;
-                slot_out[out] = sl[j];
-                out++;
             }
         }
+        out += __popc(sb[j]);
+        if (hm) carry = __shfl_sync(kFullMask, sl[j], 31 - __clz((int)hm));
     }
 }
 
