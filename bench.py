@@ -36,6 +36,16 @@ SAMPLE_OLD = 2 << 20
 SAMPLE_NEW = (2 << 20) + (1 << 17)
 
 
+def pass_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one round-0 onesweep launch from the committed ncu --set full
+    capture (profiles/r01_onesweep_pass_full_v2.md); per launch, like `achieved`."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_pass_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_round0_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -223,7 +233,6 @@ def main():
         step_device(True)
     barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: host buffers through the C ABI ------------------------------------------------
     ctx.set_timing(False)
@@ -240,7 +249,7 @@ def main():
         streams = ctx.bsdiff_streams(p_old.array, p_new.array)
     barrier()
     dt_e2e = time.perf_counter() - t1
-    e2e_launches = ctx.stats()["kernel_launches"]
+    clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device arm + e2e arm)
 
     # max over ranks
     if world > 1:
@@ -273,7 +282,9 @@ def main():
                          "algorithmic_bytes_per_pair": 24, "launches_timed": acc["passes"],
                          "share_of_device_time": acc["pass_ms"] / (acc["device_ms"] + acc["search_ms"])
                          if acc["device_ms"] else None,
-                         "traffic": None},
+                         "traffic": pass_traffic(),
+                         "traffic_note": "ncu capture of a round-0 launch (16,777,216 pairs, 402,653,184 algorithmic B); "
+                                         "achieved averages all launches of the step (round 0 and the smaller doubling rounds)"},
             "device_ms_per_step": {"sort": acc["device_ms"] / args.steps, "search": acc["search_ms"] / args.steps},
             "sort": {"rounds": acc["rounds"], "algorithmic_bytes": acc["alg_bytes"],
                      "input_MBps_device": n / (acc["device_ms"] / args.steps * 1e-3) / 1e6 if acc["device_ms"] else None,
