@@ -62,6 +62,12 @@ struct dq_ctx {
     DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
 
+    // pipelined D2H of the (pos, len) table for dq_cuda_bsdiff_streams
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t slice_ready[8] = {}, slice_done[8] = {};
+    int32_t slice_end[8] = {};
+    int slices_used = 0;
+
     // diff streams (host)
     dq::diffhost::Streams streams;
     PinBuf h_pos, h_len;
@@ -381,6 +387,14 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
         return fail("cudaDeviceGetAttribute", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
+    for (int i = 0; i < 8; ++i) {
+        if ((e = cudaEventCreateWithFlags(&ctx->slice_ready[i], cudaEventDisableTiming)) != cudaSuccess)
+            return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->slice_done[i], cudaEventDisableTiming)) != cudaSuccess)
+            return fail("cudaEventCreate", e);
+    }
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void **)&ctx->h_count, 64, cudaHostAllocDefault)) != cudaSuccess)
@@ -414,6 +428,11 @@ int dq_cuda_destroy(dq_ctx *ctx)
     if (ctx->h_len.p) cudaFreeHost(ctx->h_len.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 8; ++i) {
+        if (ctx->slice_ready[i]) cudaEventDestroy(ctx->slice_ready[i]);
+        if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DQ_OK;
@@ -560,19 +579,39 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     std::lock_guard<std::mutex> lock(ctx->mu);
     DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || new_), "bsdiff_streams: bad arguments"));
     DQ_CK(ctx, cudaSetDevice(ctx->device));
-    // Diff.cs:90 -- suffixSort.Sort(oldData, I[..^1]); the suffix array stays on the device
+    // Diff.cs:90 -- suffixSort.Sort(oldData, I[..^1]); the suffix array stays on the device.  `new` goes up on
+    // the copy stream while the sort runs.
     ctx->resident_n = -1;
+    DQ_TRY(ensure(ctx, ctx->newtext, (size_t)m + 64));
+    if (m) DQ_CK(ctx, cudaMemcpyAsync(ctx->newtext.p, new_, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
+    DQ_CK(ctx, cudaMemsetAsync(ctx->newtext.as<uint8_t>() + m, 0, 64, ctx->copy_stream));
+    DQ_CK(ctx, cudaEventRecord(ctx->slice_done[0], ctx->copy_stream));
     DQ_TRY(upload_text(ctx, ctx->text, old_, (uint32_t)n, cudaMemcpyHostToDevice));
     DQ_TRY(sort_resident(ctx, (uint32_t)n));
     ctx->resident_n = n;
-    // Diff.cs:106 for every scan position
+    DQ_CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slice_done[0], 0));
+    // Diff.cs:106 for every scan position, in slices whose D2H overlaps the later slices and the host loop
     DQ_TRY(ensure_pinned(ctx, ctx->h_pos, (size_t)m * 4 + 4));
     DQ_TRY(ensure_pinned(ctx, ctx->h_len, (size_t)m * 4 + 4));
-    DQ_TRY(search_common(ctx, old_, n, nullptr, new_, m, 0, m, static_cast<int32_t *>(ctx->h_pos.p),
-                         static_cast<int32_t *>(ctx->h_len.p), false));
-    // Diff.cs:100-223 on the host
-    dq::diffhost::greedy_emit(old_, n, new_, m, static_cast<const int32_t *>(ctx->h_pos.p),
-                              static_cast<const int32_t *>(ctx->h_len.p), ctx->streams);
+    int32_t *h_pos = static_cast<int32_t *>(ctx->h_pos.p), *h_len = static_cast<int32_t *>(ctx->h_len.p);
+    DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, 0, (uint32_t)m, h_pos, h_len));
+    // Diff.cs:100-223 on the host, consuming the table as its slices land
+    int next = 0;
+    int32_t ready_end = 0;
+    cudaError_t werr = cudaSuccess;
+    auto ready = [&](int32_t upto) {
+        if (upto > m) upto = m;
+        while (ready_end < upto && next < ctx->slices_used) {
+            cudaError_t e_ = cudaEventSynchronize(ctx->slice_done[next]);
+            if (e_ != cudaSuccess) werr = e_;
+            ready_end = ctx->slice_end[next++];
+        }
+    };
+    dq::diffhost::greedy_emit(old_, n, new_, m, h_pos, h_len, ctx->streams, ready);
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    DQ_CK(ctx, werr);
+    if (m) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_ms, ctx->ev0, ctx->ev1));
     export_streams(ctx, out);
     return DQ_OK;
 }

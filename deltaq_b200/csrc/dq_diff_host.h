@@ -41,6 +41,23 @@ inline uint32_t eq_mask32(const uint8_t *a, const uint8_t *b)
 #endif
 }
 
+// any of v[0..16) > 8 ?
+inline bool any_greater_than_8(const int32_t *v)
+{
+#if defined(__SSE2__)
+    const __m128i eight = _mm_set1_epi32(8);
+    __m128i g = _mm_cmpgt_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(v)), eight);
+    g = _mm_or_si128(g, _mm_cmpgt_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(v + 4)), eight));
+    g = _mm_or_si128(g, _mm_cmpgt_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(v + 8)), eight));
+    g = _mm_or_si128(g, _mm_cmpgt_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(v + 12)), eight));
+    return _mm_movemask_epi8(g) != 0;
+#else
+    for (int k = 0; k < 16; ++k)
+        if (v[k] > 8) return true;
+    return false;
+#endif
+}
+
 inline int32_t count_equal(const uint8_t *a, const uint8_t *b, int32_t len)
 {
     int32_t cnt = 0, k = 0;
@@ -58,8 +75,11 @@ inline void put_packed_long(std::vector<uint8_t> &out, int64_t y)
     out.insert(out.end(), b, b + 8);
 }
 
+// ready(upto): returns once table entries [0, min(upto, newLen)) are valid (the table may still be arriving from
+// the device in slices while the loop runs)
+template <typename Ready>
 inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
-                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out)
+                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out, Ready &&ready)
 {
     out.ctrl.clear();
     out.diff.clear();
@@ -74,6 +94,29 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
         int32_t oldscore = 0;
 
         for (int32_t scsc = scan += len; scan < newLen; scan++) {
+            ready(scan + 64);
+            // Block step over positions that cannot end the scan.  While oldscore == 0 and no byte of
+            // new[scan .. scan+kBlk+8) equals its partner at the current offset, nothing can be added to or
+            // taken from oldscore by the next kBlk positions (their matches are <= 8 long, so scsc stays inside
+            // that window): each of them evaluates "(len == 0 && len != 0) || len > 8" = false.  The reference
+            // would visit them one by one with the same outcome; scsc ends at the same running maximum.
+            {
+                constexpr int32_t kBlk = 16;
+                while (oldscore == 0 && scan + 32 + kBlk <= newLen && scsc <= scan + kBlk + 8 &&
+                       (int64_t)scan + lastoffset + 32 <= (int64_t)oldLen) {
+                    if (eq_mask32(oldData + scan + lastoffset, newData + scan) & 0x00ffffffu) break;
+                    if (any_greater_than_8(len_tab + scan)) break;
+                    int32_t e = scsc;
+                    for (int32_t i = 0; i < kBlk; ++i) {
+                        const int32_t t = scan + i + len_tab[scan + i];
+                        e = t > e ? t : e;
+                    }
+                    scsc = e;
+                    scan += kBlk;
+                    out.visits += kBlk;
+                    ready(scan + 64);
+                }
+            }
             len = len_tab[scan];
             pos = pos_tab[scan];
             out.visits++;
@@ -114,9 +157,14 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
                             }
                             continue;
                         }
-                        if (eq == 0) {  // the score only falls over this block: no update can happen
-                            i += 32;
-                            continue;
+                        {   // p matching bytes can lift the score by at most p inside the block: if even that
+                            // does not beat the running best, no statement of the loop body fires here
+                            const int32_t p = __builtin_popcount(eq);
+                            if (s * 2 - i + p <= sf * 2 - lenf) {
+                                s += p;
+                                i += 32;
+                                continue;
+                            }
                         }
                         for (int k = 0; k < 32; ++k) {
                             s += (int32_t)((eq >> k) & 1u);
@@ -158,9 +206,13 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
                             i++;
                             continue;
                         }
-                        if (eq == 0) {
-                            i += 32;
-                            continue;
+                        {
+                            const int32_t p = __builtin_popcount(eq);
+                            if (s * 2 - (i - 1) + p <= sb * 2 - lenb) {
+                                s += p;
+                                i += 32;
+                                continue;
+                            }
                         }
                         for (int k = 31; k >= 0; --k) {
                             s += (int32_t)((eq >> k) & 1u);
@@ -185,13 +237,36 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
                 const int32_t overlap = (lastscan + lenf) - (scan - lenb);
                 s = 0;
                 int32_t ss = 0, lens = 0;
-                for (int32_t i = 0; i < overlap; i++) {
-                    if (newData[lastscan + lenf - overlap + i] == oldData[lastpos + lenf - overlap + i]) s++;
-                    if (newData[scan - lenb + i] == oldData[pos - lenb + i]) s--;
+                // Diff.cs:172-188.  s <= ss holds after every step; over a 32-byte block s can rise by at most
+                // the number of positions where only the first comparison matches, so a block that cannot lift
+                // s above ss is applied in one step.
+                const uint8_t *n1 = newData + lastscan + lenf - overlap, *o1 = oldData + lastpos + lenf - overlap;
+                const uint8_t *n2 = newData + scan - lenb, *o2 = oldData + pos - lenb;
+                int32_t i = 0;
+                while (i < overlap) {
+                    if (i + 32 <= overlap) {
+                        const uint32_t ma = eq_mask32(n1 + i, o1 + i), mb = eq_mask32(n2 + i, o2 + i);
+                        if (s + __builtin_popcount(ma & ~mb) <= ss) {
+                            s += __builtin_popcount(ma) - __builtin_popcount(mb);
+                            i += 32;
+                            continue;
+                        }
+                        for (int k = 0; k < 32; ++k, ++i) {
+                            s += (int32_t)((ma >> k) & 1u) - (int32_t)((mb >> k) & 1u);
+                            if (s > ss) {
+                                ss = s;
+                                lens = i + 1;
+                            }
+                        }
+                        continue;
+                    }
+                    if (n1[i] == o1[i]) s++;
+                    if (n2[i] == o2[i]) s--;
                     if (s > ss) {
                         ss = s;
                         lens = i + 1;
                     }
+                    i++;
                 }
                 lenf += lens - overlap;
                 lenb -= lens;
@@ -226,6 +301,12 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
             lastoffset = pos - scan;
         }
     }
+}
+
+inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
+                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out)
+{
+    greedy_emit(oldData, oldLen, newData, newLen, pos_tab, len_tab, out, [](int32_t) {});
 }
 
 }  // namespace diffhost

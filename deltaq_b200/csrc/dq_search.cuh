@@ -574,11 +574,13 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
 // search, level B: one thread per chunk; writes the reference's (pos, len) for every position.
 __global__ void __launch_bounds__(kThreads)
 search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, const uint32_t *__restrict__ head_p,
-                    const uint32_t *__restrict__ head_l, int32_t *__restrict__ pos_out, int32_t *__restrict__ len_out)
+                    const uint32_t *__restrict__ head_l, int32_t *__restrict__ pos_out, int32_t *__restrict__ len_out,
+                    uint32_t chain_begin, uint32_t chain_end)
 {
-    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // chains [chain_begin, chain_end) of the search: lets the host pipeline the table in slices
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + chain_begin;
     const uint64_t k0 = c * kChunk;
-    if (k0 >= count) return;
+    if (c >= chain_end || k0 >= count) return;
     DQ_DBG(unsigned long long b0 = g_dbg.cmp_bytes + 64 * g_dbg.probes;)
     DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes + 64 * g_dbg.probes - b0; g_dbg.thr_max[1] = max(g_dbg.thr_max[1], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[1][k]++; } } fin{b0};)
     if (t.n == 0) {

@@ -62,9 +62,16 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
 
 // (ctx->text, ctx->sa, ctx->isa) describe `old` (n bytes); ctx->newtext holds `new` (m bytes, padded).
 // Fills ctx->s_pos / ctx->s_len [0, count).
-int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count)
+// h_pos/h_len != nullptr: pipeline mode for dq_cuda_bsdiff_streams -- the chain kernel runs in kSlices launches,
+// each followed by an asynchronous D2H of its slice on the copy stream; slice_end[] / slice_done[] tell the host
+// loop when a prefix of the table is usable.
+constexpr int kSlices = 8;
+
+int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count, int32_t *h_pos = nullptr,
+                    int32_t *h_len = nullptr)
 {
     ctx->stats.search_queries = (int32_t)count;
+    ctx->slices_used = 0;
     if (count == 0) return DQ_OK;
     DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     DQ_TRY(build_lcp(ctx, n));
@@ -92,13 +99,29 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
         DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin,
                   count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>());
     }
-    {
+    const int slices = h_pos ? kSlices : 1;
+    const uint32_t per = (uint32_t)div_up(div_up(chunks, slices), sr::kThreads) * sr::kThreads;  // chains per slice
+    ctx->slices_used = 0;
+    for (int sl = 0; sl < slices; ++sl) {
+        const uint32_t cb = std::min<uint64_t>((uint64_t)sl * per, chunks), ce = std::min<uint64_t>((uint64_t)(sl + 1) * per, chunks);
+        if (cb >= ce) break;
         auto k = sr::search_chain_kernel;
-        DQ_LAUNCH(k, (uint32_t)div_up(chunks, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
+        DQ_LAUNCH(k, (uint32_t)div_up(ce - cb, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
                   ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), ctx->s_pos.as<int32_t>(),
-                  ctx->s_len.as<int32_t>());
+                  ctx->s_len.as<int32_t>(), cb, ce);
+        ctx->stats.kernel_launches++;
+        if (h_pos) {
+            const uint64_t b = (uint64_t)cb * sr::kChunk, e = std::min<uint64_t>((uint64_t)ce * sr::kChunk, count);
+            DQ_CK(ctx, cudaEventRecord(ctx->slice_ready[sl], ctx->stream));
+            DQ_CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->slice_ready[sl], 0));
+            DQ_CK(ctx, cudaMemcpyAsync(h_pos + b, ctx->s_pos.as<int32_t>() + b, (e - b) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            DQ_CK(ctx, cudaMemcpyAsync(h_len + b, ctx->s_len.as<int32_t>() + b, (e - b) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            DQ_CK(ctx, cudaEventRecord(ctx->slice_done[sl], ctx->copy_stream));
+            ctx->slice_end[sl] = (int32_t)e;
+            ctx->slices_used = sl + 1;
+        }
     }
-    ctx->stats.kernel_launches += 2;
+    ctx->stats.kernel_launches += 1;
     DQ_CK(ctx, cudaGetLastError());
     DQ_CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     return DQ_OK;
