@@ -25,8 +25,15 @@
 namespace dq {
 namespace search {
 
-constexpr int kChunk = 64;              // positions per chain
-constexpr int kSuper = kChunk * kChunk; // positions per from-scratch search
+#ifndef DQ_SEARCH_CHUNK
+#define DQ_SEARCH_CHUNK 32
+#endif
+constexpr int kChunk = DQ_SEARCH_CHUNK; // positions per chain
+#ifndef DQ_SEARCH_HEADS
+#define DQ_SEARCH_HEADS 64
+#endif
+constexpr int kHeads = DQ_SEARCH_HEADS;  // chain heads walked by one warp of the head kernels
+constexpr int kSuper = kChunk * kHeads; // positions per from-scratch search
 constexpr int kThreads = 128;
 constexpr uint32_t kNone = 0xffffffffu;
 
@@ -460,7 +467,7 @@ lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
     const uint64_t i0 = sc * kSuper;
     if (i0 >= n) return;
     uint32_t l = 0;
-    for (int k = 0; k < kChunk; ++k) {
+    for (int k = 0; k < kHeads; ++k) {
         const uint64_t i64 = i0 + (uint64_t)k * kChunk;
         if (i64 >= n) break;
         const uint32_t i = (uint32_t)i64;
@@ -557,7 +564,7 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
     if (k0 >= count || t.n == 0) return;
     Carry cy{0, 0, false};
     bool have = false;
-    for (int k = 0; k < kChunk; ++k) {
+    for (int k = 0; k < kHeads; ++k) {
         const uint64_t kk = k0 + (uint64_t)k * kChunk;
         if (kk >= count) break;
         const uint32_t j = scan_begin + (uint32_t)kk;
