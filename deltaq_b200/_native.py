@@ -49,7 +49,8 @@ EXPORTS = [
     "dq_cuda_get_pass_times",
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
     "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
-    "dq_cuda_radix_sort_pairs",
+    "dq_cuda_radix_sort_pairs", "dq_cuda_radix_sort_pairs_device",
+    "dq_cuda_dist_pack", "dq_cuda_dist_partition", "dq_cuda_dist_round0", "dq_cuda_dist_requests", "dq_cuda_dist_round",
 ]
 
 
@@ -80,6 +81,12 @@ class Library:
         L.dq_cuda_bsdiff_streams.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_greedy_emit.argtypes = [vp, vp, i32, vp, i32, vp, vp, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
+        L.dq_cuda_radix_sort_pairs_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        L.dq_cuda_dist_pack.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.dq_cuda_dist_partition.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+        L.dq_cuda_dist_requests.argtypes = [vp, i64, vp, vp]
+        L.dq_cuda_dist_round0.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_int32)]
+        L.dq_cuda_dist_round.argtypes = [vp, vp, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_int32)]
         for name in EXPORTS:
             if name != "dq_cuda_last_error":
                 getattr(L, name).restype = ctypes.c_int
@@ -227,6 +234,42 @@ class Context:
     def radix_sort_pairs(self, keys, vals, key_bits=64):
         assert keys.dtype == np.uint64 and vals.dtype == np.uint32 and keys.size == vals.size
         self._check(self.lib.L.dq_cuda_radix_sort_pairs(self._h, _addr(keys), _addr(vals), keys.size, key_bits))
+
+    # ---- multi-GPU building blocks (raw device addresses) ----------------------------------------
+    def radix_sort_pairs_device(self, d_keys, d_vals, count, bit_lo, nbits, want_hist=False):
+        hist = np.zeros(256, dtype=np.int64) if want_hist else None
+        self._check(self.lib.L.dq_cuda_radix_sort_pairs_device(self._h, ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals),
+                                                               count, bit_lo, nbits, _addr(hist)))
+        return hist
+
+    def dist_pack(self, d_slice, pos_begin, pos_count, d_keys, d_vals, d_hist16):
+        self._check(self.lib.L.dq_cuda_dist_pack(self._h, ctypes.c_void_p(d_slice), pos_begin, pos_count,
+                                                 ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals),
+                                                 ctypes.c_void_p(d_hist16)))
+
+    def dist_partition(self, d_keys, d_vals, count, d_lut, d_keys_out, d_vals_out):
+        counts = np.zeros(256, dtype=np.int64)
+        self._check(self.lib.L.dq_cuda_dist_partition(self._h, ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals), count,
+                                                      ctypes.c_void_p(d_lut), ctypes.c_void_p(d_keys_out),
+                                                      ctypes.c_void_p(d_vals_out), _addr(counts)))
+        return counts
+
+    def dist_requests(self, h, d_q, d_idx):
+        self._check(self.lib.L.dq_cuda_dist_requests(self._h, int(h), ctypes.c_void_p(d_q), ctypes.c_void_p(d_idx)))
+
+    def dist_round0(self, d_keys, d_vals, count, n, slot_base, d_sa_local, d_upd_pos, d_upd_rank):
+        a = ctypes.c_int32(0)
+        self._check(self.lib.L.dq_cuda_dist_round0(self._h, ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals), count, n,
+                                                   slot_base, ctypes.c_void_p(d_sa_local), ctypes.c_void_p(d_upd_pos),
+                                                   ctypes.c_void_p(d_upd_rank), ctypes.byref(a)))
+        return a.value
+
+    def dist_round(self, d_r2, n, slot_base, d_sa_local, d_upd_pos, d_upd_rank):
+        a = ctypes.c_int32(0)
+        self._check(self.lib.L.dq_cuda_dist_round(self._h, ctypes.c_void_p(d_r2), n, slot_base,
+                                                  ctypes.c_void_p(d_sa_local), ctypes.c_void_p(d_upd_pos),
+                                                  ctypes.c_void_p(d_upd_rank), ctypes.byref(a)))
+        return a.value
 
     # ---- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr()) ---------------
     def suffix_sort_device(self, d_text, n, d_sa_out):

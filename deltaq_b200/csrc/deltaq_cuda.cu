@@ -51,7 +51,7 @@ struct dq_ctx {
     bool timing = false;
 
     // suffix-sort state (device)
-    DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist;
+    DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -61,6 +61,11 @@ struct dq_ctx {
     // search state (device)
     DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
+
+    // multi-GPU session (dq_cuda_dist_*): the unresolved set between calls
+    uint64_t *dist_kin = nullptr, *dist_kout = nullptr;
+    uint32_t *dist_vin = nullptr, *dist_vout = nullptr, *dist_slot_cur = nullptr, *dist_slot_nxt = nullptr;
+    uint32_t dist_a = 0, dist_cap = 0;
 
     // pipelined D2H of the (pos, len) table for dq_cuda_bsdiff_streams
     cudaStream_t copy_stream = nullptr;
@@ -203,9 +208,11 @@ uint32_t producer_grid(const dq_ctx *ctx, uint64_t items)
 }
 
 // rank_compact over the sorted active set; returns the next active count through ctx->h_count
-template <bool ROUND0>
+template <bool ROUND0, bool DIST = false>
 int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
-             uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a)
+             uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a,
+             int32_t *sa_array = nullptr, uint32_t slot_base = 0, uint64_t *upd_pos = nullptr,
+             uint32_t *upd_rank = nullptr)
 {
     const uint32_t tiles = (uint32_t)div_up(a, sx::kRankTile);
     const size_t bytes = 256 + (size_t)tiles * 8;
@@ -215,9 +222,10 @@ int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32
     uint32_t *ticket = reinterpret_cast<uint32_t *>(lbp);
     uint32_t *count = ticket + 1;
     uint64_t *desc = reinterpret_cast<uint64_t *>(lbp + 256);
-    auto k = sx::rank_compact_kernel<ROUND0>;
+    auto k = sx::rank_compact_kernel<ROUND0, DIST>;
     DQ_LAUNCH(k, tiles, sx::kRankThreads, 0, ctx->stream, keys, sa, slot_in, a, n, ctx->isa.as<uint32_t>(),
-              ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count);
+              sa_array ? sa_array : ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count, slot_base,
+              upd_pos, upd_rank);
     ctx->stats.kernel_launches++;
     DQ_CK(ctx, cudaGetLastError());
     DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -415,7 +423,7 @@ int dq_cuda_destroy(dq_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
-                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->newtext, &ctx->s_pos,
+                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -653,3 +661,215 @@ extern "C" void dq_emu_debug_counters(unsigned long long *out, int reset)
     if (reset) d = dq::search::DebugCounters{};
 }
 #endif
+
+// ======================================================================================================
+// multi-GPU building blocks
+namespace {
+
+int dist_reserve(dq_ctx *ctx, uint32_t count)
+{
+    const size_t c8 = (size_t)std::max<uint32_t>(count, 1) * 8, c4 = (size_t)std::max<uint32_t>(count, 1) * 4;
+    DQ_TRY(ensure(ctx, ctx->keyA, c8));
+    DQ_TRY(ensure(ctx, ctx->keyB, c8));
+    DQ_TRY(ensure(ctx, ctx->valA, c4));
+    DQ_TRY(ensure(ctx, ctx->valB, c4));
+    DQ_TRY(ensure(ctx, ctx->slotA, c4));
+    DQ_TRY(ensure(ctx, ctx->slotB, c4));
+    return DQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dq_cuda_dist_pack(dq_ctx *ctx, const uint8_t *d_slice, int32_t pos_begin, int32_t pos_count, uint64_t *d_keys,
+                      uint32_t *d_vals, uint64_t *d_hist16)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, pos_begin >= 0 && pos_count >= 0 && (pos_count == 0 || (d_slice && d_keys && d_vals)),
+                      "dist_pack: bad arguments"));
+    if (pos_count == 0) return DQ_OK;
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    auto k = sx::pack_slice_kernel;
+    DQ_LAUNCH(k, producer_grid(ctx, (uint64_t)pos_count), sx::kPackThreads, 0, ctx->stream, d_slice, (uint32_t)pos_begin,
+              (uint32_t)pos_count, d_keys, d_vals, reinterpret_cast<unsigned long long *>(d_hist16));
+    DQ_CK(ctx, cudaGetLastError());
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+// shared by the public entry point and dist_partition: sorts in place, optionally returns the first digit's counts
+static int radix_sort_device_locked(dq_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, int32_t count, int32_t bit_lo,
+                                    int32_t nbits, int64_t *hist_out_host)
+{
+    if (hist_out_host) std::fill(hist_out_host, hist_out_host + 256, (int64_t)0);
+    if (count == 0 || nbits == 0) return DQ_OK;
+    const size_t c8 = (size_t)count * 8, c4 = (size_t)count * 4;
+    // own scratch: keyA/keyB/valA/valB may hold a multi-GPU session's unresolved set
+    DQ_TRY(ensure(ctx, ctx->auxK, c8));
+    DQ_TRY(ensure(ctx, ctx->auxV, c4));
+    rx::PassPlan plan{};
+    rx::plan_add_field(plan, bit_lo, nbits);
+    DQ_TRY(zero_hist(ctx));
+    {
+        auto k = sx::hist_only_kernel;
+        DQ_LAUNCH(k, producer_grid(ctx, (uint64_t)count), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream, d_keys,
+                  (uint32_t)count, plan, ctx->hist.as<uint32_t>());
+    }
+    if (hist_out_host) {
+        uint32_t h32[256];
+        DQ_CK(ctx, cudaMemcpyAsync(h32, ctx->hist.p, sizeof h32, cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 256; ++i) hist_out_host[i] = h32[i];
+    }
+    SortBufs s{d_keys, ctx->auxK.as<uint64_t>(), d_vals, ctx->auxV.as<uint32_t>()};
+    DQ_TRY(run_passes(ctx, s, (uint32_t)count, plan, false));
+    if (s.kin != d_keys) {
+        DQ_CK(ctx, cudaMemcpyAsync(d_keys, s.kin, c8, cudaMemcpyDeviceToDevice, ctx->stream));
+        DQ_CK(ctx, cudaMemcpyAsync(d_vals, s.vin, c4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+int dq_cuda_radix_sort_pairs_device(dq_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, int32_t count, int32_t bit_lo,
+                                    int32_t nbits, int64_t *hist_out_host)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, count >= 0 && bit_lo >= 0 && nbits >= 0 && bit_lo + nbits <= 64 && (count == 0 || (d_keys && d_vals)),
+                      "radix_sort_pairs_device: bad arguments"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    return radix_sort_device_locked(ctx, d_keys, d_vals, count, bit_lo, nbits, hist_out_host);
+}
+
+int dq_cuda_dist_partition(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, int32_t count,
+                           const uint8_t *d_lut, uint64_t *d_keys_out, uint32_t *d_vals_out, int64_t *counts_out_host)
+{
+    if (!ctx || !counts_out_host) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, count >= 0 && d_lut && (count == 0 || (d_keys && d_vals && d_keys_out && d_vals_out)),
+                      "dist_partition: bad arguments"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    std::fill(counts_out_host, counts_out_host + 256, (int64_t)0);
+    if (count == 0) return DQ_OK;
+    // destination keys + identity permutation, one radix pass over them, then one gather of the tuples
+    DQ_TRY(ensure(ctx, ctx->partK, (size_t)count * 8));
+    DQ_TRY(ensure(ctx, ctx->partV, (size_t)count * 4));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up((uint64_t)count, 256), (uint64_t)ctx->sm_count * 16));
+    {
+        auto k = sx::dest_keys_kernel;
+        DQ_LAUNCH(k, grid, 256, 0, ctx->stream, d_keys, (uint32_t)count, d_lut, ctx->partK.as<uint64_t>(),
+                  ctx->partV.as<uint32_t>());
+    }
+    DQ_TRY(radix_sort_device_locked(ctx, ctx->partK.as<uint64_t>(), ctx->partV.as<uint32_t>(), count, 0, 8, counts_out_host));
+    {
+        auto k = sx::gather_pairs_kernel;
+        DQ_LAUNCH(k, grid, 256, 0, ctx->stream, d_keys, d_vals, ctx->partV.as<uint32_t>(), (uint32_t)count, d_keys_out,
+                  d_vals_out);
+    }
+    DQ_CK(ctx, cudaGetLastError());
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+int dq_cuda_dist_requests(dq_ctx *ctx, int64_t h, uint64_t *d_q, uint32_t *d_idx)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->dist_a == 0) return DQ_OK;
+    DQ_TRY(check_args(ctx, h >= 0 && d_q && d_idx, "dist_requests: bad arguments"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    const uint32_t a = ctx->dist_a;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up((uint64_t)a, 256), (uint64_t)ctx->sm_count * 16));
+    auto k = sx::requests_kernel;
+    DQ_LAUNCH(k, grid, 256, 0, ctx->stream, ctx->dist_vout, a, (uint64_t)h, d_q, d_idx);
+    DQ_CK(ctx, cudaGetLastError());
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+int dq_cuda_dist_round0(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, int32_t count, int32_t n,
+                        int32_t slot_base, int32_t *d_sa_local, uint64_t *d_upd_pos, uint32_t *d_upd_rank,
+                        int32_t *active_out)
+{
+    if (!ctx || !active_out) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DQ_TRY(check_args(ctx, count >= 0 && n >= 0 && slot_base >= 0 &&
+                               (count == 0 || (d_keys && d_vals && d_sa_local && d_upd_pos && d_upd_rank)),
+                      "dist_round0: bad arguments"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    ctx->resident_n = -1;
+    ctx->lcp_valid = false;
+    ctx->dist_a = 0;
+    *active_out = 0;
+    if (count == 0) return DQ_OK;
+    DQ_TRY(dist_reserve(ctx, (uint32_t)count));
+    const size_t c8 = (size_t)count * 8, c4 = (size_t)count * 4;
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->keyA.p, d_keys, c8, cudaMemcpyDeviceToDevice, ctx->stream));
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->valA.p, d_vals, c4, cudaMemcpyDeviceToDevice, ctx->stream));
+    rx::PassPlan plan{};
+    rx::plan_add_field(plan, 0, 64);
+    DQ_TRY(zero_hist(ctx));
+    {
+        auto k = sx::hist_only_kernel;
+        DQ_LAUNCH(k, producer_grid(ctx, (uint64_t)count), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream,
+                  ctx->keyA.as<uint64_t>(), (uint32_t)count, plan, ctx->hist.as<uint32_t>());
+    }
+    SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
+    DQ_TRY(run_passes(ctx, s, (uint32_t)count, plan, false));
+    uint32_t a = 0;
+    uint32_t *slot_cur = ctx->slotA.as<uint32_t>(), *slot_nxt = ctx->slotB.as<uint32_t>();
+    DQ_TRY((run_rank<true, true>(ctx, s.kin, s.vin, nullptr, (uint32_t)count, (uint32_t)n, s.vout,
+                                 reinterpret_cast<uint32_t *>(s.kout), slot_cur, &a, d_sa_local, (uint32_t)slot_base,
+                                 d_upd_pos, d_upd_rank)));
+    ctx->dist_kin = s.kin;
+    ctx->dist_kout = s.kout;
+    ctx->dist_vin = s.vin;
+    ctx->dist_vout = s.vout;
+    ctx->dist_slot_cur = slot_cur;
+    ctx->dist_slot_nxt = slot_nxt;
+    ctx->dist_a = a;
+    *active_out = (int32_t)a;
+    return DQ_OK;
+}
+
+int dq_cuda_dist_round(dq_ctx *ctx, const uint32_t *d_r2, int32_t n, int32_t slot_base, int32_t *d_sa_local,
+                       uint64_t *d_upd_pos, uint32_t *d_upd_rank, int32_t *active_out)
+{
+    if (!ctx || !active_out) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const uint32_t a = ctx->dist_a;
+    *active_out = 0;
+    if (a == 0) return DQ_OK;
+    DQ_TRY(check_args(ctx, n > 0 && d_r2 && d_sa_local && d_upd_pos && d_upd_rank, "dist_round: bad arguments"));
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    // active set: sa = dist_vout, rank = (uint32*)dist_kout, slot = dist_slot_cur; keys go to dist_kin
+    SortBufs s{ctx->dist_kin, ctx->dist_kout, ctx->dist_vin, ctx->dist_vout};
+    rx::PassPlan rp{};
+    rx::plan_add_field(rp, 0, bit_length((uint64_t)n));
+    rx::plan_add_field(rp, 32, bit_length(n > 1 ? (uint64_t)n - 1 : 1));
+    DQ_TRY(zero_hist(ctx));
+    {
+        auto k = sx::build_keys_r2_kernel;
+        DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream,
+                  reinterpret_cast<uint32_t *>(s.kout), d_r2, a, s.kin, rp, ctx->hist.as<uint32_t>());
+    }
+    std::swap(s.vin, s.vout);
+    DQ_TRY(run_passes(ctx, s, a, rp, true));
+    uint32_t next_a = 0;
+    DQ_TRY((run_rank<false, true>(ctx, s.kin, s.vin, ctx->dist_slot_cur, a, (uint32_t)n, s.vout,
+                                  reinterpret_cast<uint32_t *>(s.kout), ctx->dist_slot_nxt, &next_a, d_sa_local,
+                                  (uint32_t)slot_base, d_upd_pos, d_upd_rank)));
+    std::swap(ctx->dist_slot_cur, ctx->dist_slot_nxt);
+    ctx->dist_kin = s.kin;
+    ctx->dist_kout = s.kout;
+    ctx->dist_vin = s.vin;
+    ctx->dist_vout = s.vout;
+    ctx->dist_a = next_a;
+    *active_out = (int32_t)next_a;
+    return DQ_OK;
+}
+
+}  // extern "C"

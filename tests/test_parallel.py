@@ -91,3 +91,78 @@ def test_search_sharded_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     _run(2, "nccl", False)
+
+
+# ---- one text sorted by several ranks (distributed prefix doubling) ---------------------------------------
+
+def _sort_texts():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import adversarial_texts, load_asset, random_bytes
+    t = adversarial_texts()
+    out = {k: t[k] for k in ("zeros_tail", "all_zero_1000", "period8_zero_end", "fibonacci", "binary_random",
+                             "repeated_paragraph", "period3_tail0")}
+    out["fuzz3"] = load_asset("fuzz3")
+    out["crash-gosais"] = load_asset("crash-gosais-force-alloc")
+    out["random_20000"] = random_bytes(20000)
+    out["tiny_5"] = np.array([3, 1, 2, 1, 0], np.uint8)
+    out["single"] = np.array([9], np.uint8)
+    out["empty"] = np.zeros(0, np.uint8)
+    return out
+
+
+def _sort_worker(rank, world, port, backend, use_emu, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from deltaq_b200 import CudaSuffixSort
+    from deltaq_b200.parallel import suffix_sort_sharded
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    if use_emu:
+        import emu
+        sorter = CudaSuffixSort(_lib=emu.library())
+    else:
+        sorter = CudaSuffixSort(device=rank)
+    res = {}
+    for name, t in _sort_texts().items():
+        res[name] = suffix_sort_sharded(t, sorter)
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+    sorter.dispose()
+
+
+def _run_sort(world, backend, use_emu):
+    import torch.multiprocessing as mp
+    import oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sort_worker, args=(r, world, port, backend, use_emu, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    texts = _sort_texts()
+    for rank, res in results:
+        for name, t in texts.items():
+            assert np.array_equal(res[name], oracle.sais(t)), (rank, name)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_suffix_sort_sharded_gloo(world):
+    import emu
+    emu.build()
+    _run_sort(world, "gloo", True)
+
+
+@pytest.mark.gpu
+def test_suffix_sort_sharded_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    _run_sort(2, "nccl", False)
