@@ -61,6 +61,7 @@ if rank == 0:
     best = min(times)
     print(json.dumps({"workload": kind, "n": int(t.size), "n_gpus": world, "best_ms": best * 1e3,
                       "input_MBps": t.size / best / 1e6, "all_ms": [x * 1e3 for x in times], "sufcheck": ok,
-                      "phases_ms_rank0": {k: round(v * 1e3, 2) for k, v in prof.items()}}), flush=True)
+                      "phases_ms_rank0": {k: round(v * 1e3, 2) for k, v in prof.items() if k != "rounds"},
+                      "rounds": prof.get("rounds")}), flush=True)
 if world > 1:
     dist.destroy_process_group()
