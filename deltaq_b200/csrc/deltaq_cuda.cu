@@ -51,7 +51,8 @@ struct dq_ctx {
     bool timing = false;
 
     // suffix-sort state (device)
-    DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV;
+    DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
+        runtile;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -212,7 +213,8 @@ template <bool ROUND0, bool DIST = false>
 int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
              uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a,
              int32_t *sa_array = nullptr, uint32_t slot_base = 0, uint64_t *upd_pos = nullptr,
-             uint32_t *upd_rank = nullptr)
+             uint32_t *upd_rank = nullptr, const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr,
+             uint32_t hmin = 0, uint32_t *min_depth = nullptr)
 {
     const uint32_t tiles = (uint32_t)div_up(a, sx::kRankTile);
     const size_t bytes = 256 + (size_t)tiles * 8;
@@ -225,12 +227,13 @@ int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32
     auto k = sx::rank_compact_kernel<ROUND0, DIST>;
     DQ_LAUNCH(k, tiles, sx::kRankThreads, 0, ctx->stream, keys, sa, slot_in, a, n, ctx->isa.as<uint32_t>(),
               sa_array ? sa_array : ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count, slot_base,
-              upd_pos, upd_rank);
+              upd_pos, upd_rank, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr);
     ctx->stats.kernel_launches++;
     DQ_CK(ctx, cudaGetLastError());
-    DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 8, cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    *next_a = *ctx->h_count;
+    *next_a = ctx->h_count[0];
+    if (min_depth) *min_depth = ~ctx->h_count[1];  // the kernel keeps max(~depth) in a word that starts at 0
     return DQ_OK;
 }
 
@@ -260,13 +263,17 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     rx::PassPlan plan{};
     rx::plan_add_field(plan, 0, 64);
     DQ_TRY(zero_hist(ctx));
+    // counter of suffixes inside equal-byte runs, kept behind the histogram tables
+    uint32_t *uniform_count = ctx->hist.as<uint32_t>() + 2 * rx::kMaxPasses * rx::kRadix + 32;
+    DQ_CK(ctx, cudaMemsetAsync(uniform_count, 0, 4, ctx->stream));
     {
         auto k = sx::pack_keys_kernel;
         DQ_LAUNCH(k, producer_grid(ctx, n), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream,
                   ctx->text.as<uint8_t>(), n, ctx->keyA.as<uint64_t>(), ctx->valA.as<uint32_t>(), plan,
-                  ctx->hist.as<uint32_t>());
+                  ctx->hist.as<uint32_t>(), uniform_count);
         st.kernel_launches++;
     }
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count + 4, uniform_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
     DQ_TRY(run_passes(ctx, s, n, plan, false));
     st.rounds = 1;
@@ -278,23 +285,52 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     // sorted pairs are in (s.kin, s.vin); (s.kout, s.vout) are free
     DQ_TRY(run_rank<true>(ctx, s.kin, s.vin, nullptr, n, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_cur, &a));
 
-    // ---- doubling rounds over the unresolved suffixes
+    // ---- doubling rounds over the unresolved suffixes.  Every group carries its own depth (bytes its members
+    // share); h is the depth every rank in ISA is consistent to.  Round 1 refines equal-byte-run groups by run
+    // length in one step (dq_suffix.cuh), so zero padding does not cost log2(run length) rounds.
     const int bits_r2 = bit_length(n);                      // ISA[.]+1 in [0, n]
     const int bits_rank = bit_length(n > 1 ? n - 1 : 1);    // rank in [0, n-1]
     uint64_t h = 8;
+    uint32_t *depth_cur = nullptr, *depth_nxt = nullptr;
+    // Run-length refinement pays when a visible share of the text sits in equal-byte runs (zero padding); without
+    // such runs plain doubling (uniform depth, no depth arrays) is the shorter path.
+    const bool run_aware = a > 0 && (uint64_t)ctx->h_count[4] * 64 >= n;
+    if (run_aware) {
+        DQ_TRY(ensure(ctx, ctx->depthA, n4));
+        DQ_TRY(ensure(ctx, ctx->depthB, n4));
+        DQ_TRY(ensure(ctx, ctx->runend, n4));
+        const uint32_t ntiles = (uint32_t)div_up(n, sx::kRunTile);
+        DQ_TRY(ensure(ctx, ctx->runtile, (size_t)ntiles * 8));
+        uint32_t *tile_first = ctx->runtile.as<uint32_t>(), *next_after = tile_first + ntiles;
+        auto k1 = sx::run_tile_first_kernel;
+        DQ_LAUNCH(k1, ntiles, 256, 0, ctx->stream, ctx->text.as<uint8_t>(), n, tile_first);
+        auto k2 = sx::run_tile_scan_kernel;
+        DQ_LAUNCH(k2, 1, 1024, 0, ctx->stream, tile_first, ntiles, n, next_after);
+        auto k3 = sx::run_end_kernel;
+        DQ_LAUNCH(k3, ntiles, 256, 0, ctx->stream, ctx->text.as<uint8_t>(), n, next_after, ctx->runend.as<uint32_t>());
+        st.kernel_launches += 3;
+        depth_cur = ctx->depthA.as<uint32_t>();
+        depth_nxt = ctx->depthB.as<uint32_t>();
+    }
+    bool first = true;
     while (a > 0) {
-        // active set: sa = s.vout, rank = (uint32*)s.kout, slot = slot_cur.  Keys go to s.kin.
+        // active set: sa = s.vout, rank = (uint32*)s.kout, slot = slot_cur, depth = depth_cur.  Keys go to s.kin.
         rx::PassPlan rp{};
-        rx::plan_add_field(rp, 0, bits_r2);
+        rx::plan_add_field(rp, 0, (first && run_aware) ? 32 : bits_r2);
         rx::plan_add_field(rp, 32, bits_rank);
         DQ_TRY(zero_hist(ctx));
-        {
+        if (first && run_aware) {
+            auto k = sx::build_keys_round1_kernel;
+            DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream, s.vout,
+                      reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), ctx->text.as<uint8_t>(),
+                      ctx->runend.as<uint32_t>(), n, a, s.kin, depth_cur, rp, ctx->hist.as<uint32_t>());
+        } else {
             auto k = sx::build_keys_kernel;
             DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream, s.vout,
-                      reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), n, a, h, s.kin, rp,
+                      reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), n, a, h, depth_cur, s.kin, rp,
                       ctx->hist.as<uint32_t>());
-            st.kernel_launches++;
         }
+        st.kernel_launches++;
         // sort (s.kin, s.vout) using (s.kout, s.vin) as the alternate
         std::swap(s.vin, s.vout);
         DQ_TRY(run_passes(ctx, s, a, rp, true));
@@ -302,17 +338,31 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         st.active_sum += a;
         st.algorithmic_bytes += (int64_t)a * (52 + 24 * rp.npass);
 
-        uint32_t next_a = 0;
-        DQ_TRY(run_rank<false>(ctx, s.kin, s.vin, slot_cur, a, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_nxt,
-                               &next_a));
+        uint32_t next_a = 0, min_depth = 0;
+        DQ_TRY((run_rank<false, false>(ctx, s.kin, s.vin, slot_cur, a, n, s.vout, reinterpret_cast<uint32_t *>(s.kout),
+                                       slot_nxt, &next_a, nullptr, 0, nullptr, nullptr, depth_cur, depth_nxt, (uint32_t)h,
+                                       &min_depth)));
         std::swap(slot_cur, slot_nxt);
+        std::swap(depth_cur, depth_nxt);
         if (next_a > a) {
             ctx->err = "internal: active set grew";
             return DQ_ERR_INTERNAL;
         }
         a = next_a;
-        h *= 2;
-        if (h > ((uint64_t)1 << 40)) {
+        first = false;
+        // every rank is now consistent to the smallest depth of an unresolved group (2h for plain doubling; a run
+        // refined group may share fewer bytes than that)
+        if (!run_aware) {
+            h *= 2;
+            if (h > ((uint64_t)1 << 31)) h = (uint64_t)1 << 31;
+        } else if (a > 0) {
+            if (min_depth <= h && st.rounds > 2) {
+                ctx->err = "internal: group depth did not grow";
+                return DQ_ERR_INTERNAL;
+            }
+            h = min_depth;
+        }
+        if (st.rounds > 200) {
             ctx->err = "internal: doubling did not converge";
             return DQ_ERR_INTERNAL;
         }
@@ -423,7 +473,8 @@ int dq_cuda_destroy(dq_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
-                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->newtext, &ctx->s_pos,
+                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
+                      &ctx->runtile, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);

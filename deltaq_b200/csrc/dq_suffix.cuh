@@ -48,13 +48,15 @@ __device__ __forceinline__ uint64_t load_key8(const uint8_t *__restrict__ T, uin
 // 8 passes are accumulated on the way.  grid-stride; dynamic smem = npass*256*4.
 __global__ void __launch_bounds__(kPackThreads)
 pack_keys_kernel(const uint8_t *__restrict__ T, uint32_t n, uint64_t *__restrict__ keys,
-                 uint32_t *__restrict__ vals, radix::PassPlan plan, uint32_t *__restrict__ ghist)
+                 uint32_t *__restrict__ vals, radix::PassPlan plan, uint32_t *__restrict__ ghist,
+                 uint32_t *__restrict__ uniform_count)
 {
     DQ_DYN_SMEM(smem);
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
     for (int i = threadIdx.x; i < plan.npass * radix::kRadix; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const uint32_t chunk = kPackThreads * kPackItems;
+    uint32_t uniform = 0;  // suffixes whose 8-byte key is one repeated byte: they sit inside equal-byte runs
     for (uint64_t base = (uint64_t)blockIdx.x * chunk; base < n; base += (uint64_t)gridDim.x * chunk) {
 #pragma unroll
         for (int j = 0; j < kPackItems; ++j) {
@@ -65,18 +67,24 @@ pack_keys_kernel(const uint8_t *__restrict__ T, uint32_t n, uint64_t *__restrict
                 keys[k] = key;
                 vals[k] = i;
                 radix::hist_accumulate(sh, plan, key);
+                uniform += key == (key & 0xffull) * 0x0101010101010101ull;
             }
         }
     }
     __syncthreads();
     radix::hist_flush(sh, plan.npass, ghist);
+    uniform = __reduce_add_sync(kFullMask, uniform);
+    if (lane_id() == 0 && uniform) atomicAdd(uniform_count, uniform);
 }
 
-// K6: key[k] = rank[k] << 32 | (sa[k]+h < n ? ISA[sa[k]+h] + 1 : 0), plus the digit histograms.
+// K6: key[k] = rank[k] << 32 | (sa[k]+d < n ? ISA[sa[k]+d] + 1 : 0), plus the digit histograms.  d = depth[k],
+// the number of leading bytes the group of position k is known to share (per active-set position: sorting only
+// permutes inside groups, so the array stays put); depth == nullptr means the uniform depth h.
 __global__ void __launch_bounds__(kPackThreads)
 build_keys_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ rank,
                   const uint32_t *__restrict__ ISA, uint32_t n, uint32_t a, uint64_t h,
-                  uint64_t *__restrict__ keys, radix::PassPlan plan, uint32_t *__restrict__ ghist)
+                  const uint32_t *__restrict__ depth, uint64_t *__restrict__ keys, radix::PassPlan plan,
+                  uint32_t *__restrict__ ghist)
 {
     DQ_DYN_SMEM(smem);
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
@@ -94,7 +102,7 @@ build_keys_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ 
 #pragma unroll
         for (int j = 0; j < kPackItems; ++j) {
             uint64_t k = base + (uint64_t)j * kPackThreads + threadIdx.x;
-            uint64_t p = (uint64_t)s[j] + h;
+            uint64_t p = (uint64_t)s[j] + (depth && k < a ? (uint64_t)depth[k] : h);
             r2[j] = (k < a && p < n) ? __ldg(ISA + p) + 1u : 0u;
         }
 #pragma unroll
@@ -190,6 +198,134 @@ requests_kernel(const uint32_t *__restrict__ sa, uint32_t a, uint64_t h, uint64_
     }
 }
 
+// ---- equal-byte runs ----------------------------------------------------------------------------------------
+// Plain doubling needs log2(L) rounds for the suffixes inside a run of L equal bytes (zero padding in
+// executables: the 16 MiB exe-like workload kept 3.5 M suffixes unresolved for 15 rounds).  A suffix inside a run
+// of byte b with R bytes of the run left is b^R followed by the suffix at the run's end, which starts with a byte
+// c != b (or is empty).  Among suffixes with the same b:
+//     c < b (or text end):  shorter run first   (it differs from a longer run at offset R with c < b)
+//     c > b             :  longer run first, and the whole "c < b" class sorts before the "c > b" class.
+// So after round 0 the groups whose 8-byte key is b^8 are refined in ONE round by the 32-bit key
+// (class << 31 | R or 2^31-1-R), and the resulting subgroups share exactly their R run bytes: their depth is R,
+// and the next round compares the suffixes at the run ends.
+constexpr uint32_t kRunTile = 4096;        // positions per block of the run_end kernels
+constexpr uint32_t kDepthFromKey = 0xffffffffu;  // depth[] marker: "this group was refined by run length"
+
+// first run boundary (position j >= 1 with T[j] != T[j-1]) of every tile, or 0xffffffff
+__global__ void __launch_bounds__(256) run_tile_first_kernel(const uint8_t *__restrict__ T, uint32_t n,
+                                                              uint32_t *__restrict__ tile_first)
+{
+    __shared__ uint32_t s_min[8];
+    const uint64_t base = (uint64_t)blockIdx.x * kRunTile;
+    uint32_t mn = 0xffffffffu;
+    for (uint32_t o = threadIdx.x; o < kRunTile; o += 256) {
+        const uint64_t j = base + o;
+        if (j >= 1 && j < n && T[j] != T[j - 1]) mn = min(mn, (uint32_t)j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(kFullMask, mn, o));
+    if (lane_id() == 0) s_min[warp_id()] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mn = min(mn, s_min[w]);
+        tile_first[blockIdx.x] = mn;
+    }
+}
+
+// next_after[t] = first run boundary in any tile after t, or n.  One block; reverse exclusive min-scan.
+__global__ void __launch_bounds__(1024) run_tile_scan_kernel(const uint32_t *__restrict__ tile_first, uint32_t ntiles,
+                                                              uint32_t n, uint32_t *__restrict__ next_after)
+{
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (ntiles + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per, hi = min(ntiles, lo + per);
+    uint32_t mn = n;
+    for (uint32_t t = lo; t < hi; ++t) mn = min(mn, tile_first[t]);
+    s_part[threadIdx.x] = mn;
+    __syncthreads();
+    uint32_t run = n;  // min over the chunks of higher threads
+    for (uint32_t w = threadIdx.x + 1; w < 1024; ++w) run = min(run, s_part[w]);
+    for (uint32_t t = hi; t-- > lo;) {
+        next_after[t] = run;
+        run = min(run, tile_first[t]);
+    }
+}
+
+// run_end[i] = first position j > i with T[j] != T[i], or n
+__global__ void __launch_bounds__(256) run_end_kernel(const uint8_t *__restrict__ T, uint32_t n,
+                                                       const uint32_t *__restrict__ next_after,
+                                                       uint32_t *__restrict__ run_end)
+{
+    __shared__ uint32_t s_first[256];
+    constexpr uint32_t kPer = kRunTile / 256;  // 16 consecutive positions per thread
+    const uint64_t base = (uint64_t)blockIdx.x * kRunTile + (uint64_t)threadIdx.x * kPer;
+    uint8_t b[kPer + 1];
+#pragma unroll
+    for (uint32_t o = 0; o <= kPer; ++o) b[o] = base + o < n ? T[base + o] : 0;
+    // first boundary strictly after each of my positions that I can see (up to base + kPer)
+    uint32_t nxt[kPer];
+    uint32_t cur = 0xffffffffu;
+#pragma unroll
+    for (int o = (int)kPer - 1; o >= 0; --o) {
+        const uint64_t j = base + o + 1;  // boundary candidate between o and o+1
+        if (j < n && b[o + 1] != b[o]) cur = (uint32_t)j;
+        nxt[o] = cur;
+    }
+    // first boundary inside my 16 positions (j in (base, base+kPer], plus j = base itself seen from the left)
+    uint32_t mine = cur;  // = first boundary in (base, base + kPer]
+    s_first[threadIdx.x] = mine;
+    __syncthreads();
+    uint32_t after = next_after[blockIdx.x];  // first boundary in later tiles
+    // boundaries owned by later threads of this tile.  Thread t+1's window (base', base'+kPer] starts where mine ends.
+    for (uint32_t w = threadIdx.x + 1; w < 256; ++w) {
+        const uint32_t f = s_first[w];
+        if (f != 0xffffffffu) {
+            after = f;
+            break;
+        }
+    }
+#pragma unroll
+    for (uint32_t o = 0; o < kPer; ++o)
+        if (base + o < n) run_end[base + o] = min(min(nxt[o], after), n);
+}
+
+// K6 of round 1: groups whose 8-byte key is one repeated byte are refined by run length (see above) and marked
+// kDepthFromKey; every other group by ISA[sa+8]+1 with depth 8 (its new depth is then 16, like plain doubling).
+__global__ void __launch_bounds__(kPackThreads)
+build_keys_round1_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ rank,
+                         const uint32_t *__restrict__ ISA, const uint8_t *__restrict__ T,
+                         const uint32_t *__restrict__ run_end, uint32_t n, uint32_t a, uint64_t *__restrict__ keys,
+                         uint32_t *__restrict__ depth, radix::PassPlan plan, uint32_t *__restrict__ ghist)
+{
+    DQ_DYN_SMEM(smem);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < plan.npass * radix::kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = sa[k];
+        const uint64_t k8 = load_key8(T, s);
+        uint32_t r2, d;
+        if ((uint64_t)s + 8 <= n && k8 == (k8 & 0xffull) * 0x0101010101010101ull) {
+            const uint32_t e = run_end[s];
+            const uint32_t R = e - s;
+            const uint32_t bb = (uint32_t)(k8 & 0xffu);
+            const bool below = e >= n || T[e] < bb;
+            r2 = below ? R : (0x80000000u | (0x7fffffffu - R));
+            d = kDepthFromKey;
+        } else {
+            const uint64_t p = (uint64_t)s + 8;
+            r2 = p < n ? __ldg(ISA + p) + 1u : 0u;
+            d = 8;
+        }
+        const uint64_t key = ((uint64_t)rank[k] << 32) | r2;
+        keys[k] = key;
+        depth[k] = d;
+        radix::hist_accumulate(sh, plan, key);
+    }
+    __syncthreads();
+    radix::hist_flush(sh, plan.npass, ghist);
+}
+
 // digit histograms of an existing key array (used by dq_cuda_radix_sort_pairs only; the suffix sorter's
 // producers accumulate their histograms while they write the keys)
 __global__ void __launch_bounds__(kPackThreads)
@@ -237,7 +373,9 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     int32_t *__restrict__ SA, uint32_t *__restrict__ sa_out, uint32_t *__restrict__ rank_out,
                     uint32_t *__restrict__ slot_out, uint64_t *__restrict__ lb, uint32_t *__restrict__ tile_ticket,
                     uint32_t *__restrict__ count_out, uint32_t slot_base = 0, uint64_t *__restrict__ upd_pos = nullptr,
-                    uint32_t *__restrict__ upd_rank = nullptr)
+                    uint32_t *__restrict__ upd_rank = nullptr, const uint32_t *__restrict__ depth_in = nullptr,
+                    uint32_t *__restrict__ depth_out = nullptr, uint32_t hmin = 0,
+                    uint32_t *__restrict__ min_depth_inv = nullptr)
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_wmax[kRankWarps], s_wsum[kRankWarps];
@@ -356,6 +494,7 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     __syncthreads();
     uint32_t carry = max(emax, rk_max(s_excl));  // slot of the last head before this warp's chunk
     uint32_t out = esum + rk_sum(s_excl);        // survivors before this warp's chunk
+    uint32_t inv_min = 0;                        // max over my survivors of ~depth (0 = none)
 
 #pragma unroll
     for (int j = 0; j < kRankItems; ++j) {
@@ -376,6 +515,20 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                 sa_out[o] = s[j];
                 rank_out[o] = nr;
                 slot_out[o] = sl[j];
+                if (depth_out) {
+                    // bytes the (sub)group now shares: a run-length refined group shares exactly its run, any
+                    // other group gained at least hmin bytes (every rank is consistent to depth hmin)
+                    const uint32_t din = depth_in[wbase + j * 32 + lane];
+                    uint32_t dn;
+                    if (din == kDepthFromKey) {
+                        const uint32_t r2 = (uint32_t)key[j];
+                        dn = (r2 & 0x80000000u) ? 0x7fffffffu - (r2 & 0x7fffffffu) : r2;
+                    } else {
+                        dn = din + hmin;
+                    }
+                    depth_out[o] = dn;
+                    inv_min = max(inv_min, ~dn);
+                }
             } else {
                 SA[sl[j] - slot_base] = (int32_t)s[j];
                 if (!DIST) ISA[s[j]] = nr;
@@ -383,6 +536,11 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         }
         out += __popc(sb[j]);
         if (hm) carry = __shfl_sync(kFullMask, sl[j], 31 - __clz((int)hm));
+    }
+    if (min_depth_inv) {
+        // smallest depth among the unresolved groups = the depth every rank is consistent to next round
+        inv_min = __reduce_max_sync(kFullMask, inv_min);
+        if (lane == 0 && inv_min) atomicMax(min_depth_inv, inv_min);
     }
 }
 

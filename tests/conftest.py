@@ -79,4 +79,17 @@ def adversarial_texts():
     rep = np.tile(para, 24)
     rep[rng.integers(0, rep.size, 12)] = 32
     out["repeated_paragraph"] = rep
+    # equal-byte runs (run-length refinement of round 1): equal lengths, both classes (next byte below / above the
+    # run byte), runs touching each other and the text end
+    runs = []
+    for b, L, c in [(5, 40, 3), (5, 40, 9), (5, 41, 3), (5, 39, 9), (5, 40, 3), (0, 100, 1), (255, 100, 0), (5, 8, 3),
+                    (5, 9, 9), (7, 300, 7), (5, 40, 5)]:
+        runs.append(np.full(L, b, np.uint8))
+        runs.append(np.array([c, int(rng.integers(0, 256))], np.uint8))
+    out["runs_mixed"] = np.concatenate(runs)
+    out["runs_to_end"] = np.concatenate(runs + [np.full(64, 5, np.uint8)])
+    out["runs_two_bytes"] = np.concatenate([np.full(int(L), int(b), np.uint8)
+                                            for b, L in zip(rng.integers(0, 2, 60), rng.integers(1, 90, 60))])
+    out["runs_long_zero_islands"] = np.zeros(30000, np.uint8)
+    out["runs_long_zero_islands"][[5000, 5001, 12000, 20000, 20001, 20002, 29990]] = [9, 9, 1, 200, 0, 3, 7]
     return out
