@@ -61,6 +61,7 @@ struct dq_ctx {
 
     // search state (device)
     DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
+    int32_t runend_valid_n = -1;  // runend[] describes the resident text of this length (set by a run-aware sort)
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
 
     // multi-GPU session (dq_cuda_dist_*): the unresolved set between calls
@@ -245,6 +246,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     st.n = (int32_t)n;
     ctx->pass_events_used = 0;
     ctx->lcp_valid = false;
+    ctx->runend_valid_n = -1;
     if (n == 0) return DQ_OK;
 
     const size_t n8 = (size_t)n * 8, n4 = (size_t)n * 4;
@@ -309,6 +311,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         auto k3 = sx::run_end_kernel;
         DQ_LAUNCH(k3, ntiles, 256, 0, ctx->stream, ctx->text.as<uint8_t>(), n, next_after, ctx->runend.as<uint32_t>());
         st.kernel_launches += 3;
+        ctx->runend_valid_n = (int32_t)n;
         depth_cur = ctx->depthA.as<uint32_t>();
         depth_nxt = ctx->depthB.as<uint32_t>();
     }

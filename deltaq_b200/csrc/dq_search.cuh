@@ -116,14 +116,16 @@ __device__ __forceinline__ uint32_t common_prefix(const uint8_t *a, uint32_t la,
     return lim;
 }
 
-// warp-cooperative version: all 32 lanes call it with the same arguments and get the same result; each
-// step compares 256 bytes (lane l takes the 8 bytes at k + 8l)
+// warp-cooperative version: all 32 lanes call it with the same arguments and get the same result.  The first
+// step compares 256 bytes (lane l takes the 8 bytes at 8l) so that short matches cost one round trip; long
+// matches continue 1 KiB per step (four independent 8-byte words per lane per stream).
 __device__ __forceinline__ uint32_t common_prefix_warp(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
 {
     const uint32_t lim = min(la, lb);
     const uint32_t lane = lane_id();
-    for (uint32_t k = 0; k < lim; k += 256) {
-        const uint32_t off = k + lane * 8u;
+    if (lim == 0) return 0;
+    {
+        const uint32_t off = lane * 8u;
         uint64_t x = 0;
         if (off < lim) x = load64u(a + off) ^ load64u(b + off);
         DQ_DBG(g_dbg.cmp_bytes += 8;)
@@ -131,7 +133,27 @@ __device__ __forceinline__ uint32_t common_prefix_warp(const uint8_t *a, uint32_
         if (m) {
             const int first = __ffs((int)m) - 1;
             const uint64_t xx = __shfl_sync(kFullMask, x, first);
-            return min(k + (uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
+            return min((uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
+        }
+        if (lim <= 256) return lim;
+    }
+    for (uint32_t k = 256; k < lim; k += 1024) {
+        // word w of lane l covers bytes k + 256w + 8l: each of the four loads of a warp is one coalesced 256 B row
+        uint64_t x[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t off = k + 256u * w + lane * 8u;
+            x[w] = off < lim ? (load64u(a + off) ^ load64u(b + off)) : 0ull;
+        }
+        DQ_DBG(g_dbg.cmp_bytes += 32;)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const unsigned m = __ballot_sync(kFullMask, x[w] != 0);
+            if (m) {
+                const int first = __ffs((int)m) - 1;
+                const uint64_t xx = __shfl_sync(kFullMask, x[w], first);
+                return min(k + 256u * w + (uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
+            }
         }
     }
     return lim;
@@ -461,7 +483,8 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint8_t *__res
 // head_l[i / kChunk] = PLCP[i] for i % kChunk == 0.
 __global__ void __launch_bounds__(kThreads)
 lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
-                 const uint32_t *__restrict__ ISA, uint32_t *__restrict__ head_l)
+                 const uint32_t *__restrict__ ISA, uint32_t *__restrict__ head_l,
+                 const uint32_t *__restrict__ run_end)
 {
     const uint64_t sc = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t i0 = sc * kSuper;
@@ -476,7 +499,14 @@ lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
             l = 0;
         } else {
             const uint32_t q = (uint32_t)SA[r - 1];
-            const uint32_t known = l > (uint32_t)kChunk ? l - kChunk : 0;
+            uint32_t known = l > (uint32_t)kChunk ? l - kChunk : 0;
+            // both suffixes inside runs of the same byte: the shorter run is common prefix, no need to read it
+            // (zero padding: without this one warp walks up to a megabyte here and the kernel waits for it)
+            if (run_end && known == 0 && T[i] == T[q]) {
+                const uint32_t ri = run_end[i] - i, rq = run_end[q] - q;
+                const uint32_t skip = min(ri, rq);
+                if (skip >= 64) known = skip;
+            }
             l = known + common_prefix_warp(T + i + known, n - i - known, T + q + known, n - q - known);
         }
         if (lane_id() == 0) head_l[i / kChunk] = l;

@@ -33,7 +33,7 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
     {
         auto k = sr::lcp_heads_kernel;
         DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
-                  ctx->headl.as<uint32_t>());
+                  ctx->headl.as<uint32_t>(), ctx->runend_valid_n == (int32_t)n ? ctx->runend.as<uint32_t>() : nullptr);
     }
     {
         auto k = sr::lcp_chain_kernel;
@@ -132,6 +132,7 @@ int adopt_index(dq_ctx *ctx, const uint8_t *old_, uint32_t n, const int32_t *I, 
 {
     ctx->resident_n = -1;
     ctx->lcp_valid = false;
+    ctx->runend_valid_n = -1;
     DQ_TRY(upload_text(ctx, ctx->text, old_, n, kind));
     DQ_TRY(ensure(ctx, ctx->sa, (size_t)n * 4));
     DQ_TRY(ensure(ctx, ctx->isa, (size_t)n * 4));
