@@ -6,6 +6,7 @@
 #include "../../include/deltaq_cuda.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <string>
@@ -49,6 +50,7 @@ struct dq_ctx {
     std::string err;
     dq_stats stats{};
     bool timing = false;
+    int match_policy = 0;  // see run_passes; DQ_MATCH_POLICY overrides (tuning only)
 
     // suffix-sort state (device)
     DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
@@ -140,7 +142,14 @@ int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &pla
     uint32_t *gbase = ghist + rx::kMaxPasses * rx::kRadix;
     uint32_t *use_match = gbase + rx::kMaxPasses * rx::kRadix;
     auto scan = rx::scan_hist_kernel;
-    DQ_LAUNCH(scan, plan.npass, rx::kRadix, 0, ctx->stream, ghist, gbase, use_match, count, locally_ordered ? 1 : 0);
+    uint32_t force_mask = 0;
+    if (locally_ordered) {
+        // policy 0: every pass of a doubling round ranks with MATCH; 1: only the rank-field passes (shift >= 32);
+        // 2: always decide from the histogram
+        for (int p = 0; p < plan.npass; ++p)
+            if (ctx->match_policy == 0 || (ctx->match_policy == 1 && plan.shift[p] >= 32)) force_mask |= 1u << p;
+    }
+    DQ_LAUNCH(scan, plan.npass, rx::kRadix, 0, ctx->stream, ghist, gbase, use_match, count, force_mask);
     ctx->stats.kernel_launches++;
 
     const uint32_t tiles = (uint32_t)div_up(count, rx::kTile);
@@ -438,6 +447,7 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
     else
         cudaGetDevice(&dev);
     ctx->device = dev;
+    if (const char *mp = getenv("DQ_MATCH_POLICY")) ctx->match_policy = atoi(mp);
     auto fail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         delete ctx;

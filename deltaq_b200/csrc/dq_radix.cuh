@@ -74,14 +74,14 @@ __device__ __forceinline__ void hist_flush(const uint32_t *sh, int npass, uint32
 
 // exclusive scan of each pass's 256 counters: ghist[p][d] -> gbase[p][d].  grid = npass, block = 256.
 // Also decides how the pass ranks its items (see match_digit): use_match[p] = 1 when a warp row of 32 items is
-// expected to hold at most kMatchMaxDistinct distinct digits.  force_match: the caller knows the input is
-// locally ordered (doubling rounds: measured faster with MATCH on every pass), skip the estimate.
+// expected to hold at most kMatchMaxDistinct distinct digits.  force_mask bit p: the caller knows pass p's digits
+// are locally ordered (rank digits of the doubling rounds), skip the estimate there.
 constexpr float kMatchMaxDistinct = 16.0f;
 
 __global__ void __launch_bounds__(kRadix) scan_hist_kernel(const uint32_t *__restrict__ ghist,
                                                           uint32_t *__restrict__ gbase,
                                                           uint32_t *__restrict__ use_match, uint32_t total,
-                                                          int force_match)
+                                                          uint32_t force_mask)
 {
     __shared__ uint32_t warp_tot[kRadix / 32];
     __shared__ float warp_exp[kRadix / 32];
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kRadix) scan_hist_kernel(const uint32_t *__res
     if (d == 0) {
         float tot = 0.f;
         for (int w = 0; w < kRadix / 32; ++w) tot += warp_exp[w];
-        use_match[blockIdx.x] = (force_match || tot <= kMatchMaxDistinct) ? 1u : 0u;
+        use_match[blockIdx.x] = (((force_mask >> blockIdx.x) & 1u) || tot <= kMatchMaxDistinct) ? 1u : 0u;
     }
 }
 
