@@ -242,11 +242,11 @@ def main():
     p_new.array[:] = new
     streams = None
     for _ in range(args.warmup):
-        streams = ctx.bsdiff_streams(p_old.array, p_new.array)
+        streams = ctx.bsdiff_streams(p_old.array, p_new.array, copy=False)
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        streams = ctx.bsdiff_streams(p_old.array, p_new.array)
+        streams = ctx.bsdiff_streams(p_old.array, p_new.array, copy=False)   # the C ABI's own result: pointers + lengths
     barrier()
     dt_e2e = time.perf_counter() - t1
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device arm + e2e arm)
@@ -273,7 +273,8 @@ def main():
                        "parallelism": f"{world} x independent pairs (one process and context per GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": n + m, "d2h_bytes_per_step": 8 * m,
-                    "includes": "H2D old+new, sort, search, D2H (pos,len), host greedy scan/emit loop; streams "
+                    "includes": "H2D old+new, sort, search, D2H (pos,len) in slices overlapped with the host greedy scan/emit loop "
+                                "(2 host threads); result = context-owned ctrl/diff/extra buffers; streams "
                                 f"ctrl/diff/extra = {len(streams['ctrl'])}/{len(streams['diff'])}/{len(streams['extra'])} B"},
             "gpu_launches": acc["launches"],
             "roofline": {"bound": "hbm", "kernel": "dq::radix::onesweep_pass_kernel",

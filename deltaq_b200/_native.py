@@ -216,10 +216,19 @@ class Context:
                                                    _addr(pos), _addr(ln), ctypes.byref(out)))
         return self._streams(out)
 
-    def bsdiff_streams(self, old, new):
+    def bsdiff_streams(self, old, new, copy=True):
+        """copy=False returns numpy views of the context-owned buffers (valid until the next call on this
+        context) -- what a C caller of dq_cuda_bsdiff_streams gets; copy=True returns bytes objects."""
         out = DqDiffStreams()
         self._check(self.lib.L.dq_cuda_bsdiff_streams(self._h, _addr(old), old.size, _addr(new), new.size,
                                                       ctypes.byref(out)))
+        if not copy:
+            def view(ptr, n):
+                if not n:
+                    return np.zeros(0, dtype=np.uint8)
+                return np.frombuffer((ctypes.c_uint8 * n).from_address(ptr), dtype=np.uint8)
+            return {"ctrl": view(out.ctrl, out.ctrl_len), "diff": view(out.diff, out.diff_len),
+                    "extra": view(out.extra, out.extra_len), "search_visits": out.search_visits}
         return self._streams(out)
 
     @staticmethod

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
+    "-Xcompiler", "-fPIC,-O2,-pthread,-Wall,-Wno-unused-function",
     "-shared", "-cudart", "static",
 ]
 

@@ -679,7 +679,7 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
             ready_end = ctx->slice_end[next++];
         }
     };
-    dq::diffhost::greedy_emit(old_, n, new_, m, h_pos, h_len, ctx->streams, ready);
+    dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, h_pos, h_len, ctx->streams, ready);
     DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     DQ_CK(ctx, werr);

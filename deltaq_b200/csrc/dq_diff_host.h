@@ -10,7 +10,11 @@
 // reference's own single-byte step.
 #pragma once
 #include <cstdint>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -75,20 +79,188 @@ inline void put_packed_long(std::vector<uint8_t> &out, int64_t y)
     out.insert(out.end(), b, b + 8);
 }
 
+// One stop of the scan: forward/backward extension, overlap split and emission (Diff.cs:127-222).  lastscan/lastpos
+// chain from one stop to the next.
+struct EmitState {
+    int32_t lastscan = 0, lastpos = 0;
+};
+
+inline void emit_stop(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen, int32_t scan,
+                      int32_t pos, EmitState &st, Streams &out)
+{
+    int32_t &lastscan = st.lastscan, &lastpos = st.lastpos;
+                int32_t s = 0, sf = 0, lenf = 0;
+                {
+                    // Diff.cs:132-145.  Over a block whose bytes all match, s*2-i rises by one per byte, so if it
+                    // ends above the running best the last byte of the block is the (strictly improving) final
+                    // update, and if not there is no update at all: one step does the whole block.
+                    const int32_t span = (scan - lastscan) < (oldLen - lastpos) ? (scan - lastscan) : (oldLen - lastpos);
+                    const uint8_t *po = oldData + lastpos, *pn = newData + lastscan;
+                    int32_t i = 0;
+                    while (i < span) {
+                        if (i + 32 <= span) {
+                            const uint32_t eq = eq_mask32(po + i, pn + i);
+                            if (eq == 0xffffffffu) {
+                                s += 32;
+                                i += 32;
+                                if (s * 2 - i > sf * 2 - lenf) {
+                                    sf = s;
+                                    lenf = i;
+                                }
+                                continue;
+                            }
+                            {   // p matching bytes can lift the score by at most p inside the block: if even that
+                                // does not beat the running best, no statement of the loop body fires here
+                                const int32_t p = __builtin_popcount(eq);
+                                if (s * 2 - i + p <= sf * 2 - lenf) {
+                                    s += p;
+                                    i += 32;
+                                    continue;
+                                }
+                            }
+                            for (int k = 0; k < 32; ++k) {
+                                s += (int32_t)((eq >> k) & 1u);
+                                i++;
+                                if (s * 2 - i > sf * 2 - lenf) {
+                                    sf = s;
+                                    lenf = i;
+                                }
+                            }
+                            continue;
+                        }
+                        if (po[i] == pn[i]) s++;
+                        i++;
+                        if (s * 2 - i > sf * 2 - lenf) {
+                            sf = s;
+                            lenf = i;
+                        }
+                    }
+                }
+
+                int32_t lenb = 0;
+                if (scan < newLen) {
+                    s = 0;
+                    int32_t sb = 0;
+                    // Diff.cs:152-164, same block argument as the forward loop (walking backwards)
+                    const int32_t span = (scan - lastscan) < pos ? (scan - lastscan) : pos;
+                    int32_t i = 1;
+                    while (i <= span) {
+                        if (i + 31 <= span) {
+                            // bit k <-> step i + 31 - k (the block is read forwards, the loop walks backwards)
+                            const uint32_t eq = eq_mask32(oldData + pos - i - 31, newData + scan - i - 31);
+                            if (eq == 0xffffffffu) {
+                                s += 32;
+                                i += 31;
+                                if (s * 2 - i > sb * 2 - lenb) {
+                                    sb = s;
+                                    lenb = i;
+                                }
+                                i++;
+                                continue;
+                            }
+                            {
+                                const int32_t p = __builtin_popcount(eq);
+                                if (s * 2 - (i - 1) + p <= sb * 2 - lenb) {
+                                    s += p;
+                                    i += 32;
+                                    continue;
+                                }
+                            }
+                            for (int k = 31; k >= 0; --k) {
+                                s += (int32_t)((eq >> k) & 1u);
+                                if (s * 2 - i > sb * 2 - lenb) {
+                                    sb = s;
+                                    lenb = i;
+                                }
+                                i++;
+                            }
+                            continue;
+                        }
+                        if (oldData[pos - i] == newData[scan - i]) s++;
+                        if (s * 2 - i > sb * 2 - lenb) {
+                            sb = s;
+                            lenb = i;
+                        }
+                        i++;
+                    }
+                }
+
+                if (lastscan + lenf > scan - lenb) {
+                    const int32_t overlap = (lastscan + lenf) - (scan - lenb);
+                    s = 0;
+                    int32_t ss = 0, lens = 0;
+                    // Diff.cs:172-188.  s <= ss holds after every step; over a 32-byte block s can rise by at most
+                    // the number of positions where only the first comparison matches, so a block that cannot lift
+                    // s above ss is applied in one step.
+                    const uint8_t *n1 = newData + lastscan + lenf - overlap, *o1 = oldData + lastpos + lenf - overlap;
+                    const uint8_t *n2 = newData + scan - lenb, *o2 = oldData + pos - lenb;
+                    int32_t i = 0;
+                    while (i < overlap) {
+                        if (i + 32 <= overlap) {
+                            const uint32_t ma = eq_mask32(n1 + i, o1 + i), mb = eq_mask32(n2 + i, o2 + i);
+                            if (s + __builtin_popcount(ma & ~mb) <= ss) {
+                                s += __builtin_popcount(ma) - __builtin_popcount(mb);
+                                i += 32;
+                                continue;
+                            }
+                            for (int k = 0; k < 32; ++k, ++i) {
+                                s += (int32_t)((ma >> k) & 1u) - (int32_t)((mb >> k) & 1u);
+                                if (s > ss) {
+                                    ss = s;
+                                    lens = i + 1;
+                                }
+                            }
+                            continue;
+                        }
+                        if (n1[i] == o1[i]) s++;
+                        if (n2[i] == o2[i]) s--;
+                        if (s > ss) {
+                            ss = s;
+                            lens = i + 1;
+                        }
+                        i++;
+                    }
+                    lenf += lens - overlap;
+                    lenb -= lens;
+                }
+
+                {
+                    // Diff.cs:197-200
+                    const size_t at = out.diff.size();
+                    out.diff.resize(at + (size_t)(lenf > 0 ? lenf : 0));
+                    uint8_t *dst = out.diff.data() + at;
+                    const uint8_t *pn = newData + lastscan, *po = oldData + lastpos;
+                    int32_t i = 0;
+    #if defined(__SSE2__)
+                    for (; i + 16 <= lenf; i += 16)
+                        _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + i),
+                                         _mm_sub_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(pn + i)),
+                                                      _mm_loadu_si128(reinterpret_cast<const __m128i *>(po + i))));
+    #endif
+                    for (; i < lenf; i++) dst[i] = (uint8_t)(pn[i] - po[i]);
+                }
+
+                const int32_t extraLength = (scan - lenb) - (lastscan + lenf);
+                if (extraLength > 0)
+                    out.extra.insert(out.extra.end(), newData + lastscan + lenf, newData + lastscan + lenf + extraLength);
+
+                put_packed_long(out.ctrl, lenf);
+                put_packed_long(out.ctrl, extraLength);
+                put_packed_long(out.ctrl, (int64_t)((pos - lenb) - (lastpos + lenf)));
+
+
+    lastscan = scan - lenb;
+    lastpos = pos - lenb;
+}
+
 // ready(upto): returns once table entries [0, min(upto, newLen)) are valid (the table may still be arriving from
 // the device in slices while the loop runs)
-template <typename Ready>
-inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
-                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out, Ready &&ready)
+template <typename Ready, typename Sink>
+inline void greedy_scan(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
+                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out, Ready &&ready, Sink &&sink)
 {
-    out.ctrl.clear();
-    out.diff.clear();
-    out.extra.clear();
-    out.visits = 0;
-    out.diff.reserve((size_t)newLen);
-
     int32_t scan = 0, pos = 0, len = 0;
-    int32_t lastscan = 0, lastpos = 0, lastoffset = 0;
+    int32_t lastoffset = 0;
 
     while (scan < newLen) {
         int32_t oldscore = 0;
@@ -137,176 +309,87 @@ inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
         }
 
         if (len != oldscore || scan == newLen) {
-            int32_t s = 0, sf = 0, lenf = 0;
-            {
-                // Diff.cs:132-145.  Over a block whose bytes all match, s*2-i rises by one per byte, so if it
-                // ends above the running best the last byte of the block is the (strictly improving) final
-                // update, and if not there is no update at all: one step does the whole block.
-                const int32_t span = (scan - lastscan) < (oldLen - lastpos) ? (scan - lastscan) : (oldLen - lastpos);
-                const uint8_t *po = oldData + lastpos, *pn = newData + lastscan;
-                int32_t i = 0;
-                while (i < span) {
-                    if (i + 32 <= span) {
-                        const uint32_t eq = eq_mask32(po + i, pn + i);
-                        if (eq == 0xffffffffu) {
-                            s += 32;
-                            i += 32;
-                            if (s * 2 - i > sf * 2 - lenf) {
-                                sf = s;
-                                lenf = i;
-                            }
-                            continue;
-                        }
-                        {   // p matching bytes can lift the score by at most p inside the block: if even that
-                            // does not beat the running best, no statement of the loop body fires here
-                            const int32_t p = __builtin_popcount(eq);
-                            if (s * 2 - i + p <= sf * 2 - lenf) {
-                                s += p;
-                                i += 32;
-                                continue;
-                            }
-                        }
-                        for (int k = 0; k < 32; ++k) {
-                            s += (int32_t)((eq >> k) & 1u);
-                            i++;
-                            if (s * 2 - i > sf * 2 - lenf) {
-                                sf = s;
-                                lenf = i;
-                            }
-                        }
-                        continue;
-                    }
-                    if (po[i] == pn[i]) s++;
-                    i++;
-                    if (s * 2 - i > sf * 2 - lenf) {
-                        sf = s;
-                        lenf = i;
-                    }
-                }
-            }
-
-            int32_t lenb = 0;
-            if (scan < newLen) {
-                s = 0;
-                int32_t sb = 0;
-                // Diff.cs:152-164, same block argument as the forward loop (walking backwards)
-                const int32_t span = (scan - lastscan) < pos ? (scan - lastscan) : pos;
-                int32_t i = 1;
-                while (i <= span) {
-                    if (i + 31 <= span) {
-                        // bit k <-> step i + 31 - k (the block is read forwards, the loop walks backwards)
-                        const uint32_t eq = eq_mask32(oldData + pos - i - 31, newData + scan - i - 31);
-                        if (eq == 0xffffffffu) {
-                            s += 32;
-                            i += 31;
-                            if (s * 2 - i > sb * 2 - lenb) {
-                                sb = s;
-                                lenb = i;
-                            }
-                            i++;
-                            continue;
-                        }
-                        {
-                            const int32_t p = __builtin_popcount(eq);
-                            if (s * 2 - (i - 1) + p <= sb * 2 - lenb) {
-                                s += p;
-                                i += 32;
-                                continue;
-                            }
-                        }
-                        for (int k = 31; k >= 0; --k) {
-                            s += (int32_t)((eq >> k) & 1u);
-                            if (s * 2 - i > sb * 2 - lenb) {
-                                sb = s;
-                                lenb = i;
-                            }
-                            i++;
-                        }
-                        continue;
-                    }
-                    if (oldData[pos - i] == newData[scan - i]) s++;
-                    if (s * 2 - i > sb * 2 - lenb) {
-                        sb = s;
-                        lenb = i;
-                    }
-                    i++;
-                }
-            }
-
-            if (lastscan + lenf > scan - lenb) {
-                const int32_t overlap = (lastscan + lenf) - (scan - lenb);
-                s = 0;
-                int32_t ss = 0, lens = 0;
-                // Diff.cs:172-188.  s <= ss holds after every step; over a 32-byte block s can rise by at most
-                // the number of positions where only the first comparison matches, so a block that cannot lift
-                // s above ss is applied in one step.
-                const uint8_t *n1 = newData + lastscan + lenf - overlap, *o1 = oldData + lastpos + lenf - overlap;
-                const uint8_t *n2 = newData + scan - lenb, *o2 = oldData + pos - lenb;
-                int32_t i = 0;
-                while (i < overlap) {
-                    if (i + 32 <= overlap) {
-                        const uint32_t ma = eq_mask32(n1 + i, o1 + i), mb = eq_mask32(n2 + i, o2 + i);
-                        if (s + __builtin_popcount(ma & ~mb) <= ss) {
-                            s += __builtin_popcount(ma) - __builtin_popcount(mb);
-                            i += 32;
-                            continue;
-                        }
-                        for (int k = 0; k < 32; ++k, ++i) {
-                            s += (int32_t)((ma >> k) & 1u) - (int32_t)((mb >> k) & 1u);
-                            if (s > ss) {
-                                ss = s;
-                                lens = i + 1;
-                            }
-                        }
-                        continue;
-                    }
-                    if (n1[i] == o1[i]) s++;
-                    if (n2[i] == o2[i]) s--;
-                    if (s > ss) {
-                        ss = s;
-                        lens = i + 1;
-                    }
-                    i++;
-                }
-                lenf += lens - overlap;
-                lenb -= lens;
-            }
-
-            {
-                // Diff.cs:197-200
-                const size_t at = out.diff.size();
-                out.diff.resize(at + (size_t)(lenf > 0 ? lenf : 0));
-                uint8_t *dst = out.diff.data() + at;
-                const uint8_t *pn = newData + lastscan, *po = oldData + lastpos;
-                int32_t i = 0;
-#if defined(__SSE2__)
-                for (; i + 16 <= lenf; i += 16)
-                    _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + i),
-                                     _mm_sub_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(pn + i)),
-                                                  _mm_loadu_si128(reinterpret_cast<const __m128i *>(po + i))));
-#endif
-                for (; i < lenf; i++) dst[i] = (uint8_t)(pn[i] - po[i]);
-            }
-
-            const int32_t extraLength = (scan - lenb) - (lastscan + lenf);
-            if (extraLength > 0)
-                out.extra.insert(out.extra.end(), newData + lastscan + lenf, newData + lastscan + lenf + extraLength);
-
-            put_packed_long(out.ctrl, lenf);
-            put_packed_long(out.ctrl, extraLength);
-            put_packed_long(out.ctrl, (int64_t)((pos - lenb) - (lastpos + lenf)));
-
-            lastscan = scan - lenb;
-            lastpos = pos - lenb;
+            // Diff.cs:127-222 for this stop of the scan.  lastoffset (all the scan needs) does not depend on the
+            // extension results, so the emission may run on the consumer side (see greedy_emit_pipelined).
+            sink(scan, pos);
             lastoffset = pos - scan;
         }
     }
+}
+
+inline void reset_streams(Streams &out, int32_t newLen)
+{
+    out.ctrl.clear();
+    out.diff.clear();
+    out.extra.clear();
+    out.visits = 0;
+    out.diff.reserve((size_t)newLen);
+}
+
+// the whole loop on the calling thread
+template <typename Ready>
+inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
+                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out, Ready &&ready)
+{
+    reset_streams(out, newLen);
+    EmitState st;
+    greedy_scan(oldData, oldLen, newData, newLen, pos_tab, len_tab, out, ready,
+                [&](int32_t scan, int32_t pos) { emit_stop(oldData, oldLen, newData, newLen, scan, pos, st, out); });
 }
 
 inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
                         const int32_t *pos_tab, const int32_t *len_tab, Streams &out)
 {
     greedy_emit(oldData, oldLen, newData, newLen, pos_tab, len_tab, out, [](int32_t) {});
+}
+
+// Two host threads: the caller runs the scan (it may block on table slices still in flight from the device) and
+// hands every stop to a consumer thread that does the extensions and the emission.  The scan needs only
+// lastoffset = pos - scan from a stop, never the extension results, so both sides compute exactly what the
+// single-threaded loop computes, in the same order.
+template <typename Ready>
+inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
+                                  const int32_t *pos_tab, const int32_t *len_tab, Streams &out, Ready &&ready)
+{
+    reset_streams(out, newLen);
+    struct Stop {
+        int32_t scan, pos;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Stop> q;
+    bool done = false;
+    std::thread consumer([&]() {
+        EmitState st;
+        for (;;) {
+            Stop sp;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return done || !q.empty(); });
+                if (q.empty()) return;
+                sp = q.front();
+                q.pop_front();
+            }
+            emit_stop(oldData, oldLen, newData, newLen, sp.scan, sp.pos, st, out);
+        }
+    });
+    int64_t visits = 0;
+    Streams scan_side;  // the scan only counts visits; keep its counter off the consumer's Streams
+    greedy_scan(oldData, oldLen, newData, newLen, pos_tab, len_tab, scan_side, ready, [&](int32_t scan, int32_t pos) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            q.push_back(Stop{scan, pos});
+        }
+        cv.notify_one();
+    });
+    visits = scan_side.visits;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        done = true;
+    }
+    cv.notify_one();
+    consumer.join();
+    out.visits = visits;
 }
 
 }  // namespace diffhost
