@@ -608,11 +608,12 @@ __global__ void __launch_bounds__(256) block_min_kernel(const uint32_t *__restri
 // head_l = less).
 __global__ void __launch_bounds__(kThreads)
 search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint32_t *__restrict__ head_p,
-                    uint32_t *__restrict__ head_l)
+                    uint32_t *__restrict__ head_l, uint32_t super_begin, uint32_t super_end)
 {
-    const uint64_t sc = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // super-chunks [super_begin, super_end) of the search (the host pipelines the table in slices)
+    const uint64_t sc = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + super_begin;
     const uint64_t k0 = sc * kSuper;
-    if (k0 >= count || t.n == 0) return;
+    if (sc >= super_end || k0 >= count || t.n == 0) return;
     Carry cy{0, 0, false};
     bool have = false;
     for (int k = 0; k < kHeads; ++k) {
@@ -633,8 +634,9 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
 __global__ void __launch_bounds__(kThreads)
 search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, const uint32_t *__restrict__ head_p,
                     const uint32_t *__restrict__ head_l, int32_t *__restrict__ pos_out, int32_t *__restrict__ len_out,
-                    uint32_t chain_begin, uint32_t chain_end)
+                    uint32_t chain_begin, uint32_t chain_end, uint32_t heads_ready)
 {
+    // heads_ready: heads [0, heads_ready) have been computed (a slice's last chain cannot look at the next head)
     // chains [chain_begin, chain_end) of the search: lets the host pipeline the table in slices
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + chain_begin;
     const uint64_t k0 = c * kChunk;
@@ -657,7 +659,7 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
     // is never re-compared byte by byte.
     uint32_t np = 0, nl = 0, back = 0;
     bool nless = false;
-    if (k0 + kChunk < count) {
+    if (k0 + kChunk < count && c + 1 < heads_ready) {
         const uint32_t v = head_l[c + 1];
         nl = v & 0x7fffffffu;
         nless = (v >> 31) != 0;

@@ -94,21 +94,27 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
             lv += ((size_t)ix.size[l] + 63) & ~(size_t)63;
         }
     }
+    const int slices = h_pos ? kSlices : 1;
+    // All heads in one launch (sliced head launches are tail-bound each: measured slower end to end), then the
+    // chain kernel in slices of whole super-chunks.
+    const uint32_t supers_per = (uint32_t)div_up(supers, slices);
+    ctx->slices_used = 0;
     {
         auto k = sr::search_heads_kernel;
         DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin,
-                  count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>());
+                  count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), 0u, supers);
+        ctx->stats.kernel_launches++;
     }
-    const int slices = h_pos ? kSlices : 1;
-    const uint32_t per = (uint32_t)div_up(div_up(chunks, slices), sr::kThreads) * sr::kThreads;  // chains per slice
-    ctx->slices_used = 0;
     for (int sl = 0; sl < slices; ++sl) {
-        const uint32_t cb = std::min<uint64_t>((uint64_t)sl * per, chunks), ce = std::min<uint64_t>((uint64_t)(sl + 1) * per, chunks);
-        if (cb >= ce) break;
-        auto k = sr::search_chain_kernel;
-        DQ_LAUNCH(k, (uint32_t)div_up(ce - cb, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
-                  ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), ctx->s_pos.as<int32_t>(),
-                  ctx->s_len.as<int32_t>(), cb, ce);
+        const uint32_t sb = std::min<uint64_t>((uint64_t)sl * supers_per, supers), se = std::min<uint64_t>((uint64_t)(sl + 1) * supers_per, supers);
+        if (sb >= se) break;
+        const uint32_t cb = sb * sr::kHeads, ce = std::min<uint64_t>((uint64_t)se * sr::kHeads, chunks);
+        {
+            auto k = sr::search_chain_kernel;
+            DQ_LAUNCH(k, (uint32_t)div_up(ce - cb, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
+                      ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), ctx->s_pos.as<int32_t>(),
+                      ctx->s_len.as<int32_t>(), cb, ce, chunks);
+        }
         ctx->stats.kernel_launches++;
         if (h_pos) {
             const uint64_t b = (uint64_t)cb * sr::kChunk, e = std::min<uint64_t>((uint64_t)ce * sr::kChunk, count);
@@ -121,7 +127,6 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
             ctx->slices_used = sl + 1;
         }
     }
-    ctx->stats.kernel_launches += 1;
     DQ_CK(ctx, cudaGetLastError());
     DQ_CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     return DQ_OK;
