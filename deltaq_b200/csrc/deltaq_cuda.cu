@@ -184,14 +184,19 @@ int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &pla
             ep->shift = plan.shift[p];
             DQ_CK(ctx, cudaEventRecord(ep->a, ctx->stream));
         }
+#if DQ_PASS_PERSISTENT
+        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)ctx->sm_count * DQ_PASS_MIN_BLOCKS);
+#else
+        const uint32_t grid = tiles;
+#endif
         if (wide) {
             auto k = rx::onesweep_pass_kernel<uint64_t>;
-            DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
+            DQ_LAUNCH(k, grid, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
                       count, plan.shift[p], mask, gbase + p * rx::kRadix, reinterpret_cast<uint64_t *>(region),
                       tickets + p, use_match + p);
         } else {
             auto k = rx::onesweep_pass_kernel<uint32_t>;
-            DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
+            DQ_LAUNCH(k, grid, rx::kThreads, rx::pass_smem_bytes(), ctx->stream, s.kin, s.vin, s.kout, s.vout,
                       count, plan.shift[p], mask, gbase + p * rx::kRadix, reinterpret_cast<uint32_t *>(region),
                       tickets + p, use_match + p);
         }

@@ -22,6 +22,9 @@ constexpr int kMaxPasses = 8;
 #ifndef DQ_PASS_ITEMS
 #define DQ_PASS_ITEMS 16
 #endif
+#ifndef DQ_PASS_PERSISTENT
+#define DQ_PASS_PERSISTENT 0
+#endif
 #ifndef DQ_PASS_MIN_BLOCKS
 #define DQ_PASS_MIN_BLOCKS 3
 #endif
@@ -157,7 +160,10 @@ constexpr unsigned kStatusAggregate = 1, kStatusInclusive = 2;
 //   4. stable ranking (match_any within the warp, running per-warp counters that already include the tile
 //      and warp offsets) writes every key straight to its slot of the shared staging area;
 //   5. values (requested before the look-back) are staged through the same slots; coalesced write-out.
-constexpr int kLookWindow = 8;
+#ifndef DQ_LOOK_WINDOW
+#define DQ_LOOK_WINDOW 8
+#endif
+constexpr int kLookWindow = DQ_LOOK_WINDOW;
 
 constexpr size_t pass_smem_bytes()
 {
@@ -334,22 +340,32 @@ onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
     uint32_t *smisc = sout + kRadix;
 
     const unsigned tid = threadIdx.x;
-    if (tid == 0) {
-        smisc[0] = atomicAdd(tile_ticket, 1u);
-        smisc[16] = *use_match;
+    const uint32_t ntiles = (count + (uint32_t)kTile - 1u) / (uint32_t)kTile;
+#if DQ_PASS_PERSISTENT
+    // persistent CTAs: each takes tickets until the tiles run out (no wave quantisation, no CTA relaunch)
+    for (;;) {
+#endif
+        if (tid == 0) {
+            smisc[0] = atomicAdd(tile_ticket, 1u);
+            smisc[16] = *use_match;
+        }
+        for (int i = tid; i < kWarps * kRadix; i += kThreads) whist[i] = 0;
+        __syncthreads();
+        const uint32_t tile = smisc[0];
+        const bool few = smisc[16] != 0;
+        if (tile >= ntiles) return;
+        const uint32_t tile_base = tile * (uint32_t)kTile;
+        const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
+        if (tile_count == (uint32_t)kTile)
+            onesweep_tile<DescT, true>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals,
+                                       whist, sout, smisc, few);
+        else
+            onesweep_tile<DescT, false>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals,
+                                        whist, sout, smisc, few);
+#if DQ_PASS_PERSISTENT
+        __syncthreads();  // the staging area and smisc are reused by the next tile
     }
-    for (int i = tid; i < kWarps * kRadix; i += kThreads) whist[i] = 0;
-    __syncthreads();
-    const uint32_t tile = smisc[0];
-    const bool few = smisc[16] != 0;
-    const uint32_t tile_base = tile * (uint32_t)kTile;
-    const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
-    if (tile_count == (uint32_t)kTile)
-        onesweep_tile<DescT, true>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
-                                   sout, smisc, few);
-    else
-        onesweep_tile<DescT, false>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals, whist,
-                                    sout, smisc, few);
+#endif
 }
 
 }  // namespace radix
