@@ -170,6 +170,10 @@ struct Texts {
     const uint8_t *old_;
     const uint8_t *new_;
     uint32_t n, m;
+    // run_end arrays of both texts (dq_suffix.cuh), or nullptr: lets a comparison jump over an equal-byte run that
+    // both sides are inside of (zero padding) instead of reading it
+    const uint32_t *run_old = nullptr;
+    const uint32_t *run_new = nullptr;
 };
 
 // lcp of old suffix p with the query at j, given that the first `known` bytes agree; *less = (suffix < query)
@@ -178,6 +182,13 @@ template <bool WARP = false>
 __device__ __forceinline__ uint32_t match_from(const Texts &t, uint32_t p, uint32_t j, uint32_t known, bool *less)
 {
     const uint32_t la = t.n - p, lq = t.m - j;
+    if (t.run_old && la - known >= 8 && lq - known >= 8) {
+        const uint64_t wa = load64u(t.old_ + p + known), wb = load64u(t.new_ + j + known);
+        if (wa == wb && wa == (wa & 0xffull) * 0x0101010101010101ull) {
+            const uint32_t a0 = p + known, b0 = j + known;
+            known += min(t.run_old[a0] - a0, t.run_new[b0] - b0);  // >= 8: both runs cover the word just read
+        }
+    }
     const uint32_t c = known + common_prefix_t<WARP>(t.old_ + p + known, la - known, t.new_ + j + known, lq - known);
     if (c == la)
         *less = c < lq;
@@ -248,6 +259,64 @@ __device__ __forceinline__ Bracket locate_scratch(const Texts &t, const Index &i
     bool dummy;
     if (lo_virtual) llo = lo >= 0 ? match_from<WARP>(t, (uint32_t)ix.SA[lo], j, 0, &dummy) : 0u;
     if (hi_virtual) lhi = hi < (int64_t)n ? match_from<WARP>(t, (uint32_t)ix.SA[hi], j, 0, &dummy) : 0u;
+    return Bracket{(uint32_t)hi, llo, lhi};
+}
+
+// locate_scratch that gives up (*aborted) as soon as one probe shares `cap` more bytes than known with the query:
+// the cheap, fully parallel first pass of the head kernel -- queries inside long matches abort after a few
+// probes and are left to the inheriting pass, queries in unrelated data (short matches) finish here.
+__device__ __forceinline__ Bracket locate_scratch_capped(const Texts &t, const Index &ix, uint32_t j, uint32_t cap,
+                                                         bool *aborted)
+{
+    const uint32_t n = t.n;
+    int64_t lo = -1, hi = n;
+    uint32_t llo = 0, lhi = 0;
+    bool lo_virtual = true, hi_virtual = true;
+    *aborted = false;
+    if (t.m - j >= 2) {
+        const uint32_t k = ((uint32_t)t.new_[j] << 8) | t.new_[j + 1];
+        lo = (int64_t)ix.bkt_lo[k] - 1;
+        hi = ix.bkt_hi[k];
+        llo = lhi = 2;
+    } else {
+        lo_virtual = hi_virtual = false;
+    }
+    const uint32_t lq = t.m - j;
+    auto probe = [&](uint32_t p, uint32_t known, bool *less) -> uint32_t {
+        const uint32_t la = n - p;
+        const uint32_t ra = la - known, rq = lq - known;
+        const uint32_t c = known + common_prefix(t.old_ + p + known, min(ra, cap), t.new_ + j + known, min(rq, cap));
+        if (c - known >= cap && ra > cap && rq > cap) {
+            *aborted = true;
+            return c;
+        }
+        if (c == la)
+            *less = c < lq;
+        else if (c == lq)
+            *less = false;
+        else
+            *less = t.old_[p + c] < t.new_[j + c];
+        return c;
+    };
+    while (hi - lo > 1) {
+        const uint32_t mid = (uint32_t)((lo + hi) >> 1);
+        bool less = false;
+        const uint32_t c = probe((uint32_t)ix.SA[mid], min(llo, lhi), &less);
+        if (*aborted) return Bracket{0, 0, 0};
+        if (less) {
+            lo = mid;
+            llo = c;
+            lo_virtual = false;
+        } else {
+            hi = mid;
+            lhi = c;
+            hi_virtual = false;
+        }
+    }
+    bool dummy = false;
+    if (lo_virtual) llo = lo >= 0 ? probe((uint32_t)ix.SA[lo], 0, &dummy) : 0u;
+    if (hi_virtual) lhi = hi < (int64_t)n ? probe((uint32_t)ix.SA[hi], 0, &dummy) : 0u;
+    if (*aborted) return Bracket{0, 0, 0};
     return Bracket{(uint32_t)hi, llo, lhi};
 }
 
@@ -614,14 +683,53 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
     const uint64_t sc = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + super_begin;
     const uint64_t k0 = sc * kSuper;
     if (sc >= super_end || k0 >= count || t.n == 0) return;
+    // pass 1, lanes in parallel: every head tries a capped from-scratch search on its own.  Heads in unrelated
+    // data (short matches, no inheritance possible anyway) finish here; heads inside long matches give up after a
+    // few probes.  Without this pass a warp over a mutated region runs kHeads binary searches back to back.
+    constexpr int kPerLane = kHeads / 32;
+    static_assert(kHeads % 32 == 0, "heads per warp must be a multiple of the warp size");
+    constexpr uint32_t kAbort = 0xffffffffu;
+    uint32_t rp[kPerLane], rl[kPerLane];
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q) {
+        const uint64_t kk = k0 + ((uint64_t)lane_id() * kPerLane + q) * kChunk;
+        rp[q] = 0;
+        rl[q] = kAbort;
+        if (kk < count) {
+            bool aborted;
+            const Bracket b = locate_scratch_capped(t, ix, scan_begin + (uint32_t)kk, 128u, &aborted);
+            if (!aborted) {
+                const Carry c1 = carry_of(t, ix, b);
+                rp[q] = c1.p;
+                rl[q] = c1.l | (c1.less ? 0x80000000u : 0u);
+            }
+        }
+    }
+    __syncwarp();
+    // pass 2, the warp together: the heads pass 1 left open inherit from their predecessor (or search from
+    // scratch with warp-cooperative comparisons)
     Carry cy{0, 0, false};
     bool have = false;
     for (int k = 0; k < kHeads; ++k) {
         const uint64_t kk = k0 + (uint64_t)k * kChunk;
         if (kk >= count) break;
         const uint32_t j = scan_begin + (uint32_t)kk;
-        const Bracket b = locate_step<true>(t, ix, j, cy, kChunk, have);
-        cy = carry_of(t, ix, b);
+        uint32_t p1 = 0, l1 = kAbort;
+#pragma unroll
+        for (int q = 0; q < kPerLane; ++q) {
+            const uint32_t pp = __shfl_sync(kFullMask, rp[q], k / kPerLane);
+            const uint32_t ll = __shfl_sync(kFullMask, rl[q], k / kPerLane);
+            if (k % kPerLane == q) {
+                p1 = pp;
+                l1 = ll;
+            }
+        }
+        if (l1 != kAbort) {
+            cy = Carry{p1, l1 & 0x7fffffffu, (l1 >> 31) != 0};
+        } else {
+            const Bracket b = locate_step<true>(t, ix, j, cy, kChunk, have);
+            cy = carry_of(t, ix, b);
+        }
         have = true;
         if (lane_id() == 0) {
             head_p[kk / kChunk] = cy.p;

@@ -81,6 +81,22 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
     DQ_TRY(ensure(ctx, ctx->headp, (size_t)chunks * 4));
     DQ_TRY(ensure(ctx, ctx->headl, (size_t)std::max<uint64_t>(chunks, div_up(n, sr::kChunk)) * 4));
     sr::Texts t{ctx->text.as<uint8_t>(), ctx->newtext.as<uint8_t>(), n, m};
+    if (ctx->runend_valid_n == (int32_t)n && m > 0) {
+        // the sort found `old` full of equal-byte runs: give the comparisons run ends of `new` as well
+        const uint32_t ntiles = (uint32_t)div_up(m, sx::kRunTile);
+        DQ_TRY(ensure(ctx, ctx->runend_new, (size_t)m * 4));
+        DQ_TRY(ensure(ctx, ctx->runtile, (size_t)std::max<uint64_t>(ntiles, div_up(n, sx::kRunTile)) * 8));
+        uint32_t *tile_first = ctx->runtile.as<uint32_t>(), *next_after = tile_first + ntiles;
+        auto k1 = sx::run_tile_first_kernel;
+        DQ_LAUNCH(k1, ntiles, 256, 0, ctx->stream, ctx->newtext.as<uint8_t>(), m, tile_first);
+        auto k2 = sx::run_tile_scan_kernel;
+        DQ_LAUNCH(k2, 1, 1024, 0, ctx->stream, tile_first, ntiles, m, next_after);
+        auto k3 = sx::run_end_kernel;
+        DQ_LAUNCH(k3, ntiles, 256, 0, ctx->stream, ctx->newtext.as<uint8_t>(), m, next_after, ctx->runend_new.as<uint32_t>());
+        ctx->stats.kernel_launches += 3;
+        t.run_old = ctx->runend.as<uint32_t>();
+        t.run_new = ctx->runend_new.as<uint32_t>();
+    }
     sr::Index ix{};
     ix.SA = ctx->sa.as<int32_t>();
     ix.ISA = ctx->isa.as<uint32_t>();
