@@ -263,6 +263,24 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     ctx->runend_valid_n = -1;
     if (n == 0) return DQ_OK;
 
+    if (n <= (uint32_t)sx::kSmallN) {
+        // one CTA, one launch (dq_suffix.cuh, "small inputs")
+        DQ_TRY(ensure(ctx, ctx->isa, (size_t)n * 4));
+        DQ_TRY(ensure(ctx, ctx->sa, (size_t)n * 4));
+        DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        auto k = sx::small_sort_kernel;
+        DQ_LAUNCH(k, 1, sx::kSmallThreads, sx::small_sort_smem_bytes(), ctx->stream, ctx->text.as<uint8_t>(), n,
+                  ctx->sa.as<int32_t>(), ctx->isa.as<uint32_t>());
+        DQ_CK(ctx, cudaGetLastError());
+        DQ_CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        DQ_CK(ctx, cudaEventElapsedTime(&st.device_ms, ctx->ev0, ctx->ev1));
+        st.rounds = 1;
+        st.kernel_launches = 1;
+        st.active_sum = n;
+        st.algorithmic_bytes = (int64_t)n * 5;
+        return DQ_OK;
+    }
     const size_t n8 = (size_t)n * 8, n4 = (size_t)n * 4;
     DQ_TRY(ensure(ctx, ctx->keyA, n8));
     DQ_TRY(ensure(ctx, ctx->keyB, n8));
@@ -480,6 +498,9 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
         return fail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(rx::onesweep_pass_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(sx::small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sx::small_sort_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
     *out = ctx;
     return DQ_OK;

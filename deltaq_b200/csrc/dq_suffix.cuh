@@ -544,5 +544,134 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     }
 }
 
+// ---- small inputs: the whole sort in one CTA ----------------------------------------------------------------
+// The multi-kernel path costs ~17 stream operations (~130 us) whatever n is; the reference's own benchmark
+// (bench/DeltaQ.Benchmarks/SuffixSortingBenchmarks.cs:27-53) is mostly sizes <= 32 KiB.  For n <= kSmallN one
+// CTA keeps text, keys, suffix indices and ISA in shared memory and runs the same prefix doubling with a bitonic
+// sort: one launch.  Round 0 orders equal 8-byte keys by descending suffix index (the end-of-text rule above).
+constexpr int kSmallN = 4096;
+constexpr int kSmallThreads = 1024;
+constexpr size_t small_sort_smem_bytes() { return (size_t)kSmallN * (8 + 4 + 4) + kSmallN + 64 + 256; }
+
+constexpr uint32_t kSmallPad = 0xffffffffu;  // index of the padding elements of the bitonic sort
+
+// (key ascending, suffix index descending), padding behind every real element
+__device__ __forceinline__ bool small_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib)
+{
+    return ka < kb || (ka == kb && ia != kSmallPad && (ib == kSmallPad || ia > ib));
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+small_sort_kernel(const uint8_t *__restrict__ T, uint32_t n, int32_t *__restrict__ SA, uint32_t *__restrict__ ISA)
+{
+    DQ_DYN_SMEM(smem);
+    uint64_t *key = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *idx = reinterpret_cast<uint32_t *>(smem + (size_t)kSmallN * 8);
+    uint32_t *isa = idx + kSmallN;
+    uint8_t *txt = reinterpret_cast<uint8_t *>(isa + kSmallN);
+    uint32_t *misc = reinterpret_cast<uint32_t *>(txt + kSmallN + 64);  // [0] = number of groups, [1..33] warp maxima
+    const unsigned tid = threadIdx.x;
+    uint32_t N = 1;
+    while (N < n) N <<= 1;  // bitonic size
+
+    for (uint32_t i = tid; i < (uint32_t)kSmallN + 64; i += kSmallThreads) txt[i] = i < n ? T[i] : 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < N; i += kSmallThreads) {
+        uint64_t k8 = ~0ull;
+        if (i < n) {
+            k8 = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) k8 = (k8 << 8) | txt[i + b];
+        }
+        key[i] = k8;
+        idx[i] = i < n ? i : kSmallPad;  // padding: largest key, and behind any real suffix that has that key too
+    }
+    __syncthreads();
+
+    for (uint64_t h = 8;; h *= 2) {
+        // bitonic sort of (key, idx) ascending by small_less
+        for (uint32_t size = 2; size <= N; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = tid; t < (N >> 1); t += kSmallThreads) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1));
+                    const uint32_t hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const uint64_t ka = key[lo], kb = key[hi];
+                    const uint32_t ia = idx[lo], ib = idx[hi];
+                    const bool swap = up ? small_less(kb, ib, ka, ia) : small_less(ka, ia, kb, ib);
+                    if (swap) {
+                        key[lo] = kb;
+                        key[hi] = ka;
+                        idx[lo] = ib;
+                        idx[hi] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // group heads and ranks (rank = position of the group head); positions >= n are padding
+        if (tid == 0) misc[0] = 0;
+        __syncthreads();
+        constexpr uint32_t kPer = kSmallN / kSmallThreads;  // 4 consecutive positions per thread
+        uint32_t head_pos[kPer];
+        uint32_t last = 0, heads = 0;
+#pragma unroll
+        for (uint32_t o = 0; o < kPer; ++o) {
+            const uint32_t k = tid * kPer + o;
+            bool hd = false;
+            if (k < n) {
+                hd = k == 0 || key[k] != key[k - 1];
+                if (h == 8 && k > 0 && n - idx[k - 1] < 8u) hd = true;  // the previous suffix is shorter than the key
+            }
+            if (hd) {
+                last = k;
+                heads++;
+            }
+            head_pos[o] = last;  // last head at or before k within this thread (0 if none yet)
+        }
+        // block max-scan of `last` (heads positions increase with k)
+        uint32_t incl = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
+            if (lane_id() >= (unsigned)o) incl = max(incl, v);
+        }
+        if (lane_id() == 31) misc[1 + warp_id()] = incl;
+        heads = __reduce_add_sync(kFullMask, heads);
+        if (lane_id() == 0 && heads) atomicAdd(&misc[0], heads);
+        __syncthreads();
+        uint32_t before = __shfl_up_sync(kFullMask, incl, 1);
+        if (lane_id() == 0) before = 0;
+        for (unsigned w = 0; w < warp_id(); ++w) before = max(before, misc[1 + w]);
+        // new keys need the ranks of the PREVIOUS round in isa[]: first ranks into registers, then all keys, then isa
+        uint32_t rk[kPer];
+#pragma unroll
+        for (uint32_t o = 0; o < kPer; ++o) rk[o] = max(head_pos[o], before);
+        const bool done = misc[0] == n;
+        __syncthreads();
+#pragma unroll
+        for (uint32_t o = 0; o < kPer; ++o) {
+            const uint32_t k = tid * kPer + o;
+            if (k < n) isa[idx[k]] = rk[o];
+        }
+        __syncthreads();
+        if (done) break;
+        const uint64_t hn = h;  // this round sorted to depth h; the next key looks h bytes ahead
+#pragma unroll
+        for (uint32_t o = 0; o < kPer; ++o) {
+            const uint32_t k = tid * kPer + o;
+            if (k < n) {
+                const uint64_t p = (uint64_t)idx[k] + hn;
+                key[k] = ((uint64_t)rk[o] << 32) | (p < n ? isa[p] + 1u : 0u);
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t k = tid; k < n; k += kSmallThreads) {
+        SA[k] = (int32_t)idx[k];
+        ISA[k] = isa[k];
+    }
+}
+
 }  // namespace suffix
 }  // namespace dq
