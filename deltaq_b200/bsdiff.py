@@ -40,14 +40,38 @@ def read_packed_long(b):
     return -y if b[7] & 0x80 else y
 
 
+_search_engine = None
+
+
+def _engine():
+    """The CudaSuffixSort whose context serves the match search when Diff.create is handed some OTHER
+    ISuffixSort provider (the reference's Diff.Create accepts any, Diff.cs:27)."""
+    global _search_engine
+    if _search_engine is None:
+        _search_engine = CudaSuffixSort()
+    return _search_engine
+
+
 def create_streams(old, new, suffix_sort):
-    """Uncompressed ctrl / diff / extra streams of Diff.Create for (old, new): GPU sort + GPU search +
-    host greedy loop.  ``suffix_sort`` must be a CudaSuffixSort."""
+    """Uncompressed ctrl / diff / extra streams of Diff.Create for (old, new).
+
+    With a CudaSuffixSort: sort + search on the GPU in one native call (the suffix array never leaves the device),
+    greedy loop on the host.  With any other provider exposing ``sort(text, suffixes)`` (the ISuffixSort contract):
+    that provider sorts (Diff.cs:90), the GPU answers every Search (Diff.cs:106) over its suffix array, and the
+    same host loop consumes the table."""
     o = as_bytes_array(old, "oldData")
     w = as_bytes_array(new, "newData")
-    if not isinstance(suffix_sort, CudaSuffixSort):
-        raise TypeError("create_streams needs a CudaSuffixSort")
-    return suffix_sort.context.bsdiff_streams(o, w)
+    if isinstance(suffix_sort, CudaSuffixSort):
+        return suffix_sort.context.bsdiff_streams(o, w)
+    if not hasattr(suffix_sort, "sort"):
+        raise TypeError("suffixSort must implement sort(text, suffixes)")
+    I = np.zeros(o.size + 1, dtype=np.int32)          # Diff.cs:78: n+1 entries, cleared
+    suffix_sort.sort(o, I[:o.size])                    # Diff.cs:90
+    ctx = _engine().context
+    pos = np.empty(w.size, dtype=np.int32)
+    ln = np.empty(w.size, dtype=np.int32)
+    ctx.bsdiff_search(o, I, w, 0, w.size, pos, ln)
+    return ctx.greedy_emit(o, w, pos, ln)
 
 
 def search_all(old, new, suffix_sort, I=None, scan_begin=0, count=None):

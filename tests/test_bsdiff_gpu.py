@@ -138,3 +138,25 @@ def test_search_without_resident_index_is_an_error(sorter):
     with pytest.raises(_native.NativeError) as ei:
         sorter.context.bsdiff_search(old, None, new, 0, 50, pos, pos.copy())
     assert ei.value.status == _native.DQ_ERR_INVALID_ARGUMENT
+
+
+def test_diff_create_accepts_any_isuffixsort(sorter):
+    """Diff.Create takes any ISuffixSort (Diff.cs:27): a foreign provider sorts, the GPU searches."""
+    from deltaq_b200 import bsdiff
+
+    class OracleSort:                       # stands in for the reference's SAIS / LibDivSufSort providers
+        def sort(self, text, suffixes):
+            if suffixes.size != text.size:
+                raise ValueError("Text and suffix buffers should have the same length")
+            suffixes[:] = oracle.sais(text)
+
+    old, new = structured_pairs()["point_edits"]
+    got = bsdiff.create_streams(old, new, OracleSort())
+    ref = oracle.bsdiff_streams(old, new)
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], k
+    out = io.BytesIO()
+    bsdiff.Diff.create(old, new, out, OracleSort())
+    rebuilt = io.BytesIO()
+    bsdiff.Patch.apply(old, out.getvalue(), rebuilt)
+    assert rebuilt.getvalue() == new.tobytes()
