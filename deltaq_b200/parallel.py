@@ -8,6 +8,8 @@
 * Independent (old, new) pairs need no code here: each rank calls ``bsdiff.create_streams`` on its own objects
   (that is what ``bench.py --gpus N`` measures).
 """
+import os
+
 import numpy as np
 
 from .suffix_sort import as_bytes_array
@@ -111,25 +113,51 @@ def _bit_length(v):
 
 
 class _Exchanger:
+    """Collectives of the sharded sort.  NCCL moves device tensors directly; with gloo and device tensors (several
+    ranks sharing one GPU, as in the single-GPU test of the multi-rank path) the payload is staged through the host."""
+
     def __init__(self, group, device):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.device = device
         self.world = dist.get_world_size(group)
+        self.stage = device.type == "cuda" and dist.get_backend(group) != "nccl"
+
+    def _in(self, t):
+        return t.cpu() if self.stage else t
+
+    def _out(self, t):
+        return t.to(self.device) if self.stage else t
 
     def counts(self, send_counts):
         import torch
-        sc = torch.tensor(send_counts, dtype=torch.int64, device=self.device)
+        sc = torch.tensor(send_counts, dtype=torch.int64, device="cpu" if self.stage else self.device)
         rc = torch.empty_like(sc)
         self.dist.all_to_all_single(rc, sc, group=self.group)
         return [int(x) for x in rc.tolist()]
 
     def data(self, t, send_counts, recv_counts):
         import torch
-        out = torch.empty(sum(recv_counts), dtype=t.dtype, device=self.device)
-        self.dist.all_to_all_single(out, t.contiguous(), recv_counts, send_counts, group=self.group)
-        return out
+        out = torch.empty(sum(recv_counts), dtype=t.dtype, device="cpu" if self.stage else self.device)
+        self.dist.all_to_all_single(out, self._in(t.contiguous()), recv_counts, send_counts, group=self.group)
+        return self._out(out)
+
+    def all_reduce(self, t):
+        if not self.stage:
+            self.dist.all_reduce(t, group=self.group)
+            return t
+        h = t.cpu()
+        self.dist.all_reduce(h, group=self.group)
+        t.copy_(h)
+        return t
+
+    def all_gather(self, t):
+        import torch
+        src = self._in(t)
+        parts = [torch.empty_like(src) for _ in range(self.world)]
+        self.dist.all_gather(parts, src, group=self.group)
+        return [self._out(p) for p in parts]
 
 
 def suffix_sort_sharded(text, suffix_sort, group=None, gather=True, profile=None, out=None):
@@ -157,8 +185,11 @@ def suffix_sort_sharded(text, suffix_sort, group=None, gather=True, profile=None
     rank = dist.get_rank(group)
     if world > 256:
         raise ValueError("suffix_sort_sharded supports at most 256 ranks")
-    nccl = dist.get_backend(group) == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    # device tensors whenever the context is the CUDA library (NCCL, or gloo with host staging); host tensors only for
+    # the CPU logic emulator of the tests
+    on_gpu = dist.get_backend(group) == "nccl" or os.path.basename(ctx.lib.path) == "libdeltaq_cuda.so"
+    nccl = on_gpu
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
     ex = _Exchanger(group, dev)
     i32, i64 = torch.int32, torch.int64
 
@@ -198,7 +229,7 @@ def suffix_sort_sharded(text, suffix_sort, group=None, gather=True, profile=None
     mark("h2d_text_slice")
     sync()
     ctx.dist_pack(T.data_ptr(), own_begin, own_cnt, keys.data_ptr(), vals.data_ptr(), hist.data_ptr())
-    dist.all_reduce(hist, group=group)
+    ex.all_reduce(hist)
     cum = torch.cumsum(hist, 0) - hist
     lut64 = torch.clamp((cum * world) // max(n, 1), max=world - 1)
     bucket_cnt = torch.zeros(world, dtype=i64, device=dev).index_add_(0, lut64, hist)
@@ -255,8 +286,7 @@ def suffix_sort_sharded(text, suffix_sort, group=None, gather=True, profile=None
 
     # ---- doubling rounds: fetch ISA[sa+h] from the position owners, sort locally, send the new ranks back
     h = 8
-    tot = torch.tensor([a], dtype=i64, device=dev)
-    dist.all_reduce(tot, group=group)
+    tot = ex.all_reduce(torch.tensor([a], dtype=i64, device=dev))
     rounds = 1
     while int(tot) > 0:
         q = empty(a, i64)
@@ -291,8 +321,7 @@ def suffix_sort_sharded(text, suffix_sort, group=None, gather=True, profile=None
         mark("rounds_route_updates")
         h *= 2
         rounds += 1
-        tot = torch.tensor([a], dtype=i64, device=dev)
-        dist.all_reduce(tot, group=group)
+        tot = ex.all_reduce(torch.tensor([a], dtype=i64, device=dev))
     if profile is not None:
         profile["rounds"] = rounds
 
@@ -311,6 +340,5 @@ def suffix_sort_sharded(text, suffix_sort, group=None, gather=True, profile=None
     maxc = max(max(cnts), 1)
     pad = torch.zeros(maxc, dtype=i32, device=dev)
     pad[:my_cnt] = mine
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
+    parts = ex.all_gather(pad)
     return torch.cat([parts[g][:cnts[g]] for g in range(world)]).cpu().numpy()

@@ -39,8 +39,11 @@ def _worker(rank, world, port, backend, use_emu, q):
     if use_emu:
         import emu
         sorter = CudaSuffixSort(_lib=emu.library())
-    else:
+    elif backend == "nccl":
         sorter = CudaSuffixSort(device=rank)
+    else:
+        torch.cuda.set_device(0)            # both ranks share GPU 0
+        sorter = CudaSuffixSort(device=0)
     old, new = _pair()
     pos, ln = search_sharded(old, new, sorter)
     q.put((rank, pos, ln))
@@ -123,8 +126,11 @@ def _sort_worker(rank, world, port, backend, use_emu, q):
     if use_emu:
         import emu
         sorter = CudaSuffixSort(_lib=emu.library())
-    else:
+    elif backend == "nccl":
         sorter = CudaSuffixSort(device=rank)
+    else:
+        torch.cuda.set_device(0)            # several ranks share GPU 0, collectives staged through gloo
+        sorter = CudaSuffixSort(device=0)
     res = {}
     for name, t in _sort_texts().items():
         res[name] = suffix_sort_sharded(t, sorter)
@@ -166,3 +172,15 @@ def test_suffix_sort_sharded_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     _run_sort(2, "nccl", False)
+
+
+@pytest.mark.gpu
+def test_suffix_sort_sharded_two_ranks_one_gpu():
+    """The multi-rank sort on a single GPU: two processes share cuda:0 (gloo moves the exchanged tuples through the
+    host), so the distributed kernels and the exchange logic run in every single-GPU `-m gpu` pass."""
+    _run_sort(2, "gloo", False)
+
+
+@pytest.mark.gpu
+def test_search_sharded_two_ranks_one_gpu():
+    _run(2, "gloo", False)
