@@ -6,6 +6,7 @@
 #include "../../include/deltaq_cuda.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <mutex>
 #include <new>
@@ -73,13 +74,18 @@ struct dq_ctx {
 
     // pipelined D2H of the (pos, len) table for dq_cuda_bsdiff_streams
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t slice_ready[8] = {}, slice_done[8] = {};
+    cudaStream_t slice_stream[8] = {};  // one per table slice, so the tail of one slice's chains overlaps the next
+    cudaEvent_t heads_done = nullptr;  // search_heads_kernel (and all before it) finished
+    cudaEvent_t slice_ready[8] = {}, slice_done[8] = {};  // slice's chains finished / slice's code bytes on the host
     int32_t slice_end[8] = {};
     int slices_used = 0;
 
     // diff streams (host)
     dq::diffhost::Streams streams;
-    PinBuf h_pos, h_len;
+    PinBuf h_pos, h_len;             // full table: fallback only
+    PinBuf h_code, h_heads, h_tiles; // coded table (encode_table_kernel)
+    DevBuf d_code, d_headcount;
+    uint32_t heads_cap = 0, heads_cap_override = 0;  // override: DQ_HEADS_CAP, to exercise the fallback in tests
 };
 
 namespace {
@@ -471,6 +477,7 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
         cudaGetDevice(&dev);
     ctx->device = dev;
     if (const char *mp = getenv("DQ_MATCH_POLICY")) ctx->match_policy = atoi(mp);
+    if (const char *hc = getenv("DQ_HEADS_CAP")) ctx->heads_cap_override = (uint32_t)atoi(hc);
     auto fail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         delete ctx;
@@ -483,7 +490,11 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
         return fail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->heads_done, cudaEventDisableTiming)) != cudaSuccess)
+        return fail("cudaEventCreate", e);
     for (int i = 0; i < 8; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->slice_stream[i], cudaStreamNonBlocking)) != cudaSuccess)
+            return fail("cudaStreamCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->slice_ready[i], cudaEventDisableTiming)) != cudaSuccess)
             return fail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->slice_done[i], cudaEventDisableTiming)) != cudaSuccess)
@@ -514,7 +525,7 @@ int dq_cuda_destroy(dq_ctx *ctx)
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
                       &ctx->runtile, &ctx->runend_new, &ctx->newtext, &ctx->s_pos,
-                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt};
+                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->pass_events) {
@@ -524,12 +535,17 @@ int dq_cuda_destroy(dq_ctx *ctx)
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     if (ctx->h_pos.p) cudaFreeHost(ctx->h_pos.p);
     if (ctx->h_len.p) cudaFreeHost(ctx->h_len.p);
+    if (ctx->h_code.p) cudaFreeHost(ctx->h_code.p);
+    if (ctx->h_heads.p) cudaFreeHost(ctx->h_heads.p);
+    if (ctx->h_tiles.p) cudaFreeHost(ctx->h_tiles.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 8; ++i) {
         if (ctx->slice_ready[i]) cudaEventDestroy(ctx->slice_ready[i]);
         if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
+        if (ctx->slice_stream[i]) cudaStreamDestroy(ctx->slice_stream[i]);
     }
+    if (ctx->heads_done) cudaEventDestroy(ctx->heads_done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -680,6 +696,9 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     // Diff.cs:90 -- suffixSort.Sort(oldData, I[..^1]); the suffix array stays on the device.  `new` goes up on
     // the copy stream while the sort runs.
     ctx->resident_n = -1;
+    const bool trace = getenv("DQ_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     DQ_TRY(ensure(ctx, ctx->newtext, (size_t)m + 64));
     if (m) DQ_CK(ctx, cudaMemcpyAsync(ctx->newtext.p, new_, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
     DQ_CK(ctx, cudaMemsetAsync(ctx->newtext.as<uint8_t>() + m, 0, 64, ctx->copy_stream));
@@ -687,12 +706,11 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     DQ_TRY(upload_text(ctx, ctx->text, old_, (uint32_t)n, cudaMemcpyHostToDevice));
     DQ_TRY(sort_resident(ctx, (uint32_t)n));
     ctx->resident_n = n;
+    if (trace) fprintf(stderr, "[dq trace] sorted %.3f ms\n", since());
     DQ_CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slice_done[0], 0));
-    // Diff.cs:106 for every scan position, in slices whose D2H overlaps the later slices and the host loop
-    DQ_TRY(ensure_pinned(ctx, ctx->h_pos, (size_t)m * 4 + 4));
-    DQ_TRY(ensure_pinned(ctx, ctx->h_len, (size_t)m * 4 + 4));
-    int32_t *h_pos = static_cast<int32_t *>(ctx->h_pos.p), *h_len = static_cast<int32_t *>(ctx->h_len.p);
-    DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, 0, (uint32_t)m, h_pos, h_len));
+    // Diff.cs:106 for every scan position, in slices; each slice crosses PCIe in its coded form (dq_search.cuh,
+    // encode_table_kernel) while later slices are still being searched and the host loop runs
+    DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, 0, (uint32_t)m, true));
     // Diff.cs:100-223 on the host, consuming the table as its slices land
     int next = 0;
     int32_t ready_end = 0;
@@ -703,9 +721,52 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
             cudaError_t e_ = cudaEventSynchronize(ctx->slice_done[next]);
             if (e_ != cudaSuccess) werr = e_;
             ready_end = ctx->slice_end[next++];
+            if (trace) fprintf(stderr, "[dq trace] slice %d landed %.3f ms\n", next - 1, since());
         }
     };
-    dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, h_pos, h_len, ctx->streams, ready);
+    // pos of a short match: only the last stop of the scan can ask (see dq_search.cuh), by then every slice is done
+    auto fetch_pos = [&](int32_t scan) -> int32_t {
+        int32_t v = 0;
+        cudaError_t e_ = cudaMemcpyAsync(&v, ctx->s_pos.as<int32_t>() + scan, 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(ctx->copy_stream);
+        if (e_ != cudaSuccess) werr = e_;
+        return v;
+    };
+    if (trace) fprintf(stderr, "[dq trace] search enqueued %.3f ms\n", since());
+    bool overflow = false;
+    if (m) {
+        static_assert(sizeof(dq::diffhost::MatchHead) == sizeof(dq::search::MatchHead) && sizeof(dq::diffhost::TileEntry) == sizeof(uint2),
+                      "host and device views of the coded table must agree");
+        dq::diffhost::CodedTable<decltype(fetch_pos)> tab{static_cast<const uint8_t *>(ctx->h_code.p),
+                                                          static_cast<const dq::diffhost::TileEntry *>(ctx->h_tiles.p),
+                                                          static_cast<const dq::diffhost::MatchHead *>(ctx->h_heads.p),
+                                                          ctx->heads_cap, fetch_pos};
+        try {
+            dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, tab, ctx->streams, ready);
+        } catch (const dq::diffhost::CodedOverflow &) {
+            overflow = true;
+        }
+    } else {
+        dq::diffhost::reset_streams(ctx->streams, 0);
+        dq::diffhost::FullTable none{nullptr, nullptr};
+        dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, none, ctx->streams, ready);
+    }
+    if (overflow) {
+        // more match heads than the pinned list holds (every few positions starts a new long match): take the
+        // whole table across and run the same loop over the plain arrays
+        DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        DQ_TRY(ensure_pinned(ctx, ctx->h_pos, (size_t)m * 4 + 4));
+        DQ_TRY(ensure_pinned(ctx, ctx->h_len, (size_t)m * 4 + 4));
+        int32_t *h_pos = static_cast<int32_t *>(ctx->h_pos.p), *h_len = static_cast<int32_t *>(ctx->h_len.p);
+        DQ_CK(ctx, cudaMemcpyAsync(h_pos, ctx->s_pos.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CK(ctx, cudaMemcpyAsync(h_len, ctx->s_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        dq::diffhost::FullTable full{h_pos, h_len};
+        dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, full, ctx->streams, [](int32_t) {});
+        ctx->stats.table_fallbacks++;
+    }
+    if (trace) fprintf(stderr, "[dq trace] host loop done %.3f ms (scan side %.3f ms), %zu stops%s\n", since(), ctx->streams.scan_done_ms, ctx->streams.ctrl.size() / 24, overflow ? " [full-table fallback]" : "");
     DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     DQ_CK(ctx, werr);
@@ -721,7 +782,9 @@ int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8
     std::lock_guard<std::mutex> lock(ctx->mu);
     DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || (new_ && pos_tab && len_tab)),
                       "greedy_emit: bad arguments"));
-    dq::diffhost::greedy_emit(old_, n, new_, m, pos_tab, len_tab, ctx->streams);
+    // same threads as dq_cuda_bsdiff_streams uses (scan / extender + crew / writers), over the caller's arrays
+    dq::diffhost::FullTable tab{pos_tab, len_tab};
+    dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, tab, ctx->streams, [](int32_t) {});
     export_streams(ctx, out);
     return DQ_OK;
 }

@@ -794,5 +794,93 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
     }
 }
 
+
+// ---- compact form of the (pos, len) table for the host loop of dq_cuda_bsdiff_streams -------------------------------
+// The loop of Diff.cs:100-223 reads len at every position it visits but uses pos only where the scan stops, and a
+// stop needs len > oldscore + 8 >= 9 (Diff.cs:116) -- except the very last one, served by a single device read.
+// So the table crosses PCIe as one byte per position, min(len, kLongLen), plus the list of "match heads": the
+// positions with len >= kLongLen whose (pos, len) is not (pos+1, len-1) of the position before.  Every other
+// long position continues the head before it (if y is long and continues y-1 then len[y-1] = len[y]+1 is long
+// too, so walking back ends at a head with no other head in between): len = head.len - (y - head.at),
+// pos = head.pos + (y - head.at).  Heads are written tile by tile, in position order inside a tile, at a base the
+// tile reserves with one atomic; tile_tab[tile] = (base, count) lets the host walk them in order.
+constexpr int kLongLen = 9;
+constexpr int kCodeTile = 1024;
+
+struct MatchHead {
+    int32_t at, pos, len;
+};
+
+__global__ void __launch_bounds__(256)
+    encode_table_kernel(const int32_t *__restrict__ pos, const int32_t *__restrict__ len, uint32_t count,
+                        uint32_t tile_begin, uint8_t *__restrict__ code, MatchHead *__restrict__ heads,
+                        uint32_t heads_cap, uint32_t *__restrict__ head_count, uint2 *__restrict__ tile_tab)
+{
+    __shared__ uint32_t warp_total[8];
+    __shared__ uint32_t tile_base;
+    const uint32_t tile = tile_begin + blockIdx.x;
+    const uint64_t x0 = (uint64_t)tile * kCodeTile + (uint64_t)threadIdx.x * 4;
+    int32_t p[5], l[5];  // [0]: the position before this thread's four
+    p[0] = 0;
+    l[0] = 0;
+    if (x0 > 0 && x0 <= count) {
+        p[0] = pos[x0 - 1];
+        l[0] = len[x0 - 1];
+    }
+    if (x0 + 4 <= count) {
+        const int4 pv = *reinterpret_cast<const int4 *>(pos + x0), lv = *reinterpret_cast<const int4 *>(len + x0);
+        p[1] = pv.x, p[2] = pv.y, p[3] = pv.z, p[4] = pv.w;
+        l[1] = lv.x, l[2] = lv.y, l[3] = lv.z, l[4] = lv.w;
+    } else {
+        for (int k = 0; k < 4; ++k) {
+            const bool in = x0 + k < count;
+            p[k + 1] = in ? pos[x0 + k] : 0;
+            l[k + 1] = in ? len[x0 + k] : 0;
+        }
+    }
+    uint32_t packed = 0, is_head = 0, mine = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int32_t lk = l[k + 1];
+        packed |= (uint32_t)(lk < kLongLen ? lk : kLongLen) << (8 * k);
+        const bool continues = (x0 + k > 0) && p[k + 1] == p[k] + 1 && lk == l[k] - 1;
+        if (lk >= kLongLen && !continues) {
+            is_head |= 1u << k;
+            ++mine;
+        }
+    }
+    if (x0 + 4 <= count) {
+        *reinterpret_cast<uint32_t *>(code + x0) = packed;
+    } else {
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k < count) code[x0 + k] = (uint8_t)(packed >> (8 * k));
+    }
+    // ordered compaction of the heads of this tile
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFullMask, incl, d);
+        if ((int)lane_id() >= d) incl += v;
+    }
+    if (lane_id() == 31) warp_total[warp_id()] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = warp_total[w];
+            warp_total[w] = run;
+            run += c;
+        }
+        const uint32_t base = run ? atomicAdd(head_count, run) : 0u;
+        tile_base = base;
+        tile_tab[tile] = make_uint2(base, run);
+    }
+    __syncthreads();
+    uint32_t at = tile_base + warp_total[warp_id()] + incl - mine;
+    for (int k = 0; k < 4; ++k)
+        if (is_head >> k & 1u) {
+            if (at < heads_cap) heads[at] = MatchHead{(int32_t)(x0 + k), p[k + 1], l[k + 1]};
+            ++at;
+        }
+}
+
 }  // namespace search
 }  // namespace dq

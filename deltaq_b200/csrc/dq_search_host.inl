@@ -60,15 +60,29 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
     return DQ_OK;
 }
 
+int ensure_pinned(dq_ctx *ctx, PinBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return DQ_OK;
+    if (b.p) {
+        DQ_CK(ctx, cudaFreeHost(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = std::max<size_t>(bytes, 4096);
+    DQ_CK(ctx, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return DQ_OK;
+}
+
 // (ctx->text, ctx->sa, ctx->isa) describe `old` (n bytes); ctx->newtext holds `new` (m bytes, padded).
 // Fills ctx->s_pos / ctx->s_len [0, count).
-// h_pos/h_len != nullptr: pipeline mode for dq_cuda_bsdiff_streams -- the chain kernel runs in kSlices launches,
-// each followed by an asynchronous D2H of its slice on the copy stream; slice_end[] / slice_done[] tell the host
-// loop when a prefix of the table is usable.
+// coded: pipeline mode for dq_cuda_bsdiff_streams -- the chain kernel runs in kSlices launches, each followed by
+// encode_table_kernel over its tiles and an asynchronous D2H of the slice's code bytes on the copy stream (heads and
+// tile entries are written by the kernel straight into pinned host memory); slice_end[] / slice_done[] tell the
+// host loop when a prefix of the coded table is usable.
 constexpr int kSlices = 8;
 
-int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count, int32_t *h_pos = nullptr,
-                    int32_t *h_len = nullptr)
+int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count, bool coded = false)
 {
     ctx->stats.search_queries = (int32_t)count;
     ctx->slices_used = 0;
@@ -110,7 +124,17 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
             lv += ((size_t)ix.size[l] + 63) & ~(size_t)63;
         }
     }
-    const int slices = h_pos ? kSlices : 1;
+    const int slices = coded ? kSlices : 1;
+    if (coded) {
+        const uint32_t tiles = (uint32_t)div_up(count, sr::kCodeTile);
+        ctx->heads_cap = ctx->heads_cap_override ? ctx->heads_cap_override : count / 4 + 4096;
+        DQ_TRY(ensure(ctx, ctx->d_code, (size_t)count + 64));
+        DQ_TRY(ensure(ctx, ctx->d_headcount, 256));
+        DQ_TRY(ensure_pinned(ctx, ctx->h_code, (size_t)count + 64));
+        DQ_TRY(ensure_pinned(ctx, ctx->h_heads, (size_t)ctx->heads_cap * sizeof(sr::MatchHead)));
+        DQ_TRY(ensure_pinned(ctx, ctx->h_tiles, (size_t)tiles * sizeof(uint2)));
+        DQ_CK(ctx, cudaMemsetAsync(ctx->d_headcount.p, 0, 4, ctx->stream));
+    }
     // All heads in one launch (sliced head launches are tail-bound each: measured slower end to end), then the
     // chain kernel in slices of whole super-chunks.
     const uint32_t supers_per = (uint32_t)div_up(supers, slices);
@@ -121,24 +145,38 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
                   count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), 0u, supers);
         ctx->stats.kernel_launches++;
     }
+    if (coded) DQ_CK(ctx, cudaEventRecord(ctx->heads_done, ctx->stream));
     for (int sl = 0; sl < slices; ++sl) {
         const uint32_t sb = std::min<uint64_t>((uint64_t)sl * supers_per, supers), se = std::min<uint64_t>((uint64_t)(sl + 1) * supers_per, supers);
         if (sb >= se) break;
         const uint32_t cb = sb * sr::kHeads, ce = std::min<uint64_t>((uint64_t)se * sr::kHeads, chunks);
+        // a slice is less than one wave of chains of very uneven length: each slice runs on its own stream so
+        // the next one fills the SMs as this one drains
+        cudaStream_t st = coded ? ctx->slice_stream[sl] : ctx->stream;
+        if (coded) DQ_CK(ctx, cudaStreamWaitEvent(st, ctx->heads_done, 0));
         {
             auto k = sr::search_chain_kernel;
-            DQ_LAUNCH(k, (uint32_t)div_up(ce - cb, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin, count,
+            DQ_LAUNCH(k, (uint32_t)div_up(ce - cb, sr::kThreads), sr::kThreads, 0, st, t, ix, scan_begin, count,
                       ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), ctx->s_pos.as<int32_t>(),
                       ctx->s_len.as<int32_t>(), cb, ce, chunks);
         }
         ctx->stats.kernel_launches++;
-        if (h_pos) {
+        if (coded) {
             const uint64_t b = (uint64_t)cb * sr::kChunk, e = std::min<uint64_t>((uint64_t)ce * sr::kChunk, count);
-            DQ_CK(ctx, cudaEventRecord(ctx->slice_ready[sl], ctx->stream));
-            DQ_CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->slice_ready[sl], 0));
-            DQ_CK(ctx, cudaMemcpyAsync(h_pos + b, ctx->s_pos.as<int32_t>() + b, (e - b) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            DQ_CK(ctx, cudaMemcpyAsync(h_len + b, ctx->s_len.as<int32_t>() + b, (e - b) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            DQ_CK(ctx, cudaEventRecord(ctx->slice_done[sl], ctx->copy_stream));
+            static_assert(sr::kSuper % sr::kCodeTile == 0, "slices must cover whole code tiles");
+            const uint32_t tb = (uint32_t)(b / sr::kCodeTile), te = (uint32_t)div_up(e, sr::kCodeTile);
+            // the first position of the slice is compared with the last one of the slice before
+            DQ_CK(ctx, cudaEventRecord(ctx->slice_ready[sl], st));
+            if (sl > 0) DQ_CK(ctx, cudaStreamWaitEvent(st, ctx->slice_ready[sl - 1], 0));
+            auto k = sr::encode_table_kernel;
+            DQ_LAUNCH(k, te - tb, 256, 0, st, ctx->s_pos.as<int32_t>(), ctx->s_len.as<int32_t>(), count, tb,
+                      ctx->d_code.as<uint8_t>(), static_cast<sr::MatchHead *>(ctx->h_heads.p), ctx->heads_cap,
+                      ctx->d_headcount.as<uint32_t>(), static_cast<uint2 *>(ctx->h_tiles.p));
+            ctx->stats.kernel_launches++;
+            DQ_CK(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(ctx->h_code.p) + b, ctx->d_code.as<uint8_t>() + b, e - b,
+                                       cudaMemcpyDeviceToHost, st));
+            DQ_CK(ctx, cudaEventRecord(ctx->slice_done[sl], st));
+            DQ_CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slice_done[sl], 0));
             ctx->slice_end[sl] = (int32_t)e;
             ctx->slices_used = sl + 1;
         }
@@ -166,20 +204,6 @@ int adopt_index(dq_ctx *ctx, const uint8_t *old_, uint32_t n, const int32_t *I, 
         DQ_CK(ctx, cudaGetLastError());
     }
     ctx->resident_n = (int32_t)n;
-    return DQ_OK;
-}
-
-int ensure_pinned(dq_ctx *ctx, PinBuf &b, size_t bytes)
-{
-    if (b.cap >= bytes && b.p) return DQ_OK;
-    if (b.p) {
-        DQ_CK(ctx, cudaFreeHost(b.p));
-        b.p = nullptr;
-        b.cap = 0;
-    }
-    size_t want = std::max<size_t>(bytes, 4096);
-    DQ_CK(ctx, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
-    b.cap = want;
     return DQ_OK;
 }
 

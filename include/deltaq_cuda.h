@@ -49,6 +49,7 @@ typedef struct dq_stats {
     int64_t pass_pairs;        /* pairs moved by those launches (sum of per-launch counts) */
     int32_t search_queries;    /* positions answered by the last search */
     float   search_ms;         /* CUDA-event time of the last search's device work (LCP build included when it ran) */
+    int32_t table_fallbacks;   /* dq_cuda_bsdiff_streams: 1 if the coded (pos,len) table overflowed and the full one was used */
 } dq_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -114,7 +115,7 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
                            dq_diff_streams *out);
 
 /* The host consumer alone: Diff.cs:100-223 over a caller-supplied (pos, len) table (m entries each, e.g. from
- * dq_cuda_bsdiff_search).  Pure host code; no device work. */
+ * dq_cuda_bsdiff_search).  Pure host code (a few threads: scan, extensions, stream writers); no device work. */
 int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                         const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out);
 

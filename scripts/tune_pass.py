@@ -15,6 +15,8 @@ if len(sys.argv) > 1:
     variants = [tuple(int(x) for x in v.split("x")) for v in sys.argv[1:]]
 variants = [tuple(list(v) + [0, 8][len(v) - 2:]) if len(v) < 4 else v for v in variants]
 texts = {"uniform16M": w.c1_uniform(16 << 20, 9), "c2_old": w.c2_exe_pair()[0]}
+if os.environ.get("TUNE_SMALL"):
+    texts = {"c1_1MiB": w.c1_uniform(), "u256K": w.c1_uniform(256 << 10, 3), "u4MiB": w.c1_uniform(4 << 20, 4)}
 res = {}
 for items, minb, ballot, window in variants:
     out = os.path.join(ROOT, "gpurun_out", f"libdq_{items}_{minb}_{ballot}_{window}.so")
@@ -35,7 +37,7 @@ for items, minb, ballot, window in variants:
     for name, t in texts.items():
         pin = ctx.pinned(t.size, np.int32)
         best = None
-        for _ in range(4):
+        for _ in range(12):
             ctx.suffix_sort(t, pin.array)
             st = ctx.stats()
             if best is None or st["device_ms"] < best["device_ms"]:

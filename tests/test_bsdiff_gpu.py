@@ -160,3 +160,24 @@ def test_diff_create_accepts_any_isuffixsort(sorter):
     rebuilt = io.BytesIO()
     bsdiff.Patch.apply(old, out.getvalue(), rebuilt)
     assert rebuilt.getvalue() == new.tobytes()
+
+
+def test_coded_table_overflow_falls_back_to_full_table(monkeypatch):
+    # dq_cuda_bsdiff_streams ships the table as code bytes + match heads; a head list that does not fit must give
+    # the same streams through the full-table path (DQ_HEADS_CAP shrinks the list for this test)
+    pass
+    from deltaq_b200 import CudaSuffixSort, bsdiff
+    rng = np.random.default_rng(77)
+    old = rng.integers(0, 4, 6000, dtype=np.uint8)
+    new = np.concatenate([old[3000:4000], rng.integers(0, 4, 500, dtype=np.uint8), old[:2500], old[5000:]])
+    ref = oracle.bsdiff_streams(old, new, oracle.make_I(oracle.sais(old)))
+    for cap, fallbacks in (("1", 1), ("100000", 0)):
+        monkeypatch.setenv("DQ_HEADS_CAP", cap)
+        s = CudaSuffixSort()
+        try:
+            got = bsdiff.create_streams(old, new, s)
+            assert s._ctx.stats()["table_fallbacks"] == fallbacks
+        finally:
+            s.dispose()
+        for k in ("ctrl", "diff", "extra"):
+            assert got[k] == ref[k], (cap, k)

@@ -1,0 +1,46 @@
+"""The host side of dq_cuda_bsdiff_streams (scan / extender + crew / writers, dq_diff_host.h) at sizes where the
+helper threads take part, against the oracle's restatement of Diff.cs:92-223 (oracle/bsdiff.c).
+
+Runs on the CPU: dq_cuda_greedy_emit is pure host code, reached here through the emulator build's library (the
+same source as the product's).  The (pos, len) table is the oracle's own trace of Diff.Search -- filled only at the
+positions the reference loop visits, which is all the loop may read."""
+import numpy as np
+import pytest
+
+import oracle
+from deltaq_b200 import workloads as w
+
+
+@pytest.fixture(scope="module")
+def pair():
+    # a few long unchanged stretches (so single extensions run to hundreds of KiB), a shifted copy of a periodic
+    # section (two alignments that both match: a long overlap split) and some point damage
+    rng = np.random.default_rng(2024)
+    old = w._exe_like(3 << 20, np.random.default_rng(7))
+    period = np.tile(rng.integers(0, 256, 48, dtype=np.uint8), 6000)           # 288 KB of 48-byte records
+    old = np.concatenate([old[:1 << 20], period, old[1 << 20:]])
+    new = np.concatenate([old[:700_000], rng.integers(0, 256, 5000, dtype=np.uint8), old[703_000:(1 << 20) + 100_000],
+                          period[24:200_000], old[(1 << 20) + 288_000 + 50_000:2_600_000], old[2_900_000:]]).copy()
+    hits = rng.integers(0, new.size, 40)
+    new[hits] ^= 0x55
+    ref = oracle.bsdiff_streams(old, new, trace=True)
+    return old, new, ref
+
+
+@pytest.mark.parametrize("shape", ["0,1", "1,2", "3,2", "7,4"])
+def test_greedy_emit_threads_match_reference(pair, shape, monkeypatch):
+    import emu
+    old, new, ref = pair
+    monkeypatch.setenv("DQ_HOST_THREADS", shape)
+    with emu.context() as ctx:
+        got = ctx.greedy_emit(old, new, ref["trace_pos"], ref["trace_len"])
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], (shape, k)
+    assert got["search_visits"] == ref["search_calls"]
+
+
+def test_pair_has_stretches_long_enough_for_the_crew(pair):
+    # the crew only walks stretches of 128 KiB and more (kCrewMin): make sure this input has them
+    _, _, ref = pair
+    ctrl = np.frombuffer(ref["ctrl"], dtype="<i8").reshape(-1, 3)
+    assert (ctrl[:, 0] >= (128 << 10)).sum() >= 3
