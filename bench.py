@@ -249,6 +249,7 @@ def main():
         streams = ctx.bsdiff_streams(p_old.array, p_new.array, copy=False)   # the C ABI's own result: pointers + lengths
     barrier()
     dt_e2e = time.perf_counter() - t1
+    e2e_stats = ctx.stats()
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device arm + e2e arm)
 
     # max over ranks
@@ -272,9 +273,13 @@ def main():
                        "l2": "working set (>= 24 B x 16.7 M pairs per radix pass, 400 MB) exceeds the 126 MB L2; no flush",
                        "parallelism": f"{world} x independent pairs (one process and context per GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": n + m, "d2h_bytes_per_step": 8 * m,
-                    "includes": "H2D old+new, sort, search, D2H (pos,len) in slices overlapped with the host greedy scan/emit loop "
-                                "(2 host threads); result = context-owned ctrl/diff/extra buffers; streams "
+                    "h2d_bytes_per_step": n + m,
+                    # the (pos,len) table crosses PCIe coded: 1 B/position + 12 B/match head + 8 B per 1024 positions
+                    "d2h_bytes_per_step": (8 * m if e2e_stats["table_fallbacks"] else
+                                           m + 12 * e2e_stats["table_heads"] + 8 * ((m + 1023) // 1024)),
+                    "includes": "H2D old+new, sort, search, D2H of the coded (pos,len) table in slices, host greedy "
+                                "scan/extend/emit loop on host threads overlapped with the slices; result = "
+                                "context-owned ctrl/diff/extra buffers; streams "
                                 f"ctrl/diff/extra = {len(streams['ctrl'])}/{len(streams['diff'])}/{len(streams['extra'])} B"},
             "gpu_launches": acc["launches"],
             "roofline": {"bound": "hbm", "kernel": "dq::radix::onesweep_pass_kernel",

@@ -490,14 +490,14 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
         return fail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail("cudaStreamCreate", e);
-    if ((e = cudaEventCreateWithFlags(&ctx->heads_done, cudaEventDisableTiming)) != cudaSuccess)
+    if ((e = cudaEventCreate(&ctx->heads_done)) != cudaSuccess)
         return fail("cudaEventCreate", e);
     for (int i = 0; i < 8; ++i) {
         if ((e = cudaStreamCreateWithFlags(&ctx->slice_stream[i], cudaStreamNonBlocking)) != cudaSuccess)
             return fail("cudaStreamCreate", e);
-        if ((e = cudaEventCreateWithFlags(&ctx->slice_ready[i], cudaEventDisableTiming)) != cudaSuccess)
+        if ((e = cudaEventCreate(&ctx->slice_ready[i])) != cudaSuccess)
             return fail("cudaEventCreate", e);
-        if ((e = cudaEventCreateWithFlags(&ctx->slice_done[i], cudaEventDisableTiming)) != cudaSuccess)
+        if ((e = cudaEventCreate(&ctx->slice_done[i])) != cudaSuccess)
             return fail("cudaEventCreate", e);
     }
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -766,11 +766,26 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
         dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, full, ctx->streams, [](int32_t) {});
         ctx->stats.table_fallbacks++;
     }
-    if (trace) fprintf(stderr, "[dq trace] host loop done %.3f ms (scan side %.3f ms), %zu stops%s\n", since(), ctx->streams.scan_done_ms, ctx->streams.ctrl.size() / 24, overflow ? " [full-table fallback]" : "");
+    if (trace) fprintf(stderr, "[dq trace] host loop done %.3f ms (scan side %.3f ms, extender done %.3f ms / busy %.3f ms), %zu stops%s\n", since(), ctx->streams.scan_done_ms, ctx->streams.extender_done_ms, ctx->streams.extender_busy_ms, ctx->streams.ctrl.size() / 24, overflow ? " [full-table fallback]" : "");
     DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     DQ_CK(ctx, werr);
     if (m) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_ms, ctx->ev0, ctx->ev1));
+    if (m) {
+        uint32_t heads = 0;
+        DQ_CK(ctx, cudaMemcpy(&heads, ctx->d_headcount.p, 4, cudaMemcpyDeviceToHost));
+        ctx->stats.table_heads = (int32_t)heads;
+    }
+    if (trace && m) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev0, ctx->heads_done);
+        fprintf(stderr, "[dq trace] device: search start -> heads done %.3f ms, -> all done %.3f ms\n", a, ctx->stats.search_ms);
+        for (int sl = 0; sl < ctx->slices_used; ++sl) {
+            cudaEventElapsedTime(&a, ctx->ev0, ctx->slice_ready[sl]);
+            cudaEventElapsedTime(&b, ctx->ev0, ctx->slice_done[sl]);
+            fprintf(stderr, "[dq trace] device: slice %d chains done %.3f ms, code on host %.3f ms\n", sl, a, b);
+        }
+    }
     export_streams(ctx, out);
     return DQ_OK;
 }

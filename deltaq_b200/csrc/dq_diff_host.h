@@ -55,7 +55,9 @@ struct Streams {
     std::vector<uint8_t> ctrl;
     ByteBuf diff, extra;
     int64_t visits = 0;
-    double scan_done_ms = 0;  // DQ_TRACE: when the scan side finished, relative to the start of the loop
+    // DQ_TRACE: when the scan side finished (relative to the start of the loop), and how long the other threads
+    // spent working rather than waiting
+    double scan_done_ms = 0, extender_busy_ms = 0, writer_busy_ms = 0, extender_done_ms = 0;
 };
 
 // bit k of the result is set iff a[k] == b[k], k in [0, 32)
@@ -98,6 +100,22 @@ inline int32_t count_equal(const uint8_t *a, const uint8_t *b, int32_t len)
     for (; k + 32 <= len; k += 32) cnt += __builtin_popcount(eq_mask32(a + k, b + k));
     for (; k < len; ++k) cnt += (a[k] == b[k]);
     return cnt;
+}
+
+// index of the last k in [0, len) with a[k] != b[k], or -1
+inline int32_t last_mismatch(const uint8_t *a, const uint8_t *b, int32_t len)
+{
+    int32_t k = len;
+    while (k > 0 && (k & 31)) {
+        --k;
+        if (a[k] != b[k]) return k;
+    }
+    while (k >= 32) {
+        const uint32_t ne = ~eq_mask32(a + k - 32, b + k - 32);
+        if (ne) return k - 32 + (31 - __builtin_clz(ne));
+        k -= 32;
+    }
+    return -1;
 }
 
 inline void put_packed_long(std::vector<uint8_t> &out, int64_t y)
@@ -225,6 +243,23 @@ template <typename FetchPos> struct CodedTable {
         pos = cur.pos + (scan - cur.at);
     }
     int32_t fetch_pos(int32_t scan) { return fetch(scan); }
+    // get(scan) just returned a long match: the last position whose long match still continues it (its len keeps
+    // scan + len where it is).  Looks at heads up to that position: the caller makes sure they have arrived.
+    int32_t chain_reach(int32_t scan) const { return cur.at + cur.len - kLong > scan ? cur.at + cur.len - kLong : scan; }
+    int32_t chain_last(int32_t reach) const
+    {
+        uint32_t t = next_tile, k = next_k;
+        const uint32_t last_tile = (uint32_t)reach >> kTileShift;
+        while (t <= last_tile && k >= tiles[t].count) {
+            ++t;
+            k = 0;
+        }
+        if (t > last_tile) return reach;
+        const uint32_t at = tiles[t].base + k;
+        if (at >= heads_cap) throw CodedOverflow{};
+        const int32_t next_head = heads[at].at;
+        return next_head - 1 < reach ? next_head - 1 : reach;
+    }
 };
 
 // ---- Diff.cs:132-145 / :152-164: the best extension ---------------------------------------------------------
@@ -393,8 +428,10 @@ public:
     }
 };
 
-constexpr int32_t kCrewPart = 64 << 10;  // bytes one crew member walks per wave
-constexpr int32_t kCrewMin = 128 << 10;  // shorter stretches stay on the calling thread
+// bytes one crew member walks per wave / stretches shorter than this stay on the calling thread
+// (DQ_HOST_THREADS="helpers,writers,part_kib,min_kib" overrides both)
+inline int32_t &crew_part() { static int32_t v = 64 << 10; return v; }
+inline int32_t &crew_min() { static int32_t v = 128 << 10; return v; }
 
 // The first step at which the walk's running value exceeds everything before it (and 0), or 0 if none does --
 // what all three loops of Diff.cs:132-188 compute.  walk(lo, len, whole) returns the Run of steps [lo, lo+len);
@@ -403,13 +440,13 @@ constexpr int32_t kCrewMin = 128 << 10;  // shorter stretches stay on the callin
 // tested between waves.
 template <typename Walk> inline int32_t first_best_step(Crew *crew, int32_t span, Walk &&walk)
 {
-    if (!crew || crew->parts() == 1 || span < kCrewMin) return walk(0, span, false).first;
+    if (!crew || crew->parts() == 1 || span < crew_min()) return walk(0, span, false).first;
     const int P = crew->parts();
     int32_t cur = 0, best = 0, at = 0, done = 0;
     Run r[16];
     while (done < span) {
         if (cur + (span - done) <= best) break;
-        const int32_t wave = (int32_t)std::min<int64_t>(span - done, (int64_t)P * kCrewPart);
+        const int32_t wave = (int32_t)std::min<int64_t>(span - done, (int64_t)P * crew_part());
         const int32_t per = (int32_t)((((int64_t)wave + P - 1) / P + 31) & ~(int64_t)31);
         crew->run([&](int part) {
             const int32_t lo = (int32_t)std::min<int64_t>(wave, (int64_t)part * per);
@@ -652,6 +689,34 @@ inline void greedy_scan(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
 
             if (far_off || (len == oldscore && len != 0) || (len > oldscore + 8)) break;
 
+            if constexpr (Table::kExactMatches) {
+                // A long match that is neither the current alignment nor far from it: 1..8 of its bytes disagree
+                // at the current offset.  The positions after this one continue the same match (len one less each,
+                // scan + len fixed) for as long as the table says so, and for them the test only changes when the
+                // LAST disagreeing byte has dropped out of [scan, scan + len): nothing stops the scan before that
+                // position, so go there directly (the reference visits every position in between; count them).
+                if (len > 8 && scsc == scan + len) {
+                    const int32_t stop = scan + len;
+                    const int32_t reach = tab.chain_reach(scan);
+                    if (reach > scan + 1) {
+                        ready(reach + 64);
+                        const int32_t chain_last = tab.chain_last(reach);
+                        const int64_t lim = (int64_t)oldLen - lastoffset;
+                        const int32_t inb = (int32_t)(lim < stop ? (lim > scan ? lim : scan) : stop);
+                        const int32_t lastmiss =
+                            inb < stop ? stop - 1 : scan + last_mismatch(oldData + lastoffset + scan, newData + scan, stop - scan);
+                        const int32_t target = lastmiss < chain_last ? lastmiss + 1 : chain_last + 1;
+                        if (target > scan + 1) {
+                            oldscore = lastmiss < target ? stop - target
+                                                         : (inb > target ? count_equal(oldData + lastoffset + target, newData + target, inb - target) : 0);
+                            out.visits += target - scan - 1;
+                            scan = target - 1;
+                            continue;
+                        }
+                    }
+                }
+            }
+
             if ((scan + lastoffset < oldLen) && (oldData[scan + lastoffset] == newData[scan])) oldscore--;
         }
 
@@ -745,8 +810,13 @@ struct PipelineShape {
     static PipelineShape for_this_machine()
     {
         if (const char *e = std::getenv("DQ_HOST_THREADS")) {
-            int h = 0, w = 1;
-            if (std::sscanf(e, "%d,%d", &h, &w) >= 1) return PipelineShape{h, w};
+            int h = 0, w = 1, part = 0, mn = 0;
+            const int got = std::sscanf(e, "%d,%d,%d,%d", &h, &w, &part, &mn);
+            if (got >= 4 && part > 0 && mn > 0) {
+                crew_part() = part << 10;
+                crew_min() = mn << 10;
+            }
+            if (got >= 1) return PipelineShape{h, w};
         }
         const unsigned hw = std::thread::hardware_concurrency();
         if (hw >= 12) return PipelineShape{3, 2};
@@ -796,6 +866,8 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
     };
     constexpr int32_t kJobBytes = 256 << 10;
     const int W = std::max(1, std::min(shape.writers, 4));
+    const auto t_loop = std::chrono::steady_clock::now();
+    out.extender_busy_ms = out.writer_busy_ms = 0;
     auto stops = std::make_unique<Handoff<Stop>>();
     std::vector<std::unique_ptr<Handoff<WriteJob>>> jobs;
     for (int w = 0; w < W; ++w) jobs.push_back(std::make_unique<Handoff<WriteJob>>());
@@ -818,7 +890,9 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
             }
         };
         while (stops->pop(sp)) {
+            const auto t_a = std::chrono::steady_clock::now();
             const Piece pc = extend_stop(oldData, oldLen, newData, newLen, sp.scan, sp.pos, st, &crew);
+            out.extender_busy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
             if (pc.lenf > 0) {
                 hand_out(newData + pc.lastscan, oldData + pc.lastpos, out.diff.p.get() + diff_at, pc.lenf);
                 diff_at += (size_t)pc.lenf;
@@ -833,9 +907,9 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
         }
         out.diff.len = diff_at;
         out.extra.len = extra_at;
+        out.extender_done_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count();
         for (auto &q : jobs) q->close();
     });
-    const auto t_loop = std::chrono::steady_clock::now();
     Streams scan_side;  // the scan only counts visits; keep its counter off the other threads' Streams
     auto finish = [&]() {
         stops->close();

@@ -50,6 +50,7 @@ typedef struct dq_stats {
     int32_t search_queries;    /* positions answered by the last search */
     float   search_ms;         /* CUDA-event time of the last search's device work (LCP build included when it ran) */
     int32_t table_fallbacks;   /* dq_cuda_bsdiff_streams: 1 if the coded (pos,len) table overflowed and the full one was used */
+    int32_t table_heads;       /* dq_cuda_bsdiff_streams: match heads in the coded table (12 B each over PCIe, + 1 B/position) */
 } dq_stats;
 
 /* ---- context ------------------------------------------------------------------------------------ */

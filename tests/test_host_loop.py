@@ -40,7 +40,25 @@ def test_greedy_emit_threads_match_reference(pair, shape, monkeypatch):
 
 
 def test_pair_has_stretches_long_enough_for_the_crew(pair):
-    # the crew only walks stretches of 128 KiB and more (kCrewMin): make sure this input has them
+    # the crew only walks stretches of 128 KiB and more (crew_min(), dq_diff_host.h): make sure this input has them
     _, _, ref = pair
     ctrl = np.frombuffer(ref["ctrl"], dtype="<i8").reshape(-1, 3)
     assert (ctrl[:, 0] >= (128 << 10)).sum() >= 3
+
+
+def test_streams_end_to_end_on_emulator_at_crew_sizes(pair, monkeypatch):
+    # the same pair through the whole of dq_cuda_bsdiff_streams on the logic emulator: sort, search,
+    # encode_table_kernel, coded-table scan (block steps, chain walks), crew and writers
+    import emu
+    from deltaq_b200 import CudaSuffixSort, bsdiff
+    old, new, ref = pair
+    monkeypatch.setenv("DQ_HOST_THREADS", "3,2")
+    s = CudaSuffixSort(_lib=emu.library())
+    try:
+        got = bsdiff.create_streams(old, new, s)
+        assert s._ctx.stats()["table_fallbacks"] == 0
+    finally:
+        s.dispose()
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], k
+    assert got["search_visits"] == ref["search_calls"]
