@@ -55,7 +55,7 @@ struct dq_ctx {
 
     // suffix-sort state (device)
     DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
-        runtile, runend_new;
+        runtile, runend_new, runtile_new, seedp, seedl;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -64,6 +64,8 @@ struct dq_ctx {
 
     // search state (device)
     DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
+    int32_t resident_rounds = -1; // doubling rounds of the sort that produced the resident SA (-1: SA came from the caller)
+    int32_t runend_new_m = -1;    // runend_new[] describes ctx->newtext of this length
     int32_t runend_valid_n = -1;  // runend[] describes the resident text of this length (set by a run-aware sort)
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
 
@@ -524,7 +526,7 @@ int dq_cuda_destroy(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
-                      &ctx->runtile, &ctx->runend_new, &ctx->newtext, &ctx->s_pos,
+                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -613,6 +615,7 @@ int dq_cuda_suffix_sort(dq_ctx *ctx, const uint8_t *text, int32_t n, int32_t *sa
     if (n) DQ_CK(ctx, cudaMemcpyAsync(sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->resident_n = n;
+    ctx->resident_rounds = ctx->stats.rounds;
     return DQ_OK;
 }
 
@@ -628,6 +631,7 @@ int dq_cuda_suffix_sort_device(dq_ctx *ctx, const uint8_t *d_text, int32_t n, in
     if (n) DQ_CK(ctx, cudaMemcpyAsync(d_sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->resident_n = n;
+    ctx->resident_rounds = ctx->stats.rounds;
     return DQ_OK;
 }
 
@@ -702,10 +706,16 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     DQ_TRY(ensure(ctx, ctx->newtext, (size_t)m + 64));
     if (m) DQ_CK(ctx, cudaMemcpyAsync(ctx->newtext.p, new_, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
     DQ_CK(ctx, cudaMemsetAsync(ctx->newtext.as<uint8_t>() + m, 0, 64, ctx->copy_stream));
+    // run ends of `new` (used by the search when the sort finds `old` full of equal-byte runs): computed now,
+    // beside the sort, rather than in front of the search
+    ctx->runend_new_m = -1;
+    if (m >= (1 << 20)) DQ_TRY(run_ends_of_new(ctx, (uint32_t)m, ctx->copy_stream));
     DQ_CK(ctx, cudaEventRecord(ctx->slice_done[0], ctx->copy_stream));
     DQ_TRY(upload_text(ctx, ctx->text, old_, (uint32_t)n, cudaMemcpyHostToDevice));
     DQ_TRY(sort_resident(ctx, (uint32_t)n));
     ctx->resident_n = n;
+    ctx->resident_rounds = ctx->stats.rounds;
+    if (ctx->runend_new_m == m) ctx->stats.kernel_launches += 3;  // run_ends_of_new above (the sort resets the stats)
     if (trace) fprintf(stderr, "[dq trace] sorted %.3f ms\n", since());
     DQ_CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slice_done[0], 0));
     // Diff.cs:106 for every scan position, in slices; each slice crosses PCIe in its coded form (dq_search.cuh,

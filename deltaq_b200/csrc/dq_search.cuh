@@ -568,38 +568,48 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint8_t *__res
     }
 }
 
-// LCP array, level A: one WARP per kSuper text positions walks the chunk heads with stride kChunk; the byte
-// comparisons are warp-cooperative (a head inside a long repeat costs length/256 steps, not length/8).
-// head_l[i / kChunk] = PLCP[i] for i % kChunk == 0.
+// LCP array, levels S and A.  One WARP walks `per_warp` text positions `stride` apart; the byte comparisons are
+// warp-cooperative (a position inside a long repeat costs length/256 steps, not length/8), and each position
+// starts from what the one before it leaves: PLCP[i + stride] >= PLCP[i] - stride.  out_l[i / stride] = PLCP[i].
+//   level S (seeds):  stride = kSuper, per_warp = a few supers, seed_l = nullptr -- the first position of a warp is
+//                     compared from byte 0, which inside a repeat of length R costs R bytes: this level keeps the
+//                     number of such cold starts to a few thousand however long the text is;
+//   level A (heads):  stride = kChunk, per_warp = kHeads; the first head of super s is position s*kSuper, whose
+//                     value level S has already written to seed_l[s].
 __global__ void __launch_bounds__(kThreads)
 lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
-                 const uint32_t *__restrict__ ISA, uint32_t *__restrict__ head_l,
-                 const uint32_t *__restrict__ run_end)
+                 const uint32_t *__restrict__ ISA, uint32_t *__restrict__ out_l,
+                 const uint32_t *__restrict__ run_end, uint32_t stride, uint32_t per_warp,
+                 const uint32_t *__restrict__ seed_l)
 {
-    const uint64_t sc = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t i0 = sc * kSuper;
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t i0 = w * stride * per_warp;
     if (i0 >= n) return;
     uint32_t l = 0;
-    for (int k = 0; k < kHeads; ++k) {
-        const uint64_t i64 = i0 + (uint64_t)k * kChunk;
+    for (uint32_t k = 0; k < per_warp; ++k) {
+        const uint64_t i64 = i0 + (uint64_t)k * stride;
         if (i64 >= n) break;
         const uint32_t i = (uint32_t)i64;
-        const uint32_t r = ISA[i];
-        if (r == 0) {
-            l = 0;
+        if (k == 0 && seed_l) {
+            l = seed_l[w];
         } else {
-            const uint32_t q = (uint32_t)SA[r - 1];
-            uint32_t known = l > (uint32_t)kChunk ? l - kChunk : 0;
-            // both suffixes inside runs of the same byte: the shorter run is common prefix, no need to read it
-            // (zero padding: without this one warp walks up to a megabyte here and the kernel waits for it)
-            if (run_end && known == 0 && T[i] == T[q]) {
-                const uint32_t ri = run_end[i] - i, rq = run_end[q] - q;
-                const uint32_t skip = min(ri, rq);
-                if (skip >= 64) known = skip;
+            const uint32_t r = ISA[i];
+            if (r == 0) {
+                l = 0;
+            } else {
+                const uint32_t q = (uint32_t)SA[r - 1];
+                uint32_t known = l > stride ? l - stride : 0;
+                // both suffixes inside runs of the same byte: the shorter run is common prefix, no need to read it
+                // (zero padding: without this one warp walks up to a megabyte here and the kernel waits for it)
+                if (run_end && known == 0 && T[i] == T[q]) {
+                    const uint32_t ri = run_end[i] - i, rq = run_end[q] - q;
+                    const uint32_t skip = min(ri, rq);
+                    if (skip >= 64) known = skip;
+                }
+                l = known + common_prefix_warp(T + i + known, n - i - known, T + q + known, n - q - known);
             }
-            l = known + common_prefix_warp(T + i + known, n - i - known, T + q + known, n - q - known);
         }
-        if (lane_id() == 0) head_l[i / kChunk] = l;
+        if (lane_id() == 0) out_l[i / stride] = l;
     }
 }
 
@@ -672,30 +682,34 @@ __global__ void __launch_bounds__(256) block_min_kernel(const uint32_t *__restri
     }
 }
 
-// search, level A: chunk heads of [scan_begin, scan_begin+count), one WARP per kSuper positions (uniform
-// control flow, warp-cooperative byte comparisons).  head_p / head_l hold the carry of each head (bit 31 of
-// head_l = less).
+// search, levels S and A: the carry (neighbour of the query with the longer match) of positions `stride` apart,
+// `per_warp` (<= 64) of them per WARP (uniform control flow, warp-cooperative byte comparisons).
+// out_p / out_l [k / stride] hold the carry of table position k (bit 31 of out_l = less).
+//   level S (seeds):  stride = kSuper, seed_* = nullptr;  level A (heads): stride = kChunk, per_warp = kHeads, the
+//   first head of a super comes from level S.  Same reason as in lcp_heads_kernel: a from-scratch search inside a
+//   long match compares the whole match, so only a few thousand warps are ever allowed to start cold.
 __global__ void __launch_bounds__(kThreads)
-search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint32_t *__restrict__ head_p,
-                    uint32_t *__restrict__ head_l, uint32_t super_begin, uint32_t super_end)
+search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint32_t *__restrict__ out_p,
+                    uint32_t *__restrict__ out_l, uint32_t stride, uint32_t per_warp,
+                    const uint32_t *__restrict__ seed_p, const uint32_t *__restrict__ seed_l)
 {
-    // super-chunks [super_begin, super_end) of the search (the host pipelines the table in slices)
-    const uint64_t sc = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + super_begin;
-    const uint64_t k0 = sc * kSuper;
-    if (sc >= super_end || k0 >= count || t.n == 0) return;
-    // pass 1, lanes in parallel: every head tries a capped from-scratch search on its own.  Heads in unrelated
-    // data (short matches, no inheritance possible anyway) finish here; heads inside long matches give up after a
-    // few probes.  Without this pass a warp over a mutated region runs kHeads binary searches back to back.
-    constexpr int kPerLane = kHeads / 32;
-    static_assert(kHeads % 32 == 0, "heads per warp must be a multiple of the warp size");
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t k0 = w * stride * per_warp;
+    if (k0 >= count || t.n == 0) return;
+    // pass 1, lanes in parallel: every position tries a capped from-scratch search on its own.  Positions in
+    // unrelated data (short matches, no inheritance possible anyway) finish here; those inside long matches give up
+    // after a few probes.  Without this pass a warp over a mutated region runs its binary searches back to back.
+    constexpr int kPerLane = 2;
+    static_assert(kHeads <= 32 * kPerLane, "a warp's positions must fit its lanes in pass 1");
     constexpr uint32_t kAbort = 0xffffffffu;
     uint32_t rp[kPerLane], rl[kPerLane];
 #pragma unroll
     for (int q = 0; q < kPerLane; ++q) {
-        const uint64_t kk = k0 + ((uint64_t)lane_id() * kPerLane + q) * kChunk;
+        const uint32_t h = lane_id() * kPerLane + q;
+        const uint64_t kk = k0 + (uint64_t)h * stride;
         rp[q] = 0;
         rl[q] = kAbort;
-        if (kk < count) {
+        if (h < per_warp && kk < count && !(h == 0 && seed_l)) {
             bool aborted;
             const Bracket b = locate_scratch_capped(t, ix, scan_begin + (uint32_t)kk, 128u, &aborted);
             if (!aborted) {
@@ -705,13 +719,17 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
             }
         }
     }
+    if (seed_l && lane_id() == 0) {
+        rp[0] = seed_p[w];
+        rl[0] = seed_l[w];
+    }
     __syncwarp();
-    // pass 2, the warp together: the heads pass 1 left open inherit from their predecessor (or search from
+    // pass 2, the warp together: the positions pass 1 left open inherit from their predecessor (or search from
     // scratch with warp-cooperative comparisons)
     Carry cy{0, 0, false};
     bool have = false;
-    for (int k = 0; k < kHeads; ++k) {
-        const uint64_t kk = k0 + (uint64_t)k * kChunk;
+    for (uint32_t k = 0; k < per_warp; ++k) {
+        const uint64_t kk = k0 + (uint64_t)k * stride;
         if (kk >= count) break;
         const uint32_t j = scan_begin + (uint32_t)kk;
         uint32_t p1 = 0, l1 = kAbort;
@@ -719,7 +737,7 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
         for (int q = 0; q < kPerLane; ++q) {
             const uint32_t pp = __shfl_sync(kFullMask, rp[q], k / kPerLane);
             const uint32_t ll = __shfl_sync(kFullMask, rl[q], k / kPerLane);
-            if (k % kPerLane == q) {
+            if ((int)(k % kPerLane) == q) {
                 p1 = pp;
                 l1 = ll;
             }
@@ -727,13 +745,13 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
         if (l1 != kAbort) {
             cy = Carry{p1, l1 & 0x7fffffffu, (l1 >> 31) != 0};
         } else {
-            const Bracket b = locate_step<true>(t, ix, j, cy, kChunk, have);
+            const Bracket b = locate_step<true>(t, ix, j, cy, stride, have);
             cy = carry_of(t, ix, b);
         }
         have = true;
         if (lane_id() == 0) {
-            head_p[kk / kChunk] = cy.p;
-            head_l[kk / kChunk] = cy.l | (cy.less ? 0x80000000u : 0u);
+            out_p[kk / stride] = cy.p;
+            out_l[kk / stride] = cy.l | (cy.less ? 0x80000000u : 0u);
         }
     }
 }

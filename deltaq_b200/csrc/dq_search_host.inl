@@ -16,6 +16,20 @@ int lcp_levels(uint32_t n, uint32_t size[sr::kMaxLevels])
     return top;
 }
 
+// Supers per warp of the seed level (0 = no seed level).  Seeds pay off when repeats are long -- a warp of the head
+// kernels that starts cold inside a repeat of R bytes compares R bytes, and without seeds every super starts cold --
+// and cost a serial ~0.5 ms otherwise.  Long repeats show in the number of doubling rounds the sort needed
+// (r rounds <=> some repeat of >= 8 * 2^(r-2) bytes); for a suffix array handed in by the caller only the size is
+// known.  With seeds: enough supers per warp to keep the cold starts to about two thousand, at least 8 so short
+// inputs still spread over many warps, at most 64 (the lanes of pass 1).
+uint32_t seeds_per_warp(dq_ctx *ctx, uint32_t n, uint32_t supers)
+{
+    if (const char *e = getenv("DQ_SEEDS_PER")) return (uint32_t)atoi(e);  // tuning only
+    const bool long_repeats = ctx->resident_rounds >= 0 ? ctx->resident_rounds >= 14 : n >= (32u << 20);
+    if (!long_repeats) return 0;
+    return (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(8, div_up(supers, 2048)));
+}
+
 // LCP array + block minima of the resident (ctx->text, ctx->sa, ctx->isa) of length n
 int build_lcp(dq_ctx *ctx, uint32_t n)
 {
@@ -31,9 +45,19 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
     const int32_t *SA = ctx->sa.as<int32_t>();
     const uint32_t *ISA = ctx->isa.as<uint32_t>();
     {
+        // level S then level A (see lcp_heads_kernel)
+        const uint32_t per = seeds_per_warp(ctx, n, supers);
+        DQ_TRY(ensure(ctx, ctx->seedl, (size_t)supers * 4));
+        DQ_TRY(ensure(ctx, ctx->seedp, (size_t)supers * 4));
+        const uint32_t *run = ctx->runend_valid_n == (int32_t)n ? ctx->runend.as<uint32_t>() : nullptr;
         auto k = sr::lcp_heads_kernel;
+        if (per)
+            DQ_LAUNCH(k, (uint32_t)div_up(div_up(supers, per) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+                      ctx->seedl.as<uint32_t>(), run, (uint32_t)sr::kSuper, per, (const uint32_t *)nullptr);
         DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
-                  ctx->headl.as<uint32_t>(), ctx->runend_valid_n == (int32_t)n ? ctx->runend.as<uint32_t>() : nullptr);
+                  ctx->headl.as<uint32_t>(), run, (uint32_t)sr::kChunk, (uint32_t)sr::kHeads,
+                  per ? (const uint32_t *)ctx->seedl.as<uint32_t>() : (const uint32_t *)nullptr);
+        ctx->stats.kernel_launches++;
     }
     {
         auto k = sr::lcp_chain_kernel;
@@ -74,6 +98,23 @@ int ensure_pinned(dq_ctx *ctx, PinBuf &b, size_t bytes)
     return DQ_OK;
 }
 
+// run_end[] of ctx->newtext (m bytes) into ctx->runend_new, on `stream`
+int run_ends_of_new(dq_ctx *ctx, uint32_t m, cudaStream_t stream)
+{
+    const uint32_t ntiles = (uint32_t)div_up(m, sx::kRunTile);
+    DQ_TRY(ensure(ctx, ctx->runend_new, (size_t)m * 4));
+    DQ_TRY(ensure(ctx, ctx->runtile_new, (size_t)ntiles * 8));
+    uint32_t *tile_first = ctx->runtile_new.as<uint32_t>(), *next_after = tile_first + ntiles;
+    auto k1 = sx::run_tile_first_kernel;
+    DQ_LAUNCH(k1, ntiles, 256, 0, stream, ctx->newtext.as<uint8_t>(), m, tile_first);
+    auto k2 = sx::run_tile_scan_kernel;
+    DQ_LAUNCH(k2, 1, 1024, 0, stream, tile_first, ntiles, m, next_after);
+    auto k3 = sx::run_end_kernel;
+    DQ_LAUNCH(k3, ntiles, 256, 0, stream, ctx->newtext.as<uint8_t>(), m, next_after, ctx->runend_new.as<uint32_t>());
+    ctx->runend_new_m = (int32_t)m;
+    return DQ_OK;
+}
+
 // (ctx->text, ctx->sa, ctx->isa) describe `old` (n bytes); ctx->newtext holds `new` (m bytes, padded).
 // Fills ctx->s_pos / ctx->s_len [0, count).
 // coded: pipeline mode for dq_cuda_bsdiff_streams -- the chain kernel runs in kSlices launches, each followed by
@@ -97,17 +138,10 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
     sr::Texts t{ctx->text.as<uint8_t>(), ctx->newtext.as<uint8_t>(), n, m};
     if (ctx->runend_valid_n == (int32_t)n && m > 0) {
         // the sort found `old` full of equal-byte runs: give the comparisons run ends of `new` as well
-        const uint32_t ntiles = (uint32_t)div_up(m, sx::kRunTile);
-        DQ_TRY(ensure(ctx, ctx->runend_new, (size_t)m * 4));
-        DQ_TRY(ensure(ctx, ctx->runtile, (size_t)std::max<uint64_t>(ntiles, div_up(n, sx::kRunTile)) * 8));
-        uint32_t *tile_first = ctx->runtile.as<uint32_t>(), *next_after = tile_first + ntiles;
-        auto k1 = sx::run_tile_first_kernel;
-        DQ_LAUNCH(k1, ntiles, 256, 0, ctx->stream, ctx->newtext.as<uint8_t>(), m, tile_first);
-        auto k2 = sx::run_tile_scan_kernel;
-        DQ_LAUNCH(k2, 1, 1024, 0, ctx->stream, tile_first, ntiles, m, next_after);
-        auto k3 = sx::run_end_kernel;
-        DQ_LAUNCH(k3, ntiles, 256, 0, ctx->stream, ctx->newtext.as<uint8_t>(), m, next_after, ctx->runend_new.as<uint32_t>());
-        ctx->stats.kernel_launches += 3;
+        if (ctx->runend_new_m != (int32_t)m) {
+            DQ_TRY(run_ends_of_new(ctx, m, ctx->stream));
+            ctx->stats.kernel_launches += 3;
+        }
         t.run_old = ctx->runend.as<uint32_t>();
         t.run_new = ctx->runend_new.as<uint32_t>();
     }
@@ -140,10 +174,20 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
     const uint32_t supers_per = (uint32_t)div_up(supers, slices);
     ctx->slices_used = 0;
     {
+        // level S then level A (see search_heads_kernel)
+        const uint32_t per = seeds_per_warp(ctx, n, supers);
+        DQ_TRY(ensure(ctx, ctx->seedl, (size_t)std::max<uint64_t>(supers, div_up(n, sr::kSuper)) * 4));
+        DQ_TRY(ensure(ctx, ctx->seedp, (size_t)std::max<uint64_t>(supers, div_up(n, sr::kSuper)) * 4));
         auto k = sr::search_heads_kernel;
+        if (per)
+            DQ_LAUNCH(k, (uint32_t)div_up(div_up(supers, per) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin,
+                      count, ctx->seedp.as<uint32_t>(), ctx->seedl.as<uint32_t>(), (uint32_t)sr::kSuper, per,
+                      (const uint32_t *)nullptr, (const uint32_t *)nullptr);
         DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, t, ix, scan_begin,
-                  count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), 0u, supers);
-        ctx->stats.kernel_launches++;
+                  count, ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), (uint32_t)sr::kChunk, (uint32_t)sr::kHeads,
+                  per ? (const uint32_t *)ctx->seedp.as<uint32_t>() : (const uint32_t *)nullptr,
+                  per ? (const uint32_t *)ctx->seedl.as<uint32_t>() : (const uint32_t *)nullptr);
+        ctx->stats.kernel_launches += 2;
     }
     if (coded) DQ_CK(ctx, cudaEventRecord(ctx->heads_done, ctx->stream));
     for (int sl = 0; sl < slices; ++sl) {
@@ -190,6 +234,7 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
 int adopt_index(dq_ctx *ctx, const uint8_t *old_, uint32_t n, const int32_t *I, cudaMemcpyKind kind)
 {
     ctx->resident_n = -1;
+    ctx->resident_rounds = -1;
     ctx->lcp_valid = false;
     ctx->runend_valid_n = -1;
     DQ_TRY(upload_text(ctx, ctx->text, old_, n, kind));
@@ -228,6 +273,7 @@ int search_common(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I,
         ctx->stats.kernel_launches = launches_before;
     }
     DQ_TRY(upload_text(ctx, ctx->newtext, new_, (uint32_t)m, in));
+    ctx->runend_new_m = -1;
     DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, (uint32_t)scan_begin, (uint32_t)count));
     if (count) {
         DQ_CK(ctx, cudaMemcpyAsync(pos_out, ctx->s_pos.p, (size_t)count * 4, out, ctx->stream));

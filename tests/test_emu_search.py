@@ -123,3 +123,17 @@ def test_coded_table_overflow_falls_back_to_full_table(monkeypatch):
             s.dispose()
         for k in ("ctrl", "diff", "extra"):
             assert got[k] == ref[k], (cap, k)
+
+
+@pytest.mark.parametrize("per", ["1", "3", "64"])
+def test_seed_level_of_the_head_kernels(sorter, per, monkeypatch):
+    # lcp_heads_kernel / search_heads_kernel run a sparse seed level first when the text has long repeats;
+    # DQ_SEEDS_PER forces it on (with that many supers per warp) for inputs of any size
+    monkeypatch.setenv("DQ_SEEDS_PER", per)
+    for old, new in list(small_random_pairs(count=12, seed=5)) + [structured_pairs()[k] for k in sorted(structured_pairs())[:6]]:
+        check_pair(sorter, old, new)
+    rng = np.random.default_rng(9)
+    blk = rng.integers(0, 256, 3000, dtype=np.uint8)
+    old = np.concatenate([blk, rng.integers(0, 256, 500, dtype=np.uint8), blk, blk[:1500], blk])   # long repeats, > 1 super
+    new = np.concatenate([blk[100:], blk, rng.integers(0, 256, 300, dtype=np.uint8), old[2000:9000]])
+    check_pair(sorter, old, new)
