@@ -53,6 +53,14 @@ typedef struct dq_stats {
     int32_t table_heads;       /* dq_cuda_bsdiff_streams: match heads in the coded table (12 B each over PCIe, + 1 B/position) */
 } dq_stats;
 
+/* Environment variables read by the library (tests and tuning only; none changes a result):
+ *   DQ_TRACE=1            dq_cuda_bsdiff_streams prints its host/device timeline to stderr
+ *   DQ_HOST_THREADS=h,w[,part_kib,min_kib]  helper walkers / writer threads of the host greedy loop
+ *   DQ_HEADS_CAP=k        capacity of the match-head list of the coded (pos,len) table (forces the full-table fallback)
+ *   DQ_SEEDS_PER=k        super-chunks per warp of the seed level of the search's head kernels (0 = off)
+ *   DQ_MATCH_POLICY=0|1|2 which radix passes of a doubling round rank with MATCH.ANY
+ */
+
 /* ---- context ------------------------------------------------------------------------------------ */
 
 /* devices/ndev: CUDA ordinals to use; NULL/0 = current device.  This build drives one device per context

@@ -12,38 +12,46 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deltaq_b200 import CudaSuffixSort, bsdiff, workloads as w  # noqa: E402
 
-mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1945
+c5 = "--c5" in sys.argv          # BASELINE's C5 recipe itself (workloads._exe_like / _mutate at full size; slower to generate)
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+mib = int(args[0]) if args else 1945
 n = mib << 20
 rng = np.random.default_rng(5)
 t0 = time.time()
-base = w.c2_exe_pair(64 << 20, (64 << 20) + 1)[0]
-parts = []
-total = 0
-while total < n:
-    parts.append(base if (len(parts) % 3) else rng.integers(0, 256, base.size, dtype=np.uint8))
-    total += base.size
-old = np.concatenate(parts)[:n]
-del parts
-# new = old with ~200 edits (overwrites / inserts / deletes of up to 1 MiB), built by slicing
-cuts = np.sort(rng.integers(0, n, 200))
-out = []
-cur = 0
-for c in cuts:
-    c = int(max(c, cur))
-    out.append(old[cur:c])
-    op = int(rng.integers(0, 3))
-    k = int(rng.integers(64, 1 << 20))
-    if op == 0:
-        out.append(rng.integers(0, 256, k, dtype=np.uint8)); cur = min(n, c + k)
-    elif op == 1:
-        out.append(rng.integers(0, 256, k, dtype=np.uint8)); cur = c
-    else:
-        cur = min(n, c + k)
-out.append(old[cur:])
-new = np.concatenate(out)
-if new.size > 2_100_000_000:
-    new = new[:2_100_000_000]
-del out
+if c5:
+    n = 2_040_109_466 if not args else n
+    old = w._exe_like(n, np.random.default_rng(5))
+    new = w._mutate(old, np.random.default_rng(105), min(n + n // 16, 2_100_000_000), regions=2000)
+    print(f"C5 recipe: old={old.size} new={new.size} in {time.time()-t0:.0f}s", flush=True)
+base = None if c5 else w.c2_exe_pair(64 << 20, (64 << 20) + 1)[0]
+if not c5:
+    parts = []
+    total = 0
+    while total < n:
+        parts.append(base if (len(parts) % 3) else rng.integers(0, 256, base.size, dtype=np.uint8))
+        total += base.size
+    old = np.concatenate(parts)[:n]
+    del parts
+    # new = old with ~200 edits (overwrites / inserts / deletes of up to 1 MiB), built by slicing
+    cuts = np.sort(rng.integers(0, n, 200))
+    out = []
+    cur = 0
+    for c in cuts:
+        c = int(max(c, cur))
+        out.append(old[cur:c])
+        op = int(rng.integers(0, 3))
+        k = int(rng.integers(64, 1 << 20))
+        if op == 0:
+            out.append(rng.integers(0, 256, k, dtype=np.uint8)); cur = min(n, c + k)
+        elif op == 1:
+            out.append(rng.integers(0, 256, k, dtype=np.uint8)); cur = c
+        else:
+            cur = min(n, c + k)
+    out.append(old[cur:])
+    new = np.concatenate(out)
+    if new.size > 2_100_000_000:
+        new = new[:2_100_000_000]
+    del out
 print(f"generated old={old.size} new={new.size} in {time.time()-t0:.0f}s", flush=True)
 s = CudaSuffixSort()
 ctx = s.context
@@ -67,4 +75,4 @@ rec = dict(old_bytes=int(old.size), new_bytes=int(new.size), e2e_ms=best * 1e3, 
            search_visits=int(st["search_visits"]), ctrl_triples=int(st["ctrl"].size // 24), round_trip_ok=bool(ok))
 print(json.dumps(rec), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rec, open("gpurun_out/big_bsdiff.json", "w"))
+json.dump(rec, open("gpurun_out/big_bsdiff_c5.json" if c5 else "gpurun_out/big_bsdiff.json", "w"))
