@@ -55,7 +55,7 @@ struct dq_ctx {
 
     // suffix-sort state (device)
     DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
-        runtile, runend_new, runtile_new, seedp, seedl;
+        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -68,6 +68,7 @@ struct dq_ctx {
     int32_t runend_new_m = -1;    // runend_new[] describes ctx->newtext of this length
     int32_t runend_valid_n = -1;  // runend[] describes the resident text of this length (set by a run-aware sort)
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
+    bool pre3_valid = false; // pre3 describes the resident text
 
     // multi-GPU session (dq_cuda_dist_*): the unresolved set between calls
     uint64_t *dist_kin = nullptr, *dist_kout = nullptr;
@@ -268,6 +269,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     st.n = (int32_t)n;
     ctx->pass_events_used = 0;
     ctx->lcp_valid = false;
+    ctx->pre3_valid = false;
     ctx->runend_valid_n = -1;
     if (n == 0) return DQ_OK;
 
@@ -526,7 +528,7 @@ int dq_cuda_destroy(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
-                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->newtext, &ctx->s_pos,
+                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -829,6 +831,15 @@ void export_streams(dq_ctx *ctx, dq_diff_streams *out)
 }
 }  // namespace
 
+#ifdef DQ_PROF
+extern "C" int dq_debug_read_prof(uint32_t *chains, uint32_t *heads)
+{
+    if (cudaMemcpyFromSymbol(chains, dq::search::g_prof_chain, sizeof(uint32_t) << 21) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(heads, dq::search::g_prof_heads, sizeof(uint32_t) << 16) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
+
 #ifdef DQ_EMU
 extern "C" void dq_emu_debug_counters(unsigned long long *out, int reset)
 {
@@ -980,6 +991,7 @@ int dq_cuda_dist_round0(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_v
     DQ_CK(ctx, cudaSetDevice(ctx->device));
     ctx->resident_n = -1;
     ctx->lcp_valid = false;
+    ctx->pre3_valid = false;
     ctx->dist_a = 0;
     *active_out = 0;
     if (count == 0) return DQ_OK;

@@ -211,7 +211,31 @@ struct Index {
     // 2-byte prefix buckets: ranks [bkt_lo[k], bkt_hi[k]) hold exactly the suffixes (>= 2 bytes long) that
     // start with the byte pair k
     const uint32_t *bkt_lo, *bkt_hi;
+    // 3-byte prefix table (prefix3_* kernels below), or nullptr: pre3[k] = number of suffixes >= 3 bytes long whose
+    // first three bytes, read as a big-endian number, are < k (k in [0, 2^24]); pre3[2^24 + 1] and [2^24 + 2] hold
+    // the zero-padded 3-byte values of the 1-byte and the 2-byte suffix at the end of the text (kNone if n is too
+    // short to have them).  Ranks [lo, hi) = [pre3[k] + a, pre3[k+1] + a), a = how many of those two values are <= k,
+    // hold exactly the suffixes (>= 3 bytes long) that start with k.
+    const uint32_t *pre3;
 };
+
+constexpr uint32_t kPrefix3Bins = 1u << 24;
+
+#ifdef DQ_PROF
+// debug build only (scripts/prof_chains.py): elapsed clocks / 64 of every chain of the last search_chain_kernel and
+// of every warp of the last search_heads_kernel launch
+__device__ uint32_t g_prof_chain[1u << 21];
+__device__ uint32_t g_prof_heads[1u << 16];
+#endif
+
+// rank interval of the suffixes that start with the three bytes at q (see Index::pre3)
+__device__ __forceinline__ void prefix3_bounds(const Index &ix, const uint8_t *q, uint32_t *lo, uint32_t *hi)
+{
+    const uint32_t k = ((uint32_t)q[0] << 16) | ((uint32_t)q[1] << 8) | q[2];
+    const uint32_t a = (uint32_t)(ix.pre3[kPrefix3Bins + 1] <= k) + (uint32_t)(ix.pre3[kPrefix3Bins + 2] <= k);
+    *lo = ix.pre3[k] + a;
+    *hi = ix.pre3[k + 1] + a;
+}
 
 struct Bracket {
     uint32_t L;  // #{old suffixes < query}
@@ -232,7 +256,13 @@ __device__ __forceinline__ Bracket locate_scratch(const Texts &t, const Index &i
     int64_t lo = -1, hi = n;
     uint32_t llo = 0, lhi = 0;
     bool lo_virtual = true, hi_virtual = true;  // bounds not yet compared with the query
-    if (t.m - j >= 2) {
+    if (ix.pre3 && t.m - j >= 3) {
+        uint32_t b_lo, b_hi;
+        prefix3_bounds(ix, t.new_ + j, &b_lo, &b_hi);
+        lo = (int64_t)b_lo - 1;
+        hi = b_hi;
+        llo = lhi = 3;  // every suffix strictly inside shares the three bytes
+    } else if (t.m - j >= 2) {
         const uint32_t k = ((uint32_t)t.new_[j] << 8) | t.new_[j + 1];
         lo = (int64_t)ix.bkt_lo[k] - 1;
         hi = ix.bkt_hi[k];
@@ -273,7 +303,13 @@ __device__ __forceinline__ Bracket locate_scratch_capped(const Texts &t, const I
     uint32_t llo = 0, lhi = 0;
     bool lo_virtual = true, hi_virtual = true;
     *aborted = false;
-    if (t.m - j >= 2) {
+    if (ix.pre3 && t.m - j >= 3) {
+        uint32_t b_lo, b_hi;
+        prefix3_bounds(ix, t.new_ + j, &b_lo, &b_hi);
+        lo = (int64_t)b_lo - 1;
+        hi = b_hi;
+        llo = lhi = 3;
+    } else if (t.m - j >= 2) {
         const uint32_t k = ((uint32_t)t.new_[j] << 8) | t.new_[j + 1];
         lo = (int64_t)ix.bkt_lo[k] - 1;
         hi = ix.bkt_hi[k];
@@ -568,6 +604,126 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint8_t *__res
     }
 }
 
+// ---- 3-byte prefix table (Index::pre3) -----------------------------------------------------------------------
+// Needs only the text, not the suffix array: a histogram of the 3-byte prefixes of all suffixes (equal keys inside a
+// warp are added with one atomic: zero padding would otherwise send a million increments to one address), then an
+// exclusive scan over the 2^24 bins in three small kernels.
+__global__ void __launch_bounds__(256) prefix3_hist_kernel(const uint8_t *__restrict__ T, uint32_t n,
+                                                            uint32_t *__restrict__ hist)
+{
+    const uint64_t total = n >= 3 ? (uint64_t)n - 2 : 0;  // suffixes with >= 3 bytes
+    const uint64_t span = (total + 31) & ~(uint64_t)31;  // whole warps: the match below is warp-wide
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < span; p += (uint64_t)gridDim.x * blockDim.x) {
+        const bool valid = p < total;
+        const uint32_t key = valid ? (((uint32_t)T[p] << 16) | ((uint32_t)T[p + 1] << 8) | T[p + 2]) : (0xff000000u + lane_id());
+        const unsigned same = __match_any_sync(kFullMask, key);
+        if (valid && (unsigned)(__ffs((int)same) - 1) == lane_id()) atomicAdd(hist + key, (uint32_t)__popc(same));
+    }
+}
+
+constexpr uint32_t kPrefix3Tile = 4096;  // bins per block of the scan kernels (256 threads x 16)
+constexpr uint32_t kPrefix3Tiles = kPrefix3Bins / kPrefix3Tile;
+
+__global__ void __launch_bounds__(256) prefix3_tile_sum_kernel(const uint32_t *__restrict__ hist,
+                                                                uint32_t *__restrict__ tile_sum)
+{
+    __shared__ uint32_t warp_sum[8];
+    const uint4 *src = reinterpret_cast<const uint4 *>(hist + (size_t)blockIdx.x * kPrefix3Tile) + threadIdx.x * 4;
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = src[q];
+        s += v.x + v.y + v.z + v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    if (lane_id() == 0) warp_sum[warp_id()] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; ++w) tot += warp_sum[w];
+        tile_sum[blockIdx.x] = tot;
+    }
+}
+
+// one block: exclusive scan of the kPrefix3Tiles tile sums in place; also the tail of the table (total, and the padded
+// values of the two short suffixes)
+__global__ void __launch_bounds__(1024) prefix3_tile_scan_kernel(uint32_t *__restrict__ tile_sum, const uint8_t *__restrict__ T,
+                                                                  uint32_t n, uint32_t *__restrict__ table)
+{
+    static_assert(kPrefix3Tiles == 4096, "four tile sums per thread");
+    __shared__ uint32_t warp_sum[32];
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[q] = tile_sum[threadIdx.x * 4 + q];
+        s += v[q];
+    }
+    uint32_t incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFullMask, incl, d);
+        if ((int)lane_id() >= d) incl += u;
+    }
+    if (lane_id() == 31) warp_sum[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+        const uint32_t w = warp_sum[lane_id()];
+        uint32_t wi = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(kFullMask, wi, d);
+            if ((int)lane_id() >= d) wi += u;
+        }
+        warp_sum[lane_id()] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_sum[warp_id()] + incl - s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        tile_sum[threadIdx.x * 4 + q] = run;
+        run += v[q];
+    }
+    if (threadIdx.x == 0) {
+        table[kPrefix3Bins] = n >= 3 ? n - 2 : 0u;
+        table[kPrefix3Bins + 1] = n >= 1 ? ((uint32_t)T[n - 1] << 16) : kNone;
+        table[kPrefix3Bins + 2] = n >= 2 ? (((uint32_t)T[n - 2] << 16) | ((uint32_t)T[n - 1] << 8)) : kNone;
+    }
+}
+
+__global__ void __launch_bounds__(256) prefix3_apply_kernel(uint32_t *__restrict__ table, const uint32_t *__restrict__ tile_off)
+{
+    __shared__ uint32_t warp_sum[8];
+    uint4 *dst = reinterpret_cast<uint4 *>(table + (size_t)blockIdx.x * kPrefix3Tile) + threadIdx.x * 4;
+    uint4 v[4];
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[q] = dst[q];
+        s += v[q].x + v[q].y + v[q].z + v[q].w;
+    }
+    uint32_t incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFullMask, incl, d);
+        if ((int)lane_id() >= d) incl += u;
+    }
+    if (lane_id() == 31) warp_sum[warp_id()] = incl;
+    __syncthreads();
+    uint32_t run = tile_off[blockIdx.x] + incl - s;
+    for (int w = 0; w < (int)warp_id(); ++w) run += warp_sum[w];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = run;
+        run += v[q].x;
+        o.y = run;
+        run += v[q].y;
+        o.z = run;
+        run += v[q].z;
+        o.w = run;
+        run += v[q].w;
+        dst[q] = o;
+    }
+}
+
 // LCP array, levels S and A.  One WARP walks `per_warp` text positions `stride` apart; the byte comparisons are
 // warp-cooperative (a position inside a long repeat costs length/256 steps, not length/8), and each position
 // starts from what the one before it leaves: PLCP[i + stride] >= PLCP[i] - stride.  out_l[i / stride] = PLCP[i].
@@ -696,6 +852,10 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
     const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t k0 = w * stride * per_warp;
     if (k0 >= count || t.n == 0) return;
+#ifdef DQ_PROF
+    const long long prof_t0 = clock64();
+    struct ProfFin { long long t0; uint64_t w; __device__ ~ProfFin() { if (w < (1u << 16) && lane_id() == 0) g_prof_heads[w] = (uint32_t)((clock64() - t0) >> 6); } } prof_fin{prof_t0, w};
+#endif
     // pass 1, lanes in parallel: every position tries a capped from-scratch search on its own.  Positions in
     // unrelated data (short matches, no inheritance possible anyway) finish here; those inside long matches give up
     // after a few probes.  Without this pass a warp over a mutated region runs its binary searches back to back.
@@ -753,6 +913,31 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
             out_p[kk / stride] = cy.p;
             out_l[kk / stride] = cy.l | (cy.less ? 0x80000000u : 0u);
         }
+        // Inside a long match the following positions are predictable (see search_chain_kernel): lane s checks
+        // position k+s -- anchor (p + s*stride, l - s*stride, same side), neighbour on the query's side sharing
+        // less -- and the run of positions that check out is written at once, with no byte compared.
+        {
+            const uint32_t s1 = lane_id();
+            const uint32_t *LCP = ix.lv[0];
+            bool ok = false;
+            uint32_t ps = 0, cs = 0;
+            if (s1 >= 1 && k + s1 < per_warp && kk + (uint64_t)s1 * stride < count && cy.l >= s1 * stride + kMinAnchor) {
+                ps = cy.p + s1 * stride;
+                cs = cy.l - s1 * stride;
+                const uint32_t r = ix.ISA[ps];
+                const bool edge = cy.less ? (r + 1 >= t.n) : (r == 0);
+                ok = !edge && LCP[cy.less ? r + 1 : r] < cs;
+            }
+            const unsigned m = __ballot_sync(kFullMask, ok) >> 1;
+            const uint32_t run = (uint32_t)__ffs((int)~m) - 1u;  // consecutive lanes 1..run checked out (<= 31)
+            if (s1 >= 1 && s1 <= run) {
+                out_p[kk / stride + s1] = ps;
+                out_l[kk / stride + s1] = cs | (cy.less ? 0x80000000u : 0u);
+            }
+            k += run;
+            cy.p += run * stride;
+            cy.l -= run * stride;
+        }
     }
 }
 
@@ -767,6 +952,10 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + chain_begin;
     const uint64_t k0 = c * kChunk;
     if (c >= chain_end || k0 >= count) return;
+#ifdef DQ_PROF
+    const long long prof_t0 = clock64();
+    struct ProfFin { long long t0; uint64_t c; __device__ ~ProfFin() { if (c < (1u << 21)) g_prof_chain[c] = (uint32_t)((clock64() - t0) >> 6); } } prof_fin{prof_t0, c};
+#endif
     DQ_DBG(unsigned long long b0 = g_dbg.cmp_bytes + 64 * g_dbg.probes;)
     DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes + 64 * g_dbg.probes - b0; g_dbg.thr_max[1] = max(g_dbg.thr_max[1], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[1][k]++; } } fin{b0};)
     if (t.n == 0) {
@@ -793,6 +982,8 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
         if (nl >= kBackMin)
             back = common_suffix(t.new_ + scan_begin + k0 + kChunk, t.old_ + np, min((uint32_t)kChunk - 1, np));
     }
+    const uint32_t *LCP = ix.lv[0];
+    const uint32_t n = t.n;
     for (int k = 0; k < kChunk; ++k) {
         const uint64_t kk = k0 + k;
         if (kk >= count) break;
@@ -809,6 +1000,39 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
         cy = reference_result(t, ix, j, b, &pos, &len);
         pos_out[kk] = pos;
         len_out[kk] = len;
+        // Inside a long match the next positions are predictable: position k+s inherits the anchor (p+s, l-s, same
+        // side), and when that suffix's neighbour on the query's side shares fewer than l-s bytes with it, the anchor
+        // IS the answer: pos = p+s, len = l-s (locate_anchor's first exit and reference_result's strict case, with no
+        // byte compared).  The kBatch ranks and their kBatch LCP entries are independent reads, so they are issued
+        // together instead of as 2*kBatch dependent round trips; the run of positions that check out is written at
+        // once and the loop resumes at the first one that does not.
+        while (k + 1 < kChunk) {
+            constexpr int kBatch = 8;
+            const int room = min(kBatch, kChunk - 1 - k);
+            if (cy.l < (uint32_t)room + kMinAnchor || k0 + k + room >= count) break;
+            uint32_t rr[kBatch], gg[kBatch];
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s) rr[s - 1] = s <= room ? ix.ISA[cy.p + s] : 0u;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s) {
+                const uint32_t r = rr[s - 1];
+                // the entry between the anchor and its neighbour on the query's side; edge ranks go the general way
+                const bool edge = cy.less ? (r + 1 >= n) : (r == 0);
+                gg[s - 1] = (s <= room && !edge) ? LCP[cy.less ? r + 1 : r] : 0xffffffffu;
+            }
+            int run = 0;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s)
+                if (run == s - 1 && s <= room && gg[s - 1] < cy.l - (uint32_t)s) run = s;
+            for (int s = 1; s <= run; ++s) {
+                pos_out[k0 + k + s] = (int32_t)(cy.p + s);
+                len_out[k0 + k + s] = (int32_t)(cy.l - s);
+            }
+            k += run;
+            cy.p += (uint32_t)run;
+            cy.l -= (uint32_t)run;
+            if (run < room) break;
+        }
     }
 }
 

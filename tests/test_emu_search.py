@@ -137,3 +137,18 @@ def test_seed_level_of_the_head_kernels(sorter, per, monkeypatch):
     old = np.concatenate([blk, rng.integers(0, 256, 500, dtype=np.uint8), blk, blk[:1500], blk])   # long repeats, > 1 super
     new = np.concatenate([blk[100:], blk, rng.integers(0, 256, 300, dtype=np.uint8), old[2000:9000]])
     check_pair(sorter, old, new)
+
+
+def test_prefix3_table_for_scratch_searches(sorter, monkeypatch):
+    # from a megabyte of text the from-scratch searches start from a 3-byte prefix table instead of the 2-byte
+    # buckets; DQ_PREFIX3=1 turns it on for small inputs (the two short suffixes at the end of old are the edge)
+    monkeypatch.setenv("DQ_PREFIX3", "1")
+    pairs = list(small_random_pairs(count=8, seed=77))
+    pairs += [structured_pairs()[k] for k in sorted(structured_pairs())[:2]]
+    rng = np.random.default_rng(3)
+    for tail in (b"", b"\x00", b"\x00\x00", b"ab", b"\xff\xff\xff"):                   # old ends in short suffixes that
+        old = np.frombuffer(rng.integers(0, 3, 300, dtype=np.uint8).tobytes() + tail, dtype=np.uint8)  # pad to real prefixes
+        new = np.concatenate([rng.integers(0, 3, 200, dtype=np.uint8), np.frombuffer(tail + b"\x00\x00\x01", dtype=np.uint8), old[50:150]])
+        pairs.append((old, new))
+    for old, new in pairs:
+        check_pair(sorter, old, new, with_streams=False)
