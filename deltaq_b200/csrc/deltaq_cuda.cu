@@ -832,6 +832,16 @@ void export_streams(dq_ctx *ctx, dq_diff_streams *out)
 }  // namespace
 
 #ifdef DQ_PROF
+extern "C" int dq_debug_read_prof_cmp(unsigned long long *clk, unsigned long long *bytes, unsigned int *calls)
+{
+    if (cudaMemcpyFromSymbol(clk, dq::search::g_prof_cmp_clk, 8u << 16) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(bytes, dq::search::g_prof_cmp_bytes, 8u << 16) != cudaSuccess) return -1;
+    return cudaMemcpyFromSymbol(calls, dq::search::g_prof_cmp_calls, 4u << 16) == cudaSuccess ? 0 : -1;
+}
+extern "C" int dq_debug_read_prof_seeds(uint32_t *seeds)
+{
+    return cudaMemcpyFromSymbol(seeds, dq::search::g_prof_seeds, sizeof(uint32_t) << 16) == cudaSuccess ? 0 : -1;
+}
 extern "C" int dq_debug_read_prof(uint32_t *chains, uint32_t *heads)
 {
     if (cudaMemcpyFromSymbol(chains, dq::search::g_prof_chain, sizeof(uint32_t) << 21) != cudaSuccess) return -1;

@@ -45,16 +45,25 @@ inline DebugCounters g_dbg;
 #define DQ_DBG(x)
 #endif
 
-// 8 bytes at an arbitrary address; the buffers are padded so that reading up to 15 bytes past p is safe
+#ifdef DQ_PROF
+// debug build only (scripts/prof_chains.py): clocks / bytes a warp spends inside common_prefix_warp (reset by the level-A
+// launch of search_heads_kernel, so they describe that launch)
+__device__ unsigned long long g_prof_cmp_clk[1u << 16];
+__device__ unsigned long long g_prof_cmp_bytes[1u << 16];
+__device__ unsigned int g_prof_cmp_calls[1u << 16];
+#endif
+
+// 8 bytes at an arbitrary address; the buffers are padded so that reading up to 16 bytes past p is safe
 __device__ __forceinline__ uint64_t load64u(const uint8_t *p)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
     const unsigned sh = (unsigned)(a & 7u) * 8u;
+    // no branch on the alignment: both words are always read, so the loads of several calls can all be in flight
+    // before the first result is needed (the warp-cooperative comparison issues up to 64 of them per lane)
     const uint64_t lo = __ldg(w);
-    if (sh == 0) return lo;
     const uint64_t hi = __ldg(w + 1);
-    return (lo >> sh) | (hi << (64u - sh));
+    return (lo >> sh) | (sh ? (hi << ((64u - sh) & 63u)) : 0ull);
 }
 
 // number of equal leading bytes of a[0..la) and b[0..lb).  Both buffers are readable (zero padded) for 64
@@ -117,46 +126,61 @@ __device__ __forceinline__ uint32_t common_prefix(const uint8_t *a, uint32_t la,
 }
 
 // warp-cooperative version: all 32 lanes call it with the same arguments and get the same result.  The first
-// step compares 256 bytes (lane l takes the 8 bytes at 8l) so that short matches cost one round trip; long
-// matches continue 1 KiB per step (four independent 8-byte words per lane per stream).
+// step compares 256 bytes (lane l takes the 8 bytes at 8l) so that short matches cost one round trip; the next one
+// 1 KiB; long matches then continue 4 KiB per step (sixteen independent 8-byte words per lane per stream in flight:
+// a warp inside a repeat of R bytes is bound by round trips, R / 4 KiB of them).
+template <int kWords>
+__device__ __forceinline__ bool common_prefix_warp_step(const uint8_t *a, const uint8_t *b, uint32_t k, uint32_t lim,
+                                                        uint32_t *result)
+{
+    // word w of lane l covers bytes k + 256w + 8l: each of the loads of a warp is one coalesced 256 B row
+    const uint32_t lane = lane_id();
+    // Every load is issued unconditionally (offsets past the end are clamped to lim: the buffers are readable there)
+    // and masked afterwards.  A conditional load puts each word into its own divergence region, the compiler waits
+    // for it before entering the next one, and the warp moves 256 bytes per round trip instead of 256 * kWords
+    // (measured: 0.64 GB/s per warp, profiles/r01_search_chain_timing.md).
+    uint64_t x[kWords];
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) {
+        const uint32_t off = k + 256u * w + lane * 8u;
+        const uint32_t at = min(off, lim);
+        x[w] = load64u(a + at) ^ load64u(b + at);
+    }
+#pragma unroll
+    for (int w = 0; w < kWords; ++w)
+        if (k + 256u * w + lane * 8u >= lim) x[w] = 0ull;
+    DQ_DBG(g_dbg.cmp_bytes += 8 * kWords;)
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) {
+        const unsigned m = __ballot_sync(kFullMask, x[w] != 0);
+        if (m) {
+            const int first = __ffs((int)m) - 1;
+            const uint64_t xx = __shfl_sync(kFullMask, x[w], first);
+            *result = min(k + 256u * w + (uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
+            return true;
+        }
+    }
+    return false;
+}
+
 __device__ __forceinline__ uint32_t common_prefix_warp(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
 {
     const uint32_t lim = min(la, lb);
-    const uint32_t lane = lane_id();
     if (lim == 0) return 0;
-    {
-        const uint32_t off = lane * 8u;
-        uint64_t x = 0;
-        if (off < lim) x = load64u(a + off) ^ load64u(b + off);
-        DQ_DBG(g_dbg.cmp_bytes += 8;)
-        const unsigned m = __ballot_sync(kFullMask, x != 0);
-        if (m) {
-            const int first = __ffs((int)m) - 1;
-            const uint64_t xx = __shfl_sync(kFullMask, x, first);
-            return min((uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
-        }
-        if (lim <= 256) return lim;
-    }
-    for (uint32_t k = 256; k < lim; k += 1024) {
-        // word w of lane l covers bytes k + 256w + 8l: each of the four loads of a warp is one coalesced 256 B row
-        uint64_t x[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t off = k + 256u * w + lane * 8u;
-            x[w] = off < lim ? (load64u(a + off) ^ load64u(b + off)) : 0ull;
-        }
-        DQ_DBG(g_dbg.cmp_bytes += 32;)
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const unsigned m = __ballot_sync(kFullMask, x[w] != 0);
-            if (m) {
-                const int first = __ffs((int)m) - 1;
-                const uint64_t xx = __shfl_sync(kFullMask, x[w], first);
-                return min(k + 256u * w + (uint32_t)first * 8u + ((uint32_t)(__ffsll((long long)xx) - 1) >> 3), lim);
-            }
-        }
-    }
-    return lim;
+#ifdef DQ_PROF
+    const long long pt0 = clock64();
+    struct PF { long long t0; uint32_t *res; __device__ ~PF() { const uint32_t w = (uint32_t)((((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) & 0xffffu); if (lane_id() == 0) { g_prof_cmp_clk[w] += (unsigned long long)(clock64() - t0); g_prof_cmp_bytes[w] += *res; g_prof_cmp_calls[w] += 1; } } };
+    uint32_t r = lim;
+    PF pf{pt0, &r};
+#else
+    uint32_t r;
+#endif
+    if (common_prefix_warp_step<1>(a, b, 0, lim, &r)) return r;
+    if (lim <= 256) return r = lim;
+    if (common_prefix_warp_step<4>(a, b, 256, lim, &r)) return r;
+    for (uint32_t k = 1280; k < lim; k += 4096)
+        if (common_prefix_warp_step<16>(a, b, k, lim, &r)) return r;
+    return r = lim;
 }
 
 template <bool WARP>
@@ -226,6 +250,7 @@ constexpr uint32_t kPrefix3Bins = 1u << 24;
 // of every warp of the last search_heads_kernel launch
 __device__ uint32_t g_prof_chain[1u << 21];
 __device__ uint32_t g_prof_heads[1u << 16];
+__device__ uint32_t g_prof_seeds[1u << 16];
 #endif
 
 // rank interval of the suffixes that start with the three bytes at q (see Index::pre3)
@@ -853,8 +878,9 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
     const uint64_t k0 = w * stride * per_warp;
     if (k0 >= count || t.n == 0) return;
 #ifdef DQ_PROF
+    if (seed_l != nullptr && lane_id() == 0 && w < (1u << 16)) g_prof_cmp_clk[w] = 0, g_prof_cmp_bytes[w] = 0, g_prof_cmp_calls[w] = 0;
     const long long prof_t0 = clock64();
-    struct ProfFin { long long t0; uint64_t w; __device__ ~ProfFin() { if (w < (1u << 16) && lane_id() == 0) g_prof_heads[w] = (uint32_t)((clock64() - t0) >> 6); } } prof_fin{prof_t0, w};
+    struct ProfFin { long long t0; uint64_t w; bool seeds; __device__ ~ProfFin() { if (w < (1u << 16) && lane_id() == 0) (seeds ? g_prof_seeds : g_prof_heads)[w] = (uint32_t)((clock64() - t0) >> 6); } } prof_fin{prof_t0, w, seed_l == nullptr && stride == (uint32_t)kSuper};
 #endif
     // pass 1, lanes in parallel: every position tries a capped from-scratch search on its own.  Positions in
     // unrelated data (short matches, no inheritance possible anyway) finish here; those inside long matches give up

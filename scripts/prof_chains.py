@@ -15,7 +15,16 @@ out = os.path.join(ROOT, "gpurun_out", "libdq_prof.so")
 subprocess.check_call([build.nvcc_path()] + build.NVCC_FLAGS + ["-DDQ_PROF", "-I", build.INCLUDE, "-o", out,
                                                                   os.path.join(build.CSRC, "deltaq_cuda.cu")])
 lib = _native.Library(out)
-old, new = w.c2_exe_pair()
+if len(sys.argv) > 1 and sys.argv[1] == "rep":
+    # 16 MiB made of four copies of a 4 MiB block with fresh random blocks in between (long repeats: the seed level runs)
+    rng = np.random.default_rng(5)
+    base = w.c2_exe_pair(4 << 20, (4 << 20) + 1)[0]
+    old = np.concatenate([base if k % 3 else rng.integers(0, 256, base.size, dtype=np.uint8) for k in range(4)])
+    new = old.copy()
+    for c in rng.integers(0, old.size - 70000, 12):
+        new[c:c + int(rng.integers(64, 65536))] = 7
+else:
+    old, new = w.c2_exe_pair()
 ctx = _native.Context(lib=lib)
 sa = ctx.pinned(old.size, np.int32)
 pos = ctx.pinned(new.size, np.int32)
@@ -54,9 +63,23 @@ for lo, hi in [(0, 0.01), (0.01, 0.5), (0.5, 0.99), (0.99, 1.01)]:
     m = (fs >= lo) & (fs < hi)
     if m.any():
         print("  warps with short fraction in [%.2f, %.2f): %6d mean %.1f us p99 %.1f max %.1f" % (lo, hi, m.sum(), h[m].mean(), np.percentile(h[m], 99), h[m].max()))
+clk = np.zeros(1 << 16, dtype=np.uint64)
+byt = np.zeros(1 << 16, dtype=np.uint64)
+calls = np.zeros(1 << 16, dtype=np.uint32)
+lib.L.dq_debug_read_prof_cmp.argtypes = [ctypes.c_void_p] * 3
+assert lib.L.dq_debug_read_prof_cmp(clk.ctypes.data, byt.ctypes.data, calls.ctypes.data) == 0
 order = np.argsort(-h)[:15]
+print("slowest warps: (us total, us inside common_prefix_warp, calls, bytes compared, position, len min/median/max, short fraction)")
 for i in order:
     a = i * 2048
     seg = L[a:a + 2048]
-    print("  %8.1f  %9d  len min/median/max %d/%d/%d  short %.2f  %s" % (h[i], a, seg.min(), int(np.median(seg)), seg.max(), fs[i], bytes(new[a:a + 12]).hex()))
+    print("  %8.1f  cmp %8.1f us %5d calls %10d B  %9d  len %d/%d/%d  short %.2f  %s" % (
+        h[i], clk[i] / 1.965e3, calls[i], byt[i], a, seg.min(), int(np.median(seg)), seg.max(), fs[i], bytes(new[a:a + 12]).hex()))
+seeds = np.zeros(1 << 16, dtype=np.uint32)
+lib.L.dq_debug_read_prof_seeds.argtypes = [ctypes.c_void_p]
+assert lib.L.dq_debug_read_prof_seeds(seeds.ctypes.data) == 0
+sd = seeds[seeds > 0].astype(np.float64) * 64 / 1.965e3
+if sd.size:
+    print("seed-level warps: n %d mean %.1f us p50 %.1f p90 %.1f p99 %.1f max %.1f" % (sd.size, sd.mean(), *np.percentile(sd, [50, 90, 99]), sd.max()))
+print("stats", ctx.stats())
 os.remove(out)
