@@ -914,6 +914,8 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
     // scratch with warp-cooperative comparisons)
     Carry cy{0, 0, false};
     bool have = false;
+    Bracket lastb{0, 0, 0};  // bracket of the position just handled, when pass 2 computed it itself
+    bool lastb_ok = false;
     for (uint32_t k = 0; k < per_warp; ++k) {
         const uint64_t kk = k0 + (uint64_t)k * stride;
         if (kk >= count) break;
@@ -930,39 +932,79 @@ search_heads_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, uint
         }
         if (l1 != kAbort) {
             cy = Carry{p1, l1 & 0x7fffffffu, (l1 >> 31) != 0};
+            lastb_ok = false;
         } else {
-            const Bracket b = locate_step<true>(t, ix, j, cy, stride, have);
-            cy = carry_of(t, ix, b);
+            lastb = locate_step<true>(t, ix, j, cy, stride, have);
+            lastb_ok = true;
+            cy = carry_of(t, ix, lastb);
         }
         have = true;
         if (lane_id() == 0) {
             out_p[kk / stride] = cy.p;
             out_l[kk / stride] = cy.l | (cy.less ? 0x80000000u : 0u);
         }
-        // Inside a long match the following positions are predictable (see search_chain_kernel): lane s checks
-        // position k+s -- anchor (p + s*stride, l - s*stride, same side), neighbour on the query's side sharing
-        // less -- and the run of positions that check out is written at once, with no byte compared.
-        {
+        // The positions after a resolved one are often predictable; both checks below let lane s test position k+s with
+        // independent reads, and the run of positions that check out is written at once.  Repeated until neither
+        // makes progress.
+        for (;;) {
+            const uint64_t at = k0 + (uint64_t)k * stride;  // table position of the last resolved one
             const uint32_t s1 = lane_id();
-            const uint32_t *LCP = ix.lv[0];
-            bool ok = false;
-            uint32_t ps = 0, cs = 0;
-            if (s1 >= 1 && k + s1 < per_warp && kk + (uint64_t)s1 * stride < count && cy.l >= s1 * stride + kMinAnchor) {
-                ps = cy.p + s1 * stride;
-                cs = cy.l - s1 * stride;
-                const uint32_t r = ix.ISA[ps];
-                const bool edge = cy.less ? (r + 1 >= t.n) : (r == 0);
-                ok = !edge && LCP[cy.less ? r + 1 : r] < cs;
+            const uint64_t step = (uint64_t)s1 * stride;
+            const bool in_range = s1 >= 1 && k + s1 < per_warp && at + step < count;
+            uint32_t run = 0;
+            // (a) two-sided inheritance (see search_chain_kernel): the two neighbours of the bracket, moved s positions
+            // on, are still adjacent in rank
+#ifndef DQ_HEADS_TWO_SIDED
+#define DQ_HEADS_TWO_SIDED 1
+#endif
+            if (DQ_HEADS_TWO_SIDED && lastb_ok && lastb.L > 0 && lastb.L < t.n) {
+                const uint32_t A = sa_at(ix, lastb.L - 1, lastb.sx), B = sa_at(ix, lastb.L, lastb.sy);
+                bool ok = false;
+                uint32_t r2 = 0;
+                if (in_range && (uint64_t)min(lastb.x, lastb.y) > step) {
+                    r2 = ix.ISA[B + (uint32_t)step];
+                    ok = r2 == ix.ISA[A + (uint32_t)step] + 1u;
+                }
+                const unsigned m = __ballot_sync(kFullMask, ok) >> 1;
+                run = (uint32_t)__ffs((int)~m) - 1u;  // consecutive lanes 1..run checked out (<= 31)
+                if (run) {
+                    const bool lower = lastb.x >= lastb.y;  // carry_of: the neighbour sharing more, ties -> the lower one
+                    if (s1 >= 1 && s1 <= run) {
+                        out_p[at / stride + s1] = (lower ? A : B) + (uint32_t)step;
+                        out_l[at / stride + s1] = ((lower ? lastb.x : lastb.y) - (uint32_t)step) | (lower ? 0x80000000u : 0u);
+                    }
+                    const uint32_t adv = run * stride;
+                    lastb = Bracket{__shfl_sync(kFullMask, r2, (int)run), lastb.x - adv, lastb.y - adv, A + adv, B + adv};
+                    cy = carry_of(t, ix, lastb);
+                    k += run;
+                    continue;
+                }
             }
-            const unsigned m = __ballot_sync(kFullMask, ok) >> 1;
-            const uint32_t run = (uint32_t)__ffs((int)~m) - 1u;  // consecutive lanes 1..run checked out (<= 31)
-            if (s1 >= 1 && s1 <= run) {
-                out_p[kk / stride + s1] = ps;
-                out_l[kk / stride + s1] = cs | (cy.less ? 0x80000000u : 0u);
+            // (b) inside a unique long match: anchor (p + s*stride, l - s*stride, same side) whose neighbour on the
+            // query's side shares less -- the anchor is the answer, with no byte compared
+            {
+                const uint32_t *LCP = ix.lv[0];
+                bool ok = false;
+                uint32_t ps = 0, cs = 0;
+                if (in_range && cy.l >= s1 * stride + kMinAnchor) {
+                    ps = cy.p + s1 * stride;
+                    cs = cy.l - s1 * stride;
+                    const uint32_t r = ix.ISA[ps];
+                    const bool edge = cy.less ? (r + 1 >= t.n) : (r == 0);
+                    ok = !edge && LCP[cy.less ? r + 1 : r] < cs;
+                }
+                const unsigned m = __ballot_sync(kFullMask, ok) >> 1;
+                run = (uint32_t)__ffs((int)~m) - 1u;
+                if (run == 0) break;
+                if (s1 >= 1 && s1 <= run) {
+                    out_p[at / stride + s1] = ps;
+                    out_l[at / stride + s1] = cs | (cy.less ? 0x80000000u : 0u);
+                }
+                k += run;
+                cy.p += run * stride;
+                cy.l -= run * stride;
+                lastb_ok = false;  // lastb describes an earlier position now
             }
-            k += run;
-            cy.p += run * stride;
-            cy.l -= run * stride;
         }
     }
 }
@@ -1032,6 +1074,42 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
         // byte compared).  The kBatch ranks and their kBatch LCP entries are independent reads, so they are issued
         // together instead of as 2*kBatch dependent round trips; the run of positions that check out is written at
         // once and the loop resumes at the first one that does not.
+        // Two-sided inheritance, for matches that are long but NOT unique (zero runs, periodic records: the anchor's LCP
+        // interval is wide and the general path would binary-search it at every position).  If the query sits between
+        // suffixes A < query <= B, adjacent in rank, sharing x and y >= s+1 bytes with it, then dropping the first s bytes
+        // of all three keeps their order; when A+s and B+s are still adjacent in rank nothing sorts between them, so the
+        // bracket of position k+s is exactly (rank of B+s; x-s, y-s) -- two independent ISA reads per position, no
+        // LCP walk, no probe.
+        while (k + 1 < kChunk && b.L > 0 && b.L < n) {
+            constexpr int kBatch = 8;
+            const int room = min(kBatch, kChunk - 1 - k);
+            if (min(b.x, b.y) <= (uint32_t)room || k0 + k + room >= count) break;
+            const uint32_t A = sa_at(ix, b.L - 1, b.sx), B = sa_at(ix, b.L, b.sy);
+            uint32_t r1[kBatch], r2[kBatch];
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s) {
+                r1[s - 1] = s <= room ? ix.ISA[A + s] : 0u;
+                r2[s - 1] = s <= room ? ix.ISA[B + s] : 0u;
+            }
+            int run = 0;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s)
+                if (run == s - 1 && s <= room && r2[s - 1] == r1[s - 1] + 1u) run = s;
+            if (run == 0) break;
+            const bool lower = b.x > b.y;  // Diff.cs:281-286: the longer match, ties -> the upper neighbour
+            for (int s = 1; s <= run; ++s) {
+                pos_out[k0 + k + s] = (int32_t)((lower ? A : B) + s);
+                len_out[k0 + k + s] = (int32_t)((lower ? b.x : b.y) - s);
+            }
+            uint32_t rank_b = 0;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s)
+                if (s == run) rank_b = r2[s - 1];
+            b = Bracket{rank_b, b.x - (uint32_t)run, b.y - (uint32_t)run, A + (uint32_t)run, B + (uint32_t)run};
+            cy = carry_of(t, ix, b);
+            k += run;
+            if (run < room) break;
+        }
         while (k + 1 < kChunk) {
             constexpr int kBatch = 8;
             const int room = min(kBatch, kChunk - 1 - k);
