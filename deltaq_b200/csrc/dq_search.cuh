@@ -829,19 +829,55 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
             back = common_suffix(T + ih, T + qh, min((uint32_t)kChunk - 1, qh));
         }
     }
+    uint32_t q_prev = kNone;  // rank predecessor of the position just done (kNone: it has none)
+    {
+        const uint32_t r0 = ISA[i0];
+        if (r0) q_prev = (uint32_t)SA[r0 - 1];
+    }
     for (int k = 1; k < kChunk; ++k) {
+        // Reducible positions: if the rank predecessor of i+s is the rank predecessor of i moved s bytes on, the two
+        // pairs of suffixes are the same strings minus their first s bytes, so PLCP[i+s] = PLCP[i] - s exactly (for
+        // s < PLCP[i]) and nothing has to be compared.  kBatch positions are tested with independent reads.
+#ifndef DQ_LCP_BATCH
+#define DQ_LCP_BATCH 1
+#endif
+        while (DQ_LCP_BATCH && q_prev != kNone && k < kChunk) {
+            constexpr int kBatch = 8;
+            const uint64_t base = i0 + k - 1;  // the position just done
+            const int room = (int)min((uint64_t)min(kBatch, kChunk - k), n - 1 - base);
+            if (room <= 0 || l <= (uint32_t)room) break;
+            uint32_t rr[kBatch], qq[kBatch];
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s) rr[s - 1] = s <= room ? ISA[base + s] : 0u;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s) qq[s - 1] = (s <= room && rr[s - 1]) ? (uint32_t)SA[rr[s - 1] - 1] : kNone;
+            int run = 0;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s)
+                if (run == s - 1 && s <= room && qq[s - 1] == q_prev + (uint32_t)s) run = s;
+#pragma unroll
+            for (int s = 1; s <= kBatch; ++s)
+                if (s <= run) LCP[rr[s - 1]] = l - (uint32_t)s;
+            k += run;
+            l -= (uint32_t)run;
+            q_prev += (uint32_t)run;
+            if (run < room) break;
+        }
+        if (k >= kChunk) break;
         const uint64_t i64 = i0 + k;
         if (i64 >= n) break;
         const uint32_t i = (uint32_t)i64;
         const uint32_t r = ISA[i];
         if (r == 0) {
             l = 0;
+            q_prev = kNone;
         } else {
             const uint32_t q = (uint32_t)SA[r - 1];
             uint32_t known = l > 0 ? l - 1 : 0;
             const uint32_t d = (uint32_t)(kChunk - k);
             if (d <= back) known = max(known, d + nl);
             l = known + common_prefix(T + i + known, n - i - known, T + q + known, n - q - known);
+            q_prev = q;
         }
         LCP[r] = l;
     }
