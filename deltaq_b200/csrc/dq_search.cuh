@@ -317,6 +317,117 @@ __device__ __forceinline__ Bracket locate_scratch(const Texts &t, const Index &i
     return Bracket{(uint32_t)hi, llo, lhi};
 }
 
+// One probe of a from-scratch search whose 8 bytes of `old` past the known prefix (wa) are already in a register: the
+// common case in unrelated data -- a mismatch inside those 8 bytes, or one side ending there -- is decided at once;
+// anything longer goes through match_from.  Same result as match_from(t, p, j, known, less).
+__device__ __forceinline__ uint32_t match_quick(const Texts &t, uint32_t p, uint64_t wa, uint32_t j, uint32_t known, bool *less)
+{
+    const uint32_t la = t.n - p, lq = t.m - j;
+    const uint32_t rem = min(la, lq) - known;
+    const uint64_t wb = load64u(t.new_ + j + known);
+    const uint64_t x = wa ^ wb;
+    const uint32_t nb = x ? ((uint32_t)(__ffsll((long long)x) - 1) >> 3) : 8u;
+    if (nb < 8 && nb < rem) {
+        *less = (uint32_t)((wa >> (8 * nb)) & 0xffu) < (uint32_t)((wb >> (8 * nb)) & 0xffu);
+        return known + nb;
+    }
+    if (rem <= 8) {  // all rem bytes agree and one side ends there
+        const uint32_t c = known + rem;
+        *less = c == la ? c < lq : false;
+        return c;
+    }
+    return match_from(t, p, j, known + 8, less);
+}
+
+// kB independent from-scratch searches (queries j0 .. j0+kB-1) with their probes interleaved: the kB reads of SA and
+// then the kB reads of `old` of one round are in flight together, so a round costs two round trips for all of them
+// instead of two each.  out[i] is what locate_scratch(t, ix, j0 + i) returns, plus the neighbours' suffixes when seen.
+template <int kB>
+__device__ __forceinline__ void locate_scratch_batch(const Texts &t, const Index &ix, uint32_t j0, Bracket *out)
+{
+    const uint32_t n = t.n;
+    int32_t lo[kB], hi[kB];
+    uint32_t llo[kB], lhi[kB], plo[kB], phi[kB];
+    uint32_t lo_virtual = 0, hi_virtual = 0;  // bit i: bound of search i not yet compared with its query
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+        const uint32_t j = j0 + i;
+        lo[i] = -1;
+        hi[i] = (int32_t)n;
+        llo[i] = lhi[i] = 0;
+        plo[i] = phi[i] = kNone;
+        if (ix.pre3 && t.m - j >= 3) {
+            uint32_t b_lo, b_hi;
+            prefix3_bounds(ix, t.new_ + j, &b_lo, &b_hi);
+            lo[i] = (int32_t)b_lo - 1;
+            hi[i] = (int32_t)b_hi;
+            llo[i] = lhi[i] = 3;
+            lo_virtual |= 1u << i;
+            hi_virtual |= 1u << i;
+        } else if (t.m - j >= 2) {
+            const uint32_t k = ((uint32_t)t.new_[j] << 8) | t.new_[j + 1];
+            lo[i] = (int32_t)ix.bkt_lo[k] - 1;
+            hi[i] = (int32_t)ix.bkt_hi[k];
+            llo[i] = lhi[i] = 2;
+            lo_virtual |= 1u << i;
+            hi_virtual |= 1u << i;
+        }
+    }
+    for (;;) {
+        uint32_t active = 0, p[kB];
+        uint64_t wa[kB];
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            p[i] = 0;
+            if (hi[i] - lo[i] > 1) {
+                active |= 1u << i;
+                p[i] = (uint32_t)ix.SA[lo[i] + ((hi[i] - lo[i]) >> 1)];
+            }
+        }
+        if (!active) break;
+#pragma unroll
+        for (int i = 0; i < kB; ++i) wa[i] = load64u(t.old_ + p[i] + min(llo[i], lhi[i]));
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            if (!(active >> i & 1u)) continue;
+            DQ_DBG(g_dbg.probes++;)
+            bool less;
+            const uint32_t c = match_quick(t, p[i], wa[i], j0 + i, min(llo[i], lhi[i]), &less);
+            const int32_t mid = lo[i] + ((hi[i] - lo[i]) >> 1);
+            if (less) {
+                lo[i] = mid;
+                llo[i] = c;
+                plo[i] = p[i];
+                lo_virtual &= ~(1u << i);
+            } else {
+                hi[i] = mid;
+                lhi[i] = c;
+                phi[i] = p[i];
+                hi_virtual &= ~(1u << i);
+            }
+        }
+    }
+    // bucket bounds that were never compared: their true lcp with the query is at most the bucket's prefix minus one
+    uint64_t wl[kB], wh[kB];
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+        if ((lo_virtual >> i & 1u) && lo[i] >= 0) plo[i] = (uint32_t)ix.SA[lo[i]];
+        if ((hi_virtual >> i & 1u) && hi[i] < (int32_t)n) phi[i] = (uint32_t)ix.SA[hi[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+        wl[i] = ((lo_virtual >> i & 1u) && lo[i] >= 0) ? load64u(t.old_ + plo[i]) : 0ull;
+        wh[i] = ((hi_virtual >> i & 1u) && hi[i] < (int32_t)n) ? load64u(t.old_ + phi[i]) : 0ull;
+    }
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+        bool dummy;
+        if (lo_virtual >> i & 1u) llo[i] = lo[i] >= 0 ? match_quick(t, plo[i], wl[i], j0 + i, 0, &dummy) : 0u;
+        if (hi_virtual >> i & 1u) lhi[i] = hi[i] < (int32_t)n ? match_quick(t, phi[i], wh[i], j0 + i, 0, &dummy) : 0u;
+        out[i] = Bracket{(uint32_t)hi[i], llo[i], lhi[i], lo[i] >= 0 ? plo[i] : kNone, hi[i] < (int32_t)n ? phi[i] : kNone};
+    }
+}
+
 // locate_scratch that gives up (*aborted) as soon as one probe shares `cap` more bytes than known with the query:
 // the cheap, fully parallel first pass of the head kernel -- queries inside long matches abort after a few
 // probes and are left to the inheriting pass, queries in unrelated data (short matches) finish here.
@@ -1172,6 +1283,26 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
             cy.p += (uint32_t)run;
             cy.l -= (uint32_t)run;
             if (run < room) break;
+        }
+        // In unrelated data (the match just found is too short to inherit from) the next positions are searched from
+        // scratch whatever they turn out to be, and those searches do not depend on each other: kScratchBatch of them
+        // run with their probes interleaved.  (A from-scratch search is always exact; inheriting is only cheaper.)
+#ifndef DQ_SCRATCH_BATCH
+#define DQ_SCRATCH_BATCH 2
+#endif
+        constexpr int kScratchBatch = DQ_SCRATCH_BATCH;
+        while (kScratchBatch > 1 && cy.l <= kMinAnchor && k + kScratchBatch < kChunk - (int)back &&
+               k0 + k + kScratchBatch < count) {
+            Bracket bb[kScratchBatch > 1 ? kScratchBatch : 1];
+            locate_scratch_batch<(kScratchBatch > 1 ? kScratchBatch : 1)>(t, ix, scan_begin + (uint32_t)(k0 + k) + 1u, bb);
+#pragma unroll
+            for (int s = 0; s < kScratchBatch; ++s) {
+                int32_t pos2, len2;
+                cy = reference_result(t, ix, scan_begin + (uint32_t)(k0 + k) + 1u + s, bb[s], &pos2, &len2);
+                pos_out[k0 + k + 1 + s] = pos2;
+                len_out[k0 + k + 1 + s] = len2;
+            }
+            k += kScratchBatch;
         }
     }
 }
