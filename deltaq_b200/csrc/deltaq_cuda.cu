@@ -69,6 +69,7 @@ struct dq_ctx {
     int32_t runend_valid_n = -1;  // runend[] describes the resident text of this length (set by a run-aware sort)
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
     bool pre3_valid = false; // pre3 describes the resident text
+    bool search_seen = false; // this context has run a match search: sorts prepare the 3-byte prefix table on the way
 
     // multi-GPU session (dq_cuda_dist_*): the unresolved set between calls
     uint64_t *dist_kin = nullptr, *dist_kout = nullptr;
@@ -262,6 +263,28 @@ int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32
 }
 
 // ctx->text holds n bytes followed by >= 16 zero bytes.  Produces ctx->sa (the suffix array) and ctx->isa.
+// 3-byte prefix table of the text being sorted, from the round-0 keys while they are in sorted order (dq_search.cuh)
+int build_prefix3_sorted(dq_ctx *ctx, const uint64_t *sorted_keys, uint32_t n)
+{
+    namespace sr = dq::search;
+    DQ_TRY(ensure(ctx, ctx->pre3, ((size_t)sr::kPrefix3Bins + 4) * 4));
+    DQ_TRY(ensure(ctx, ctx->pre3tile, (size_t)sr::kPrefix3Tiles * 4));
+    uint32_t *table = ctx->pre3.as<uint32_t>(), *tiles = ctx->pre3tile.as<uint32_t>();
+    DQ_CK(ctx, cudaMemsetAsync(table, 0xff, (size_t)sr::kPrefix3Bins * 4, ctx->stream));
+    const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n, 256), (uint64_t)ctx->sm_count * 16));
+    auto k1 = sr::prefix3_mark_kernel;
+    DQ_LAUNCH(k1, g, 256, 0, ctx->stream, sorted_keys, n, table);
+    auto k2 = sr::prefix3_fill_tile_min_kernel;
+    DQ_LAUNCH(k2, sr::kPrefix3Tiles, 256, 0, ctx->stream, table, tiles);
+    auto k3 = sr::prefix3_fill_tile_scan_kernel;
+    DQ_LAUNCH(k3, 1, 1024, 0, ctx->stream, tiles, ctx->text.as<uint8_t>(), n, table);
+    auto k4 = sr::prefix3_fill_apply_kernel;
+    DQ_LAUNCH(k4, sr::kPrefix3Tiles, 256, 0, ctx->stream, table, tiles);
+    ctx->stats.kernel_launches += 4;
+    ctx->pre3_valid = true;
+    return DQ_OK;
+}
+
 int sort_resident(dq_ctx *ctx, uint32_t n)
 {
     dq_stats &st = ctx->stats;
@@ -320,6 +343,12 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count + 4, uniform_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
     DQ_TRY(run_passes(ctx, s, n, plan, false));
+    // a context that searches gets its 3-byte prefix table here, from the keys while they are in sorted order
+    {
+        const char *min_env = getenv("DQ_PREFIX3_SORTED_MIN");  // tests: lets small inputs take this path
+        const uint32_t min_n = min_env ? (uint32_t)atoi(min_env) : (1u << 20);
+        if (ctx->search_seen && n >= min_n && !getenv("DQ_PREFIX3")) DQ_TRY(build_prefix3_sorted(ctx, s.kin, n));
+    }
     st.rounds = 1;
     st.active_sum = n;
     st.algorithmic_bytes = (int64_t)n * (41 + 24 * plan.npass);
@@ -702,6 +731,7 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     // Diff.cs:90 -- suffixSort.Sort(oldData, I[..^1]); the suffix array stays on the device.  `new` goes up on
     // the copy stream while the sort runs.
     ctx->resident_n = -1;
+    ctx->search_seen = true;
     const bool trace = getenv("DQ_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };

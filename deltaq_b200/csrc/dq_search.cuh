@@ -235,11 +235,12 @@ struct Index {
     // 2-byte prefix buckets: ranks [bkt_lo[k], bkt_hi[k]) hold exactly the suffixes (>= 2 bytes long) that
     // start with the byte pair k
     const uint32_t *bkt_lo, *bkt_hi;
-    // 3-byte prefix table (prefix3_* kernels below), or nullptr: pre3[k] = number of suffixes >= 3 bytes long whose
-    // first three bytes, read as a big-endian number, are < k (k in [0, 2^24]); pre3[2^24 + 1] and [2^24 + 2] hold
-    // the zero-padded 3-byte values of the 1-byte and the 2-byte suffix at the end of the text (kNone if n is too
-    // short to have them).  Ranks [lo, hi) = [pre3[k] + a, pre3[k+1] + a), a = how many of those two values are <= k,
-    // hold exactly the suffixes (>= 3 bytes long) that start with k.
+    // 3-byte prefix table (prefix3_* kernels below), or nullptr: pre3[k] = number of suffixes whose first three bytes
+    // (zero padded for the two suffixes shorter than that), read as a big-endian number, are < k (k in [0, 2^24]) --
+    // also their ranks, because a shorter suffix sorts in front of everything its padded value could tie with.
+    // pre3[2^24 + 1] and [2^24 + 2] hold the padded values of the 1-byte and the 2-byte suffix (kNone if n is too short
+    // to have them).  Ranks [lo, hi) = [pre3[k] + a, pre3[k+1]), a = how many of those two values are == k, hold exactly
+    // the suffixes (>= 3 bytes long) that start with k.
     const uint32_t *pre3;
 };
 
@@ -257,9 +258,9 @@ __device__ uint32_t g_prof_seeds[1u << 16];
 __device__ __forceinline__ void prefix3_bounds(const Index &ix, const uint8_t *q, uint32_t *lo, uint32_t *hi)
 {
     const uint32_t k = ((uint32_t)q[0] << 16) | ((uint32_t)q[1] << 8) | q[2];
-    const uint32_t a = (uint32_t)(ix.pre3[kPrefix3Bins + 1] <= k) + (uint32_t)(ix.pre3[kPrefix3Bins + 2] <= k);
+    const uint32_t a = (uint32_t)(ix.pre3[kPrefix3Bins + 1] == k) + (uint32_t)(ix.pre3[kPrefix3Bins + 2] == k);
     *lo = ix.pre3[k] + a;
-    *hi = ix.pre3[k + 1] + a;
+    *hi = ix.pre3[k + 1];
 }
 
 struct Bracket {
@@ -741,13 +742,16 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint8_t *__res
 }
 
 // ---- 3-byte prefix table (Index::pre3) -----------------------------------------------------------------------
-// Needs only the text, not the suffix array: a histogram of the 3-byte prefixes of all suffixes (equal keys inside a
+// Two ways to build it.  From the text alone: a histogram of the 3-byte prefixes of all suffixes (equal keys inside a
 // warp are added with one atomic: zero padding would otherwise send a million increments to one address), then an
-// exclusive scan over the 2^24 bins in three small kernels.
+// exclusive scan over the 2^24 bins in three small kernels (~0.35 ms at 16 MiB, the atomics).  Or, when this library's
+// own sort produced the suffix array, from the keys of its round 0 while they are still in sorted order: the first
+// index of every 3-byte value is marked (one coalesced read of the keys) and the empty bins are filled from the right
+// (~0.06 ms) -- prefix3_mark_kernel + prefix3_fill_* below.
 __global__ void __launch_bounds__(256) prefix3_hist_kernel(const uint8_t *__restrict__ T, uint32_t n,
                                                             uint32_t *__restrict__ hist)
 {
-    const uint64_t total = n >= 3 ? (uint64_t)n - 2 : 0;  // suffixes with >= 3 bytes
+    const uint64_t total = n;  // every suffix; the text is zero padded, which is the padding the short ones need
     const uint64_t span = (total + 31) & ~(uint64_t)31;  // whole warps: the match below is warp-wide
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < span; p += (uint64_t)gridDim.x * blockDim.x) {
         const bool valid = p < total;
@@ -819,7 +823,7 @@ __global__ void __launch_bounds__(1024) prefix3_tile_scan_kernel(uint32_t *__res
         run += v[q];
     }
     if (threadIdx.x == 0) {
-        table[kPrefix3Bins] = n >= 3 ? n - 2 : 0u;
+        table[kPrefix3Bins] = n;
         table[kPrefix3Bins + 1] = n >= 1 ? ((uint32_t)T[n - 1] << 16) : kNone;
         table[kPrefix3Bins + 2] = n >= 2 ? (((uint32_t)T[n - 2] << 16) | ((uint32_t)T[n - 1] << 8)) : kNone;
     }
@@ -858,6 +862,109 @@ __global__ void __launch_bounds__(256) prefix3_apply_kernel(uint32_t *__restrict
         run += v[q].w;
         dst[q] = o;
     }
+}
+
+// pre3 from the sorted round-0 keys (big-endian packed 8 bytes, zero padded): table[k] = first index whose key starts
+// with k, for the values that occur; the table must hold kNone everywhere before
+__global__ void __launch_bounds__(256) prefix3_mark_kernel(const uint64_t *__restrict__ sorted_keys, uint32_t n,
+                                                            uint32_t *__restrict__ table)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(sorted_keys[i] >> 40);
+        if (i == 0 || (uint32_t)(sorted_keys[i - 1] >> 40) != k) table[k] = (uint32_t)i;
+    }
+}
+
+// empty bins take the value of the next marked bin to their right (n if there is none): a suffix-minimum scan, in the
+// same three steps as the sum scan above
+__global__ void __launch_bounds__(256) prefix3_fill_tile_min_kernel(const uint32_t *__restrict__ table,
+                                                                     uint32_t *__restrict__ tile_min)
+{
+    __shared__ uint32_t warp_min[8];
+    const uint4 *src = reinterpret_cast<const uint4 *>(table + (size_t)blockIdx.x * kPrefix3Tile) + threadIdx.x * 4;
+    uint32_t m = kNone;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = src[q];
+        m = min(m, min(min(v.x, v.y), min(v.z, v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+    if (lane_id() == 0) warp_min[warp_id()] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = kNone;
+        for (int w = 0; w < 8; ++w) t = min(t, warp_min[w]);
+        tile_min[blockIdx.x] = t;
+    }
+}
+
+// one block: tile_min[t] <- min over the tiles to the right of t (n if none); also the tail of the table
+__global__ void __launch_bounds__(1024) prefix3_fill_tile_scan_kernel(uint32_t *__restrict__ tile_min, const uint8_t *__restrict__ T,
+                                                                       uint32_t n, uint32_t *__restrict__ table)
+{
+    __shared__ uint32_t sm[kPrefix3Tiles];
+    for (uint32_t t = threadIdx.x; t < kPrefix3Tiles; t += blockDim.x) sm[t] = tile_min[t];
+    __syncthreads();
+    // 4096 values: thread x owns tiles [4x, 4x+4); suffix minima inside, then across threads through shared memory
+    __shared__ uint32_t part[1024];
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = sm[threadIdx.x * 4 + q];
+    part[threadIdx.x] = min(min(v[0], v[1]), min(v[2], v[3]));
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const uint32_t other = threadIdx.x + d < 1024 ? part[threadIdx.x + d] : kNone;
+        __syncthreads();
+        part[threadIdx.x] = min(part[threadIdx.x], other);
+        __syncthreads();
+    }
+    uint32_t run = min(threadIdx.x + 1 < 1024 ? part[threadIdx.x + 1] : kNone, n);  // everything right of this thread's tiles
+#pragma unroll
+    for (int q = 3; q >= 0; --q) {
+        tile_min[threadIdx.x * 4 + q] = run;
+        run = min(run, v[q]);
+    }
+    if (threadIdx.x == 0) {
+        table[kPrefix3Bins] = n;
+        table[kPrefix3Bins + 1] = n >= 1 ? ((uint32_t)T[n - 1] << 16) : kNone;
+        table[kPrefix3Bins + 2] = n >= 2 ? (((uint32_t)T[n - 2] << 16) | ((uint32_t)T[n - 1] << 8)) : kNone;
+    }
+}
+
+__global__ void __launch_bounds__(256) prefix3_fill_apply_kernel(uint32_t *__restrict__ table, const uint32_t *__restrict__ tile_right)
+{
+    __shared__ uint32_t warp_min[8];
+    uint4 *dst = reinterpret_cast<uint4 *>(table + (size_t)blockIdx.x * kPrefix3Tile) + threadIdx.x * 4;
+    uint32_t v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 u = dst[q];
+        v[4 * q] = u.x, v[4 * q + 1] = u.y, v[4 * q + 2] = u.z, v[4 * q + 3] = u.w;
+    }
+    uint32_t mine = kNone;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) mine = min(mine, v[e]);
+    // minimum over the threads to the right inside the warp, then over the warps to the right
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_down_sync(kFullMask, incl, d);
+        if ((int)lane_id() + d < 32) incl = min(incl, u);
+    }
+    if (lane_id() == 0) warp_min[warp_id()] = incl;
+    __syncthreads();
+    uint32_t right = tile_right[blockIdx.x];
+    for (int w = (int)warp_id() + 1; w < 8; ++w) right = min(right, warp_min[w]);
+    const uint32_t next_lane = __shfl_down_sync(kFullMask, incl, 1);
+    if (lane_id() < 31) right = min(right, next_lane);
+    uint32_t run = right;
+#pragma unroll
+    for (int e = 15; e >= 0; --e) {
+        run = min(run, v[e]);
+        v[e] = run;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // LCP array, levels S and A.  One WARP walks `per_warp` text positions `stride` apart; the byte comparisons are

@@ -293,6 +293,7 @@ int search_common(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I,
     DQ_TRY(check_args(ctx, (n == 0 || old_ || !I) && (m == 0 || new_) && (count == 0 || (pos_out && len_out)),
                       "bsdiff_search: null buffer"));
     DQ_CK(ctx, cudaSetDevice(ctx->device));
+    ctx->search_seen = true;
     const cudaMemcpyKind in = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const cudaMemcpyKind out = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const int32_t launches_before = ctx->stats.kernel_launches;

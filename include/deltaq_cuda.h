@@ -58,6 +58,9 @@ typedef struct dq_stats {
  *   DQ_HOST_THREADS=h,w[,part_kib,min_kib]  helper walkers / writer threads of the host greedy loop
  *   DQ_HEADS_CAP=k        capacity of the match-head list of the coded (pos,len) table (forces the full-table fallback)
  *   DQ_SEEDS_PER=k        super-chunks per warp of the seed level of the search's head kernels (0 = off)
+ *   DQ_PREFIX3=0|1        3-byte prefix table of the search: never / always built from the text (default: from 32 MiB up,
+ *                         or from 1 MiB up out of the sort's round-0 keys once the context has searched;
+ *                         DQ_PREFIX3_SORTED_MIN=n lowers that 1 MiB)
  *   DQ_MATCH_POLICY=0|1|2 which radix passes of a doubling round rank with MATCH.ANY
  */
 

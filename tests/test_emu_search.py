@@ -152,3 +152,17 @@ def test_prefix3_table_for_scratch_searches(sorter, monkeypatch):
         pairs.append((old, new))
     for old, new in pairs:
         check_pair(sorter, old, new, with_streams=False)
+
+
+def test_prefix3_table_from_the_sorts_round0_keys(sorter, monkeypatch):
+    # once a context has searched, its sorts build the 3-byte prefix table from their round-0 keys (1 MiB and up;
+    # DQ_PREFIX3_SORTED_MIN lowers that for this test).  check_pair searches with a supplied I first, then sorts.
+    monkeypatch.setenv("DQ_PREFIX3_SORTED_MIN", "1")
+    pairs = list(small_random_pairs(count=6, seed=78)) + [structured_pairs()[k] for k in sorted(structured_pairs())[2:4]]
+    rng = np.random.default_rng(4)
+    for tail in (b"", b"\x00", b"\x00\x00", b"ab", b"\xff\xff\xff"):
+        old = np.frombuffer(rng.integers(0, 3, 300, dtype=np.uint8).tobytes() + tail, dtype=np.uint8)
+        new = np.concatenate([rng.integers(0, 3, 200, dtype=np.uint8), np.frombuffer(tail + b"\x00\x00\x01", dtype=np.uint8), old[50:150]])
+        pairs.append((old, new))
+    for old, new in pairs:
+        check_pair(sorter, old, new)
