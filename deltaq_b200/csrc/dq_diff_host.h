@@ -4,10 +4,11 @@
 // is the array read  len = len_tab[scan]; pos = pos_tab[scan];  -- the hook SURVEY.md section 8(b) describes.
 // Emits the three UNCOMPRESSED streams (ctrl triples as packed longs, SpanExtensions.cs:7-30).
 //
-// Same statements, faster stepping: the byte-at-a-time loops of the reference are advanced 32 bytes at a time
-// wherever a whole block behaves uniformly (all bytes equal, or the bound check cannot fire), which leaves
-// every variable exactly as the reference's loop would (proofs at each site); anything else falls back to the
-// reference's own single-byte step.
+// Same results, faster stepping: the byte-at-a-time loops of the reference are advanced many bytes at a time wherever
+// a whole stretch behaves uniformly (all bytes equal, a running maximum that cannot be beaten, a test whose outcome
+// is already decided), which leaves every variable the loop looks at again exactly as the reference's loop would
+// (the argument is written at each site); anything else falls back to the reference's own single-byte step.
+// The loop runs on a few host threads (greedy_emit_pipelined): scan -> extender (+ crew) -> writers.
 #pragma once
 #include <cstdint>
 #include <chrono>
@@ -176,17 +177,6 @@ template <typename FetchPos> struct CodedTable {
     uint32_t next_tile = 0, next_k = 0;
     MatchHead cur{-1, 0, 0};
 
-    bool any_long16(int32_t scan) const
-    {
-#if defined(__SSE2__)
-        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(code + scan));
-        return _mm_movemask_epi8(_mm_cmpgt_epi8(c, _mm_set1_epi8(8))) != 0;
-#else
-        for (int k = 0; k < 16; ++k)
-            if (code[scan + k] > 8) return true;
-        return false;
-#endif
-    }
     // masks over positions scan + i, i in [0, 16): len > 8 / len != 0 / len == 1
     void classify16(int32_t scan, uint32_t &is_long, uint32_t &nonzero, uint32_t &one) const
     {
@@ -205,14 +195,6 @@ template <typename FetchPos> struct CodedTable {
 #endif
     }
     int32_t short_len(int32_t scan) const { return code[scan]; }
-    int32_t max_end16(int32_t scan, int32_t e) const
-    {
-        for (int32_t i = 0; i < 16; ++i) {
-            const int32_t t = scan + i + (int32_t)code[scan + i];
-            e = t > e ? t : e;
-        }
-        return e;
-    }
     void advance(int32_t scan)
     {
         const uint32_t last_tile = (uint32_t)scan >> kTileShift;
@@ -568,12 +550,6 @@ inline void write_piece(const uint8_t *oldData, const uint8_t *newData, const Pi
     put_packed_long(out.ctrl, pc.seek);
 }
 
-inline void emit_stop(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen, int32_t scan,
-                      int32_t pos, EmitState &st, Streams &out)
-{
-    write_piece(oldData, newData, extend_stop(oldData, oldLen, newData, newLen, scan, pos, st), out);
-}
-
 // ready(upto): returns once table entries [0, min(upto, newLen)) are valid (the table may still be arriving from
 // the device in slices while the loop runs)
 template <typename Table, typename Ready, typename Sink>
@@ -737,24 +713,6 @@ inline void reset_streams(Streams &out, int32_t newLen)
     out.extra.clear();
     out.visits = 0;
     out.diff.reserve((size_t)newLen);  // sum of lenf <= newLen: the diffed ranges of `new` are disjoint
-}
-
-// the whole loop on the calling thread
-template <typename Ready>
-inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
-                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out, Ready &&ready)
-{
-    reset_streams(out, newLen);
-    EmitState st;
-    FullTable tab{pos_tab, len_tab};
-    greedy_scan(oldData, oldLen, newData, newLen, tab, out, ready,
-                [&](int32_t scan, int32_t pos) { emit_stop(oldData, oldLen, newData, newLen, scan, pos, st, out); });
-}
-
-inline void greedy_emit(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
-                        const int32_t *pos_tab, const int32_t *len_tab, Streams &out)
-{
-    greedy_emit(oldData, oldLen, newData, newLen, pos_tab, len_tab, out, [](int32_t) {});
 }
 
 // single-producer single-consumer hand-off between the stages of greedy_emit_pipelined
