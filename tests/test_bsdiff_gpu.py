@@ -181,3 +181,18 @@ def test_coded_table_overflow_falls_back_to_full_table(monkeypatch):
             s.dispose()
         for k in ("ctrl", "diff", "extra"):
             assert got[k] == ref[k], (cap, k)
+
+
+@pytest.mark.parametrize("shape", ["0,1", "1,1", "7,3"])
+def test_streams_identical_for_every_host_thread_shape(shape, monkeypatch):
+    # the host loop of dq_cuda_bsdiff_streams (scan / extender + crew / writers) on the real library, with no helpers,
+    # one helper, and more helpers than the default; same pair, same bytes
+    from deltaq_b200 import CudaSuffixSort, bsdiff, workloads as w
+    monkeypatch.setenv("DQ_HOST_THREADS", shape)
+    old, new = w.c2_exe_pair(n_old=2 << 20, n_new=(2 << 20) + (1 << 17))
+    ref = oracle.bsdiff_streams(old, new)
+    with CudaSuffixSort() as s:
+        got = bsdiff.create_streams(old, new, s)
+    for k in ("ctrl", "diff", "extra"):
+        assert got[k] == ref[k], (shape, k)
+    assert got["search_visits"] == ref["search_calls"]
