@@ -24,6 +24,9 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 namespace dq {
 namespace diffhost {
@@ -776,7 +779,16 @@ struct PipelineShape {
             }
             if (got >= 1) return PipelineShape{h, w};
         }
-        const unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = std::thread::hardware_concurrency();
+#if defined(__linux__)
+        {   // the CPUs this process may actually run on (containers, taskset), not the machine's
+            cpu_set_t set;
+            if (sched_getaffinity(0, sizeof set, &set) == 0) {
+                const unsigned allowed = (unsigned)CPU_COUNT(&set);
+                if (allowed && allowed < hw) hw = allowed;
+            }
+        }
+#endif
         if (hw >= 12) return PipelineShape{3, 2};
         if (hw >= 6) return PipelineShape{1, 2};
         return PipelineShape{0, 1};
