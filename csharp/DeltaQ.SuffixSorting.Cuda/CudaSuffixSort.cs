@@ -72,6 +72,7 @@ internal sealed unsafe class PinnedSuffixOwner : MemoryManager<int>
 public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposable
 {
     private IntPtr _ctx;
+    internal IntPtr Handle => _ctx;   // CudaDiff.Create drives the same native context
     private readonly object _gate = new();
 
     public CudaSuffixSort(int device = -1)
