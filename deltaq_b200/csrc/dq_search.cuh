@@ -1013,8 +1013,24 @@ lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
 }
 
 // number of equal bytes walking backwards from a[-1], b[-1], at most cap
-__device__ __forceinline__ uint32_t common_suffix(const uint8_t *a, const uint8_t *b, uint32_t cap)
+#ifndef DQ_SUFFIX_WORDS
+#define DQ_SUFFIX_WORDS 1
+#endif
+__device__ __forceinline__ uint32_t common_suffix(const uint8_t *a, const uint8_t *b, uint32_t cap, bool room32 = false)
 {
+    // room32: the 32 bytes in front of both pointers are readable.  Then the usual case (cap = kChunk - 1 = 31) is four
+    // independent 8-byte reads per side instead of up to 31 dependent byte reads.
+    if (DQ_SUFFIX_WORDS && room32 && cap == 31u) {
+        uint64_t x[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) x[w] = load64u(a - 8 * (w + 1)) ^ load64u(b - 8 * (w + 1));
+        uint32_t e = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (e == 8u * w) e += x[w] ? ((uint32_t)__clzll((long long)x[w]) >> 3) : 8u;  // a[-1] is the top byte of x[0]
+        }
+        return min(e, 31u);
+    }
     uint32_t e = 0;
     while (e < cap && a[-(int)e - 1] == b[-(int)e - 1]) ++e;
     return e;
@@ -1044,7 +1060,7 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
         nl = head_l[c + 1];
         if (nl >= kBackMin) {
             const uint32_t qh = (uint32_t)SA[ISA[ih] - 1];  // nl > 0 => the head has a predecessor
-            back = common_suffix(T + ih, T + qh, min((uint32_t)kChunk - 1, qh));
+            back = common_suffix(T + ih, T + qh, min((uint32_t)kChunk - 1, qh), kChunk == 32 && qh >= 32);
         }
     }
     uint32_t q_prev = kNone;  // rank predecessor of the position just done (kNone: it has none)
@@ -1302,7 +1318,7 @@ search_chain_kernel(Texts t, Index ix, uint32_t scan_begin, uint32_t count, cons
         nless = (v >> 31) != 0;
         np = head_p[c + 1];
         if (nl >= kBackMin)
-            back = common_suffix(t.new_ + scan_begin + k0 + kChunk, t.old_ + np, min((uint32_t)kChunk - 1, np));
+            back = common_suffix(t.new_ + scan_begin + k0 + kChunk, t.old_ + np, min((uint32_t)kChunk - 1, np), kChunk == 32 && np >= 32);
     }
     const uint32_t *LCP = ix.lv[0];
     const uint32_t n = t.n;
