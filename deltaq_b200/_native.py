@@ -51,7 +51,6 @@ EXPORTS = [
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
     "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
     "dq_cuda_radix_sort_pairs", "dq_cuda_radix_sort_pairs_device",
-    "dq_cuda_dist_pack", "dq_cuda_dist_partition", "dq_cuda_dist_round0", "dq_cuda_dist_requests", "dq_cuda_dist_round",
 ]
 
 
@@ -83,11 +82,6 @@ class Library:
         L.dq_cuda_greedy_emit.argtypes = [vp, vp, i32, vp, i32, vp, vp, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
         L.dq_cuda_radix_sort_pairs_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
-        L.dq_cuda_dist_pack.argtypes = [vp, vp, i32, i32, vp, vp, vp]
-        L.dq_cuda_dist_partition.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
-        L.dq_cuda_dist_requests.argtypes = [vp, i64, vp, vp]
-        L.dq_cuda_dist_round0.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_int32)]
-        L.dq_cuda_dist_round.argtypes = [vp, vp, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_int32)]
         for name in EXPORTS:
             if name != "dq_cuda_last_error":
                 getattr(L, name).restype = ctypes.c_int
@@ -140,7 +134,9 @@ class PinnedArray:
 
 
 class Context:
-    """dq_ctx wrapper: one device, one stream, scratch memory; one call at a time."""
+    """dq_ctx wrapper: one call at a time.  `device`: None (current device), one CUDA ordinal, or a list of ordinals
+    -- a device GROUP driven by this one context: inputs of at least DQ_SHARD_MIN bytes (default 128 MiB) are sorted
+    and searched by all of them (the same ordinal may be listed several times: logical shards on one GPU)."""
 
     def __init__(self, device=None, lib=None):
         self.lib = lib or default_library()
@@ -148,8 +144,9 @@ class Context:
         if device is None:
             rc = self.lib.L.dq_cuda_create(ctypes.byref(self._h), None, 0)
         else:
-            dev = (ctypes.c_int * 1)(int(device))
-            rc = self.lib.L.dq_cuda_create(ctypes.byref(self._h), dev, 1)
+            devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+            dev = (ctypes.c_int * len(devs))(*devs)
+            rc = self.lib.L.dq_cuda_create(ctypes.byref(self._h), dev, len(devs))
         if rc != DQ_OK:
             raise NativeError(rc, self.lib.L.dq_cuda_last_error(None).decode())
 
@@ -251,35 +248,6 @@ class Context:
         self._check(self.lib.L.dq_cuda_radix_sort_pairs_device(self._h, ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals),
                                                                count, bit_lo, nbits, _addr(hist)))
         return hist
-
-    def dist_pack(self, d_slice, pos_begin, pos_count, d_keys, d_vals, d_hist16):
-        self._check(self.lib.L.dq_cuda_dist_pack(self._h, ctypes.c_void_p(d_slice), pos_begin, pos_count,
-                                                 ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals),
-                                                 ctypes.c_void_p(d_hist16)))
-
-    def dist_partition(self, d_keys, d_vals, count, d_lut, d_keys_out, d_vals_out):
-        counts = np.zeros(256, dtype=np.int64)
-        self._check(self.lib.L.dq_cuda_dist_partition(self._h, ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals), count,
-                                                      ctypes.c_void_p(d_lut), ctypes.c_void_p(d_keys_out),
-                                                      ctypes.c_void_p(d_vals_out), _addr(counts)))
-        return counts
-
-    def dist_requests(self, h, d_q, d_idx):
-        self._check(self.lib.L.dq_cuda_dist_requests(self._h, int(h), ctypes.c_void_p(d_q), ctypes.c_void_p(d_idx)))
-
-    def dist_round0(self, d_keys, d_vals, count, n, slot_base, d_sa_local, d_upd_pos, d_upd_rank):
-        a = ctypes.c_int32(0)
-        self._check(self.lib.L.dq_cuda_dist_round0(self._h, ctypes.c_void_p(d_keys), ctypes.c_void_p(d_vals), count, n,
-                                                   slot_base, ctypes.c_void_p(d_sa_local), ctypes.c_void_p(d_upd_pos),
-                                                   ctypes.c_void_p(d_upd_rank), ctypes.byref(a)))
-        return a.value
-
-    def dist_round(self, d_r2, n, slot_base, d_sa_local, d_upd_pos, d_upd_rank):
-        a = ctypes.c_int32(0)
-        self._check(self.lib.L.dq_cuda_dist_round(self._h, ctypes.c_void_p(d_r2), n, slot_base,
-                                                  ctypes.c_void_p(d_sa_local), ctypes.c_void_p(d_upd_pos),
-                                                  ctypes.c_void_p(d_upd_rank), ctypes.byref(a)))
-        return a.value
 
     # ---- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr()) ---------------
     def suffix_sort_device(self, d_text, n, d_sa_out):

@@ -17,6 +17,7 @@
 #include "dq_radix.cuh"
 #include "dq_suffix.cuh"
 #include "dq_search.cuh"
+#include "dq_dist.cuh"
 #include "dq_diff_host.h"
 
 namespace {
@@ -41,9 +42,12 @@ struct PinBuf {
     size_t cap = 0;
 };
 
+struct Group;  // dq_group.inl: the shards of a context created with ndev > 1
+
 }  // namespace
 
 struct dq_ctx {
+    Group *group = nullptr;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -70,11 +74,6 @@ struct dq_ctx {
     bool lcp_valid = false;  // lcp (+ its block-minimum levels) describes the resident (text, sa)
     bool pre3_valid = false; // pre3 describes the resident text
     bool search_seen = false; // this context has run a match search: sorts prepare the 3-byte prefix table on the way
-
-    // multi-GPU session (dq_cuda_dist_*): the unresolved set between calls
-    uint64_t *dist_kin = nullptr, *dist_kout = nullptr;
-    uint32_t *dist_vin = nullptr, *dist_vout = nullptr, *dist_slot_cur = nullptr, *dist_slot_nxt = nullptr;
-    uint32_t dist_a = 0, dist_cap = 0;
 
     // pipelined D2H of the (pos, len) table for dq_cuda_bsdiff_streams
     cudaStream_t copy_stream = nullptr;
@@ -233,13 +232,13 @@ uint32_t producer_grid(const dq_ctx *ctx, uint64_t items)
     return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8));
 }
 
-// rank_compact over the sorted active set; returns the next active count through ctx->h_count
+// rank_compact over the sorted active set.  enqueue_rank launches it and the copy of its counters; finish_rank waits
+// and reads them (the group paths enqueue on every shard before they wait on any).
 template <bool ROUND0, bool DIST = false>
-int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
-             uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a,
-             int32_t *sa_array = nullptr, uint32_t slot_base = 0, uint64_t *upd_pos = nullptr,
-             uint32_t *upd_rank = nullptr, const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr,
-             uint32_t hmin = 0, uint32_t *min_depth = nullptr)
+int enqueue_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
+                 uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, int32_t *sa_array = nullptr,
+                 uint32_t slot_base = 0, uint64_t *upd = nullptr, uint64_t *act_out = nullptr,
+                 const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr, uint32_t hmin = 0)
 {
     const uint32_t tiles = (uint32_t)div_up(a, sx::kRankTile);
     const size_t bytes = 256 + (size_t)tiles * 8;
@@ -252,14 +251,31 @@ int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32
     auto k = sx::rank_compact_kernel<ROUND0, DIST>;
     DQ_LAUNCH(k, tiles, sx::kRankThreads, 0, ctx->stream, keys, sa, slot_in, a, n, ctx->isa.as<uint32_t>(),
               sa_array ? sa_array : ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count, slot_base,
-              upd_pos, upd_rank, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr);
+              upd, act_out, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr);
     ctx->stats.kernel_launches++;
     DQ_CK(ctx, cudaGetLastError());
     DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return DQ_OK;
+}
+
+int finish_rank(dq_ctx *ctx, uint32_t *next_a, uint32_t *min_depth)
+{
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     *next_a = ctx->h_count[0];
     if (min_depth) *min_depth = ~ctx->h_count[1];  // the kernel keeps max(~depth) in a word that starts at 0
     return DQ_OK;
+}
+
+template <bool ROUND0>
+int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
+             uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a,
+             const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr, uint32_t hmin = 0,
+             uint32_t *min_depth = nullptr)
+{
+    DQ_TRY((enqueue_rank<ROUND0, false>(ctx, keys, sa, slot_in, a, n, sa_out, rank_out, slot_out, nullptr, 0, nullptr,
+                                        nullptr, depth_in, depth_out, hmin)));
+    return finish_rank(ctx, next_a, min_depth);
 }
 
 // ctx->text holds n bytes followed by >= 16 zero bytes.  Produces ctx->sa (the suffix array) and ctx->isa.
@@ -413,9 +429,8 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         st.algorithmic_bytes += (int64_t)a * (52 + 24 * rp.npass);
 
         uint32_t next_a = 0, min_depth = 0;
-        DQ_TRY((run_rank<false, false>(ctx, s.kin, s.vin, slot_cur, a, n, s.vout, reinterpret_cast<uint32_t *>(s.kout),
-                                       slot_nxt, &next_a, nullptr, 0, nullptr, nullptr, depth_cur, depth_nxt, (uint32_t)h,
-                                       &min_depth)));
+        DQ_TRY(run_rank<false>(ctx, s.kin, s.vin, slot_cur, a, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_nxt,
+                               &next_a, depth_cur, depth_nxt, (uint32_t)h, &min_depth));
         std::swap(slot_cur, slot_nxt);
         std::swap(depth_cur, depth_nxt);
         if (next_a > a) {
@@ -480,40 +495,71 @@ int check_args(dq_ctx *ctx, bool ok, const char *what)
 
 #include "dq_search_host.inl"
 
+int dist_reserve(dq_ctx *ctx, uint32_t count)
+{
+    const size_t c8 = (size_t)std::max<uint32_t>(count, 1) * 8, c4 = (size_t)std::max<uint32_t>(count, 1) * 4;
+    DQ_TRY(ensure(ctx, ctx->keyA, c8));
+    DQ_TRY(ensure(ctx, ctx->keyB, c8));
+    DQ_TRY(ensure(ctx, ctx->valA, c4));
+    DQ_TRY(ensure(ctx, ctx->valB, c4));
+    DQ_TRY(ensure(ctx, ctx->slotA, c4));
+    DQ_TRY(ensure(ctx, ctx->slotB, c4));
+    return DQ_OK;
+}
+
+int create_single(dq_ctx **out, int dev);
+int destroy_single(dq_ctx *ctx);
+
+#include "dq_group.inl"
+
 void export_streams(dq_ctx *ctx, dq_diff_streams *out);
 
-}  // namespace
-
-// ======================================================================================================
-extern "C" {
-
-int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
+int destroy_single(dq_ctx *ctx)
 {
-    if (!out) return DQ_ERR_INVALID_ARGUMENT;
-    *out = nullptr;
-    if (ndev > 1) {
-        g_create_error = "one device per context: use one process/context per GPU";
-        return DQ_ERR_INVALID_ARGUMENT;
+    if (!ctx) return DQ_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
+                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
+                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->newtext, &ctx->s_pos,
+                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (auto &e : ctx->pass_events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
     }
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); libdeltaq_cuda has no CPU fallback";
-        return DQ_ERR_NO_DEVICE;
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->h_pos.p) cudaFreeHost(ctx->h_pos.p);
+    if (ctx->h_len.p) cudaFreeHost(ctx->h_len.p);
+    if (ctx->h_code.p) cudaFreeHost(ctx->h_code.p);
+    if (ctx->h_heads.p) cudaFreeHost(ctx->h_heads.p);
+    if (ctx->h_tiles.p) cudaFreeHost(ctx->h_tiles.p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 8; ++i) {
+        if (ctx->slice_ready[i]) cudaEventDestroy(ctx->slice_ready[i]);
+        if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
+        if (ctx->slice_stream[i]) cudaStreamDestroy(ctx->slice_stream[i]);
     }
+    if (ctx->heads_done) cudaEventDestroy(ctx->heads_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DQ_OK;
+}
+
+int create_single(dq_ctx **out, int dev)
+{
+    cudaError_t e = cudaSuccess;
     dq_ctx *ctx = new (std::nothrow) dq_ctx();
     if (!ctx) return DQ_ERR_OUT_OF_MEMORY;
-    int dev = 0;
-    if (devices && ndev == 1)
-        dev = devices[0];
-    else
-        cudaGetDevice(&dev);
     ctx->device = dev;
     if (const char *mp = getenv("DQ_MATCH_POLICY")) ctx->match_policy = atoi(mp);
     if (const char *hc = getenv("DQ_HEADS_CAP")) ctx->heads_cap_override = (uint32_t)atoi(hc);
     auto fail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
-        delete ctx;
+        destroy_single(ctx);
         return DQ_ERR_CUDA;
     };
     if ((e = cudaSetDevice(dev)) != cudaSuccess) return fail("cudaSetDevice", e);
@@ -546,6 +592,56 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
     if ((e = cudaFuncSetAttribute(sx::small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sx::small_sort_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(rx::onesweep_policy_kernel<ds::BucketPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(rx::onesweep_policy_kernel<ds::RequestPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(rx::onesweep_policy_kernel<ds::UpdatePolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    *out = ctx;
+    return DQ_OK;
+}
+
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
+{
+    if (!out) return DQ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (ndev < 0 || ndev > ds::kMaxShards || (ndev > 0 && !devices)) {
+        g_create_error = "dq_cuda_create: ndev must be 0.." + std::to_string(ds::kMaxShards) + " with a device list";
+        return DQ_ERR_INVALID_ARGUMENT;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); libdeltaq_cuda has no CPU fallback";
+        return DQ_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    if (ndev >= 1)
+        dev = devices[0];
+    else
+        cudaGetDevice(&dev);
+    dq_ctx *ctx = nullptr;
+    int rc = create_single(&ctx, dev);
+    if (rc != DQ_OK) return rc;
+    if (ndev > 1) {
+        rc = create_group(ctx, devices, ndev);
+        if (rc != DQ_OK) {
+            g_create_error = ctx->err;
+            destroy_group(ctx);
+            destroy_single(ctx);
+            return rc;
+        }
+    }
     *out = ctx;
     return DQ_OK;
 }
@@ -553,35 +649,8 @@ int dq_cuda_create(dq_ctx **out, const int *devices, int ndev)
 int dq_cuda_destroy(dq_ctx *ctx)
 {
     if (!ctx) return DQ_OK;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
-                      &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
-                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->newtext, &ctx->s_pos,
-                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
-    for (DevBuf *b : bufs)
-        if (b->p) cudaFree(b->p);
-    for (auto &e : ctx->pass_events) {
-        cudaEventDestroy(e.a);
-        cudaEventDestroy(e.b);
-    }
-    if (ctx->h_count) cudaFreeHost(ctx->h_count);
-    if (ctx->h_pos.p) cudaFreeHost(ctx->h_pos.p);
-    if (ctx->h_len.p) cudaFreeHost(ctx->h_len.p);
-    if (ctx->h_code.p) cudaFreeHost(ctx->h_code.p);
-    if (ctx->h_heads.p) cudaFreeHost(ctx->h_heads.p);
-    if (ctx->h_tiles.p) cudaFreeHost(ctx->h_tiles.p);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    for (int i = 0; i < 8; ++i) {
-        if (ctx->slice_ready[i]) cudaEventDestroy(ctx->slice_ready[i]);
-        if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
-        if (ctx->slice_stream[i]) cudaStreamDestroy(ctx->slice_stream[i]);
-    }
-    if (ctx->heads_done) cudaEventDestroy(ctx->heads_done);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    destroy_group(ctx);
+    destroy_single(ctx);
     return DQ_OK;
 }
 
@@ -641,6 +710,10 @@ int dq_cuda_suffix_sort(dq_ctx *ctx, const uint8_t *text, int32_t n, int32_t *sa
     DQ_TRY(check_args(ctx, n >= 0 && (n == 0 || (text && sa_out)), "dq_cuda_suffix_sort: null buffer or negative length"));
     DQ_CK(ctx, cudaSetDevice(ctx->device));
     ctx->resident_n = -1;
+    if (ctx->group) {
+        ctx->group->n = 0;
+        if ((uint32_t)n >= ctx->group->shard_min) return group_sort(ctx, text, (uint32_t)n, sa_out);
+    }
     DQ_TRY(upload_text(ctx, ctx->text, text, (uint32_t)n, cudaMemcpyHostToDevice));
     DQ_TRY(sort_resident(ctx, (uint32_t)n));
     if (n) DQ_CK(ctx, cudaMemcpyAsync(sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -657,6 +730,10 @@ int dq_cuda_suffix_sort_device(dq_ctx *ctx, const uint8_t *d_text, int32_t n, in
     DQ_TRY(check_args(ctx, n >= 0 && (n == 0 || (d_text && d_sa_out)), "dq_cuda_suffix_sort_device: null buffer or negative length"));
     DQ_CK(ctx, cudaSetDevice(ctx->device));
     ctx->resident_n = -1;
+    if (ctx->group) {
+        ctx->group->n = 0;
+        if ((uint32_t)n >= ctx->group->shard_min) return group_sort(ctx, d_text, (uint32_t)n, d_sa_out);
+    }
     DQ_TRY(upload_text(ctx, ctx->text, d_text, (uint32_t)n, cudaMemcpyDeviceToDevice));
     DQ_TRY(sort_resident(ctx, (uint32_t)n));
     if (n) DQ_CK(ctx, cudaMemcpyAsync(d_sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -709,6 +786,8 @@ int dq_cuda_bsdiff_search(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int
 {
     if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (group_wants_search(ctx, n, I_or_null, count))
+        return group_search_common(ctx, old_, n, I_or_null, new_, m, scan_begin, count, pos_out, len_out);
     return search_common(ctx, old_, n, I_or_null, new_, m, scan_begin, count, pos_out, len_out, false);
 }
 
@@ -718,6 +797,8 @@ int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *d_old, int32_t n, c
 {
     if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (group_wants_search(ctx, n, d_I_or_null, count))
+        return group_search_common(ctx, d_old, n, d_I_or_null, d_new, m, scan_begin, count, d_pos_out, d_len_out);
     return search_common(ctx, d_old, n, d_I_or_null, d_new, m, scan_begin, count, d_pos_out, d_len_out, true);
 }
 
@@ -892,43 +973,10 @@ extern "C" void dq_emu_debug_counters(unsigned long long *out, int reset)
 #endif
 
 // ======================================================================================================
-// multi-GPU building blocks
-namespace {
-
-int dist_reserve(dq_ctx *ctx, uint32_t count)
-{
-    const size_t c8 = (size_t)std::max<uint32_t>(count, 1) * 8, c4 = (size_t)std::max<uint32_t>(count, 1) * 4;
-    DQ_TRY(ensure(ctx, ctx->keyA, c8));
-    DQ_TRY(ensure(ctx, ctx->keyB, c8));
-    DQ_TRY(ensure(ctx, ctx->valA, c4));
-    DQ_TRY(ensure(ctx, ctx->valB, c4));
-    DQ_TRY(ensure(ctx, ctx->slotA, c4));
-    DQ_TRY(ensure(ctx, ctx->slotB, c4));
-    return DQ_OK;
-}
-
-}  // namespace
-
+// building blocks exported for tests and reuse
 extern "C" {
 
-int dq_cuda_dist_pack(dq_ctx *ctx, const uint8_t *d_slice, int32_t pos_begin, int32_t pos_count, uint64_t *d_keys,
-                      uint32_t *d_vals, uint64_t *d_hist16)
-{
-    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    DQ_TRY(check_args(ctx, pos_begin >= 0 && pos_count >= 0 && (pos_count == 0 || (d_slice && d_keys && d_vals)),
-                      "dist_pack: bad arguments"));
-    if (pos_count == 0) return DQ_OK;
-    DQ_CK(ctx, cudaSetDevice(ctx->device));
-    auto k = sx::pack_slice_kernel;
-    DQ_LAUNCH(k, producer_grid(ctx, (uint64_t)pos_count), sx::kPackThreads, 0, ctx->stream, d_slice, (uint32_t)pos_begin,
-              (uint32_t)pos_count, d_keys, d_vals, reinterpret_cast<unsigned long long *>(d_hist16));
-    DQ_CK(ctx, cudaGetLastError());
-    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return DQ_OK;
-}
-
-// shared by the public entry point and dist_partition: sorts in place, optionally returns the first digit's counts
+// sorts in place, optionally returns the first digit's counts
 static int radix_sort_device_locked(dq_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, int32_t count, int32_t bit_lo,
                                     int32_t nbits, int64_t *hist_out_host)
 {
@@ -971,135 +1019,6 @@ int dq_cuda_radix_sort_pairs_device(dq_ctx *ctx, uint64_t *d_keys, uint32_t *d_v
                       "radix_sort_pairs_device: bad arguments"));
     DQ_CK(ctx, cudaSetDevice(ctx->device));
     return radix_sort_device_locked(ctx, d_keys, d_vals, count, bit_lo, nbits, hist_out_host);
-}
-
-int dq_cuda_dist_partition(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, int32_t count,
-                           const uint8_t *d_lut, uint64_t *d_keys_out, uint32_t *d_vals_out, int64_t *counts_out_host)
-{
-    if (!ctx || !counts_out_host) return DQ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    DQ_TRY(check_args(ctx, count >= 0 && d_lut && (count == 0 || (d_keys && d_vals && d_keys_out && d_vals_out)),
-                      "dist_partition: bad arguments"));
-    DQ_CK(ctx, cudaSetDevice(ctx->device));
-    std::fill(counts_out_host, counts_out_host + 256, (int64_t)0);
-    if (count == 0) return DQ_OK;
-    // destination keys + identity permutation, one radix pass over them, then one gather of the tuples
-    DQ_TRY(ensure(ctx, ctx->partK, (size_t)count * 8));
-    DQ_TRY(ensure(ctx, ctx->partV, (size_t)count * 4));
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up((uint64_t)count, 256), (uint64_t)ctx->sm_count * 16));
-    {
-        auto k = sx::dest_keys_kernel;
-        DQ_LAUNCH(k, grid, 256, 0, ctx->stream, d_keys, (uint32_t)count, d_lut, ctx->partK.as<uint64_t>(),
-                  ctx->partV.as<uint32_t>());
-    }
-    DQ_TRY(radix_sort_device_locked(ctx, ctx->partK.as<uint64_t>(), ctx->partV.as<uint32_t>(), count, 0, 8, counts_out_host));
-    {
-        auto k = sx::gather_pairs_kernel;
-        DQ_LAUNCH(k, grid, 256, 0, ctx->stream, d_keys, d_vals, ctx->partV.as<uint32_t>(), (uint32_t)count, d_keys_out,
-                  d_vals_out);
-    }
-    DQ_CK(ctx, cudaGetLastError());
-    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return DQ_OK;
-}
-
-int dq_cuda_dist_requests(dq_ctx *ctx, int64_t h, uint64_t *d_q, uint32_t *d_idx)
-{
-    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    if (ctx->dist_a == 0) return DQ_OK;
-    DQ_TRY(check_args(ctx, h >= 0 && d_q && d_idx, "dist_requests: bad arguments"));
-    DQ_CK(ctx, cudaSetDevice(ctx->device));
-    const uint32_t a = ctx->dist_a;
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up((uint64_t)a, 256), (uint64_t)ctx->sm_count * 16));
-    auto k = sx::requests_kernel;
-    DQ_LAUNCH(k, grid, 256, 0, ctx->stream, ctx->dist_vout, a, (uint64_t)h, d_q, d_idx);
-    DQ_CK(ctx, cudaGetLastError());
-    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return DQ_OK;
-}
-
-int dq_cuda_dist_round0(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, int32_t count, int32_t n,
-                        int32_t slot_base, int32_t *d_sa_local, uint64_t *d_upd_pos, uint32_t *d_upd_rank,
-                        int32_t *active_out)
-{
-    if (!ctx || !active_out) return DQ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    DQ_TRY(check_args(ctx, count >= 0 && n >= 0 && slot_base >= 0 &&
-                               (count == 0 || (d_keys && d_vals && d_sa_local && d_upd_pos && d_upd_rank)),
-                      "dist_round0: bad arguments"));
-    DQ_CK(ctx, cudaSetDevice(ctx->device));
-    ctx->resident_n = -1;
-    ctx->lcp_valid = false;
-    ctx->pre3_valid = false;
-    ctx->dist_a = 0;
-    *active_out = 0;
-    if (count == 0) return DQ_OK;
-    DQ_TRY(dist_reserve(ctx, (uint32_t)count));
-    const size_t c8 = (size_t)count * 8, c4 = (size_t)count * 4;
-    DQ_CK(ctx, cudaMemcpyAsync(ctx->keyA.p, d_keys, c8, cudaMemcpyDeviceToDevice, ctx->stream));
-    DQ_CK(ctx, cudaMemcpyAsync(ctx->valA.p, d_vals, c4, cudaMemcpyDeviceToDevice, ctx->stream));
-    rx::PassPlan plan{};
-    rx::plan_add_field(plan, 0, 64);
-    DQ_TRY(zero_hist(ctx));
-    {
-        auto k = sx::hist_only_kernel;
-        DQ_LAUNCH(k, producer_grid(ctx, (uint64_t)count), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream,
-                  ctx->keyA.as<uint64_t>(), (uint32_t)count, plan, ctx->hist.as<uint32_t>());
-    }
-    SortBufs s{ctx->keyA.as<uint64_t>(), ctx->keyB.as<uint64_t>(), ctx->valA.as<uint32_t>(), ctx->valB.as<uint32_t>()};
-    DQ_TRY(run_passes(ctx, s, (uint32_t)count, plan, false));
-    uint32_t a = 0;
-    uint32_t *slot_cur = ctx->slotA.as<uint32_t>(), *slot_nxt = ctx->slotB.as<uint32_t>();
-    DQ_TRY((run_rank<true, true>(ctx, s.kin, s.vin, nullptr, (uint32_t)count, (uint32_t)n, s.vout,
-                                 reinterpret_cast<uint32_t *>(s.kout), slot_cur, &a, d_sa_local, (uint32_t)slot_base,
-                                 d_upd_pos, d_upd_rank)));
-    ctx->dist_kin = s.kin;
-    ctx->dist_kout = s.kout;
-    ctx->dist_vin = s.vin;
-    ctx->dist_vout = s.vout;
-    ctx->dist_slot_cur = slot_cur;
-    ctx->dist_slot_nxt = slot_nxt;
-    ctx->dist_a = a;
-    *active_out = (int32_t)a;
-    return DQ_OK;
-}
-
-int dq_cuda_dist_round(dq_ctx *ctx, const uint32_t *d_r2, int32_t n, int32_t slot_base, int32_t *d_sa_local,
-                       uint64_t *d_upd_pos, uint32_t *d_upd_rank, int32_t *active_out)
-{
-    if (!ctx || !active_out) return DQ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    const uint32_t a = ctx->dist_a;
-    *active_out = 0;
-    if (a == 0) return DQ_OK;
-    DQ_TRY(check_args(ctx, n > 0 && d_r2 && d_sa_local && d_upd_pos && d_upd_rank, "dist_round: bad arguments"));
-    DQ_CK(ctx, cudaSetDevice(ctx->device));
-    // active set: sa = dist_vout, rank = (uint32*)dist_kout, slot = dist_slot_cur; keys go to dist_kin
-    SortBufs s{ctx->dist_kin, ctx->dist_kout, ctx->dist_vin, ctx->dist_vout};
-    rx::PassPlan rp{};
-    rx::plan_add_field(rp, 0, bit_length((uint64_t)n));
-    rx::plan_add_field(rp, 32, bit_length(n > 1 ? (uint64_t)n - 1 : 1));
-    DQ_TRY(zero_hist(ctx));
-    {
-        auto k = sx::build_keys_r2_kernel;
-        DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream,
-                  reinterpret_cast<uint32_t *>(s.kout), d_r2, a, s.kin, rp, ctx->hist.as<uint32_t>());
-    }
-    std::swap(s.vin, s.vout);
-    DQ_TRY(run_passes(ctx, s, a, rp, true));
-    uint32_t next_a = 0;
-    DQ_TRY((run_rank<false, true>(ctx, s.kin, s.vin, ctx->dist_slot_cur, a, (uint32_t)n, s.vout,
-                                  reinterpret_cast<uint32_t *>(s.kout), ctx->dist_slot_nxt, &next_a, d_sa_local,
-                                  (uint32_t)slot_base, d_upd_pos, d_upd_rank)));
-    std::swap(ctx->dist_slot_cur, ctx->dist_slot_nxt);
-    ctx->dist_kin = s.kin;
-    ctx->dist_kout = s.kout;
-    ctx->dist_vin = s.vin;
-    ctx->dist_vout = s.vout;
-    ctx->dist_a = next_a;
-    *active_out = (int32_t)next_a;
-    return DQ_OK;
 }
 
 }  // extern "C"

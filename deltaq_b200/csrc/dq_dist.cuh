@@ -1,0 +1,206 @@
+// dq_dist.cuh -- device side of the multi-GPU ("group") suffix sort: one text sorted by all the GPUs of a context
+// created with ndev > 1 (include/deltaq_cuda.h, dq_cuda_create).  Host side: dq_group.inl.
+//
+// The reference has no analogue (it is single threaded, /root/reference/src/DeltaQ.SuffixSorting.LibDivSufSort/
+// DivSufSort.cs:18-42); this is SURVEY.md section 8(e): distributed prefix doubling.
+//   * SA is partitioned by KEY: shard d owns the suffixes whose 8-byte key falls in its splitter interval, i.e. a
+//     contiguous range of SA slots.  Groups never cross shards, so every sort after the first exchange is local.
+//   * ISA is partitioned by text POSITION: shard o owns ISA[o << kb, (o+1) << kb).
+// Every exchange is a stable partition by destination whose scatter writes straight into the destination GPU's
+// memory over NVLink (peer pointers in the policy of the onesweep pass, dq_radix.cuh): partition and all-to-all-v are
+// ONE kernel, the receive offsets are known before it starts, and nothing is staged or re-packed on either side.
+//   round 0   (key, position) tuples  -> the bucket owner's sort input                     BucketPolicy
+//   round r   requests ISA[sa+h]      -> the position owner's inbox (4 B each); the owner answers into the requester's
+//             reply array in request order, so the requester never gathers                 RequestPolicy / reply_kernel
+//   round r   (position, new rank)    -> the position owner's inbox (8 B each), applied there  UpdatePolicy / apply_kernel
+#pragma once
+#include "dq_common.cuh"
+#include "dq_radix.cuh"
+#include "dq_suffix.cuh"
+
+namespace dq {
+namespace dist {
+
+constexpr int kMaxShards = 16;
+constexpr uint32_t kPastEnd = 0xffffffffu;  // request marker: sa + h is past the end of the text, the answer is 0
+
+struct Splitters {
+    uint64_t s[kMaxShards];  // s[0..n): ascending; shard d owns the keys in [s[d-1], s[d])
+    int n;
+};
+
+__device__ __forceinline__ uint32_t dest_of(const Splitters &sp, uint64_t key)
+{
+    uint32_t d = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxShards - 1; ++j)
+        if (j < sp.n) d += key >= sp.s[j] ? 1u : 0u;
+    return d;
+}
+
+// ---- policies of the partition + exchange passes ------------------------------------------------------------
+struct BucketPolicy {
+    static constexpr bool kHasVal = true;
+    Splitters sp;
+    uint64_t *kout[kMaxShards];  // shard d's round-0 sort input (peer memory)
+    uint32_t *vout[kMaxShards];
+    int bits;
+    __device__ __forceinline__ uint32_t digit(uint64_t key) const { return dest_of(sp, key); }
+    __device__ __forceinline__ int nbits() const { return bits; }
+    // gbase[d] of this pass = where this source's run starts inside shard d's input, so dst indexes it directly
+    __device__ __forceinline__ void store(uint32_t d, uint32_t dst, uint64_t key, uint32_t val) const
+    {
+        kout[d][dst] = key;
+        vout[d][dst] = val;
+    }
+};
+
+// active element = (rank << 32 | sa)
+struct RequestPolicy {
+    static constexpr bool kHasVal = false;
+    uint64_t *kout;              // local: the active set regrouped by position owner
+    uint32_t *qout[kMaxShards];  // this source's region of owner d's request inbox (peer memory)
+    const uint32_t *gbase;       // local exclusive digit offsets (the pass's own gbase)
+    uint64_t h;
+    uint32_t n;
+    int kb;
+    uint32_t self;
+    int bits;
+    __device__ __forceinline__ uint32_t digit(uint64_t key) const
+    {
+        const uint64_t q = (uint64_t)(uint32_t)key + h;
+        return q < n ? (uint32_t)(q >> kb) : self;
+    }
+    __device__ __forceinline__ int nbits() const { return bits; }
+    __device__ __forceinline__ void store(uint32_t d, uint32_t dst, uint64_t key, uint32_t) const
+    {
+        kout[dst] = key;
+        const uint64_t q = (uint64_t)(uint32_t)key + h;
+        qout[d][dst - gbase[d]] = q < n ? (uint32_t)(q - ((uint64_t)d << kb)) : kPastEnd;
+    }
+};
+
+// update = (new rank << 32 | position); the owner receives (new rank << 32 | position - first owned position)
+struct UpdatePolicy {
+    static constexpr bool kHasVal = false;
+    uint64_t *uout[kMaxShards];  // this source's region of owner d's update inbox (peer memory)
+    const uint32_t *gbase;
+    int kb;
+    int bits;
+    __device__ __forceinline__ uint32_t digit(uint64_t key) const { return (uint32_t)key >> kb; }
+    __device__ __forceinline__ int nbits() const { return bits; }
+    __device__ __forceinline__ void store(uint32_t d, uint32_t dst, uint64_t key, uint32_t) const
+    {
+        uout[d][dst - gbase[d]] = key - ((uint64_t)d << kb);
+    }
+};
+
+// counts of the policy's digits over keys[0..count) -> ghist[0..256) (zero before the launch).  The digits are few
+// (<= kMaxShards), so equal digits inside a warp are merged before they touch the shared counters.
+template <typename Policy>
+__global__ void __launch_bounds__(256)
+hist_policy_kernel(const uint64_t *__restrict__ keys, uint32_t count, const Policy pol, uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t sh[kMaxShards];
+    if (threadIdx.x < kMaxShards) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (count + stride - 1) / stride;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t k = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = k < count;
+        const uint32_t d = valid ? pol.digit(keys[k]) : 0xffffu;
+        const unsigned peers = __match_any_sync(kFullMask, d);
+        if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxShards && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// what a destination needs to know about one source's run in its inbox
+struct RunMeta {
+    uint32_t count;  // entries this source sent
+    uint32_t base;   // where the run sits in the source's own regrouped array (requests: where the answers go)
+};
+
+struct MetaPtrs {
+    RunMeta *p[kMaxShards];  // shard d's meta array (peer memory), indexed by source
+};
+struct ReplyPtrs {
+    uint32_t *p[kMaxShards];  // shard s's reply array (peer memory)
+};
+
+// after the digit scan: tell every destination d how many entries this source sends it.  One warp.
+__global__ void publish_meta_kernel(const uint32_t *__restrict__ ghist, const uint32_t *__restrict__ gbase,
+                                    const MetaPtrs meta_of, uint32_t self, uint32_t shards)
+{
+    const unsigned d = threadIdx.x;
+    if (d < shards) meta_of.p[d][self] = RunMeta{ghist[d], gbase[d]};
+}
+
+// sampled 8-byte keys of a text slice, for the splitters: position = a fixed odd multiplier walk over the slice
+__global__ void __launch_bounds__(256)
+sample_keys_kernel(const uint8_t *__restrict__ T, uint32_t count, uint32_t nsamples, uint64_t *__restrict__ out)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nsamples) return;
+    const uint32_t off = (uint32_t)(((uint64_t)j * 0x9E3779B1ull + 12345u) % count);
+    out[j] = suffix::load_key8(T, off);
+}
+
+// owner side of the ISA fetch: for every source s, answer its requests in order, straight into the requester's
+// reply array (peer memory): reply_of[s][meta[s].base + j] = ISA[q_j] + 1, or 0 past the end of the text.
+__global__ void __launch_bounds__(256)
+reply_kernel(const uint32_t *__restrict__ inbox, uint32_t cap, const RunMeta *__restrict__ meta,
+             const uint32_t *__restrict__ ISA, const ReplyPtrs reply_of, uint32_t shards)
+{
+    for (uint32_t s = 0; s < shards; ++s) {
+        const RunMeta m = meta[s];
+        const uint32_t *q = inbox + (size_t)s * cap;
+        uint32_t *out = reply_of.p[s] + m.base;
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m.count; j += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t p = ld_stream(q + j);
+            out[j] = p == kPastEnd ? 0u : __ldg(ISA + p) + 1u;
+        }
+    }
+}
+
+// owner side of the rank updates: ISA[position] = rank for every entry of every source's run
+__global__ void __launch_bounds__(256)
+apply_kernel(const uint64_t *__restrict__ inbox, uint32_t cap, const RunMeta *__restrict__ meta,
+             uint32_t *__restrict__ ISA, uint32_t shards)
+{
+    for (uint32_t s = 0; s < shards; ++s) {
+        const uint32_t cnt = meta[s].count;
+        const uint64_t *u = inbox + (size_t)s * cap;
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t v = ld_stream(u + j);
+            ISA[(uint32_t)v] = (uint32_t)(v >> 32);
+        }
+    }
+}
+
+// key[k] = rank << 32 | reply[k], val[k] = sa, from the regrouped active set and the owners' answers; histograms of
+// the round's digits on the way (as build_keys_kernel does on one GPU)
+__global__ void __launch_bounds__(suffix::kPackThreads)
+build_keys_reply_kernel(const uint64_t *__restrict__ act, const uint32_t *__restrict__ reply, uint32_t a,
+                        uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, radix::PassPlan plan,
+                        uint32_t *__restrict__ ghist)
+{
+    DQ_DYN_SMEM(smem);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < plan.npass * radix::kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = act[k];
+        const uint64_t key = (e & 0xffffffff00000000ull) | reply[k];
+        keys[k] = key;
+        vals[k] = (uint32_t)e;
+        radix::hist_accumulate(sh, plan, key);
+    }
+    __syncthreads();
+    radix::hist_flush(sh, plan.npass, ghist);
+}
+
+}  // namespace dist
+}  // namespace dq

@@ -170,17 +170,36 @@ constexpr size_t pass_smem_bytes()
     return (size_t)kTile * 8 + (size_t)kTile * 4 + (size_t)kWarps * kRadix * 4 + kRadix * 4 + 128;
 }
 
+
+// ---- what a pass sorts by and where it puts the result ------------------------------------------------------
+// A policy names the digit of a key and stores one ranked pair.  `dst` is the pair's index inside the output
+// sequence of its digit, counted from gbase[digit] (for the plain pass: the global output index).
+struct PlainPolicy {
+    static constexpr bool kHasVal = true;
+    int shift;
+    uint32_t mask;
+    uint64_t *__restrict__ kout;
+    uint32_t *__restrict__ vout;
+    __device__ __forceinline__ uint32_t digit(uint64_t key) const { return (uint32_t)(key >> shift) & mask; }
+    __device__ __forceinline__ int nbits() const { return __popc(mask); }
+    __device__ __forceinline__ void store(uint32_t, uint32_t dst, uint64_t key, uint32_t val) const
+    {
+        kout[dst] = key;
+        vout[dst] = val;
+    }
+};
+
 // stable rank of every item of the warp among the tile's items with the same digit; wh[] = the warp's
 // running counters, pre-loaded with (slot of the digit in the tile) + (items of earlier warps)
-template <bool FULL, bool USE_MATCH>
+template <bool FULL, bool USE_MATCH, typename Policy>
 __device__ __forceinline__ void rank_and_stage(const uint64_t (&key)[kItems], uint32_t (&rk)[kItems / 2], uint32_t *wh,
-                                               uint64_t *skeys, uint32_t wbase, uint32_t tile_count, int shift,
-                                               uint32_t mask, int nbits)
+                                               uint64_t *skeys, uint32_t wbase, uint32_t tile_count, const Policy &pol,
+                                               int nbits)
 {
     const unsigned lane = lane_id();
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
-        const uint32_t dj = (uint32_t)(key[j] >> shift) & mask;
+        const uint32_t dj = pol.digit(key[j]);
         unsigned peers = match_digit<USE_MATCH>(dj, nbits);
         bool valid = true;
         if (!FULL) {
@@ -204,10 +223,9 @@ __device__ __forceinline__ void rank_and_stage(const uint64_t (&key)[kItems], ui
     }
 }
 
-template <typename DescT, bool FULL>
+template <typename DescT, bool FULL, typename Policy>
 __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
-                                              uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
-                                              uint32_t tile, uint32_t tile_count, int shift, uint32_t mask,
+                                              const Policy &pol, uint32_t tile, uint32_t tile_count,
                                               const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
                                               uint64_t *skeys, uint32_t *svals, uint32_t *whist, uint32_t *sout,
                                               uint32_t *smisc, bool few_distinct)
@@ -226,7 +244,7 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     uint32_t *wh = whist + warp * kRadix;
 #pragma unroll
     for (int j = 0; j < kItems; ++j)
-        if (FULL || wbase + j * 32 < tile_count) atomicAdd(&wh[(uint32_t)(key[j] >> shift) & mask], 1u);
+        if (FULL || wbase + j * 32 < tile_count) atomicAdd(&wh[pol.digit(key[j])], 1u);
     __syncthreads();
 
     // ---- 2. thread d: tile count of digit d, published immediately
@@ -242,14 +260,14 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     }
     DescT *my = lb + (size_t)tile * kRadix + d;
     if (tile > 0) st_desc(my, ((DescT)kStatusAggregate << VB) | (DescT)sum);
-    const int nbits = __popc(mask);
+    const int nbits = pol.nbits();
 
     // values are requested now and land during the look-back and the ranking
     uint32_t val[kItems];
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
         const uint32_t li = wbase + j * 32;
-        val[j] = (FULL || li < tile_count) ? ld_stream(vin + tile_base + li) : 0u;
+        val[j] = (Policy::kHasVal && (FULL || li < tile_count)) ? ld_stream(vin + tile_base + li) : 0u;
     }
 
     // exclusive scan of the 256 digit counts -> first slot of each digit inside the tile
@@ -305,32 +323,33 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     // ---- 4. stable ranking; keys go straight to their slot
     uint32_t rk[kItems / 2];  // two 16-bit slots per register (slots are < kTile <= 65536)
     if (few_distinct)
-        rank_and_stage<FULL, true>(key, rk, wh, skeys, wbase, tile_count, shift, mask, nbits);
+        rank_and_stage<FULL, true>(key, rk, wh, skeys, wbase, tile_count, pol, nbits);
     else
-        rank_and_stage<FULL, false>(key, rk, wh, skeys, wbase, tile_count, shift, mask, nbits);
+        rank_and_stage<FULL, false>(key, rk, wh, skeys, wbase, tile_count, pol, nbits);
     // ---- 5. values through the same slots, then stream the tile out
+    if (Policy::kHasVal) {
 #pragma unroll
-    for (int j = 0; j < kItems; ++j)
-        if (FULL || wbase + j * 32 < tile_count) svals[(rk[j >> 1] >> (16 * (j & 1))) & 0xffffu] = val[j];
+        for (int j = 0; j < kItems; ++j)
+            if (FULL || wbase + j * 32 < tile_count) svals[(rk[j >> 1] >> (16 * (j & 1))) & 0xffffu] = val[j];
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
         const uint32_t i = tid + j * kThreads;
         if (FULL || i < tile_count) {
             const uint64_t k = skeys[i];
-            const uint32_t dst = sout[(uint32_t)(k >> shift) & mask] + i;
-            kout[dst] = k;
-            vout[dst] = svals[i];
+            const uint32_t dg = pol.digit(k);
+            pol.store(dg, sout[dg] + i, k, Policy::kHasVal ? svals[i] : 0u);
         }
     }
 }
 
-template <typename DescT>
-__global__ void __launch_bounds__(kThreads, DQ_PASS_MIN_BLOCKS)
-onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
-                     uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t count, int shift,
-                     uint32_t mask, const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
-                     uint32_t *__restrict__ tile_ticket, const uint32_t *__restrict__ use_match)
+template <typename DescT, typename Policy>
+__device__ __forceinline__ void onesweep_pass_body(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                   const Policy &pol, uint32_t count,
+                                                   const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
+                                                   uint32_t *__restrict__ tile_ticket,
+                                                   const uint32_t *__restrict__ use_match)
 {
     DQ_DYN_SMEM(smem);
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
@@ -357,15 +376,35 @@ onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
         const uint32_t tile_base = tile * (uint32_t)kTile;
         const uint32_t tile_count = min((uint32_t)kTile, count - tile_base);
         if (tile_count == (uint32_t)kTile)
-            onesweep_tile<DescT, true>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals,
-                                       whist, sout, smisc, few);
+            onesweep_tile<DescT, true>(kin, vin, pol, tile, tile_count, gbase, lb, skeys, svals, whist, sout, smisc, few);
         else
-            onesweep_tile<DescT, false>(kin, vin, kout, vout, tile, tile_count, shift, mask, gbase, lb, skeys, svals,
-                                        whist, sout, smisc, few);
+            onesweep_tile<DescT, false>(kin, vin, pol, tile, tile_count, gbase, lb, skeys, svals, whist, sout, smisc, few);
 #if DQ_PASS_PERSISTENT
         __syncthreads();  // the staging area and smisc are reused by the next tile
     }
 #endif
+}
+
+template <typename DescT>
+__global__ void __launch_bounds__(kThreads, DQ_PASS_MIN_BLOCKS)
+onesweep_pass_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                     uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t count, int shift,
+                     uint32_t mask, const uint32_t *__restrict__ gbase, DescT *__restrict__ lb,
+                     uint32_t *__restrict__ tile_ticket, const uint32_t *__restrict__ use_match)
+{
+    const PlainPolicy pol{shift, mask, kout, vout};
+    onesweep_pass_body<DescT>(kin, vin, pol, count, gbase, lb, tile_ticket, use_match);
+}
+
+// The same pass with a caller-defined digit and destination (dq_dist.cuh: partition + peer-memory exchange in one
+// kernel).  Counts are < 2^30 on this path (one shard's share of an int32-sized text).
+template <typename Policy>
+__global__ void __launch_bounds__(kThreads, DQ_PASS_MIN_BLOCKS)
+onesweep_policy_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin, const Policy pol,
+                       uint32_t count, const uint32_t *__restrict__ gbase, uint32_t *__restrict__ lb,
+                       uint32_t *__restrict__ tile_ticket, const uint32_t *__restrict__ use_match)
+{
+    onesweep_pass_body<uint32_t>(kin, vin, pol, count, gbase, lb, tile_ticket, use_match);
 }
 
 }  // namespace radix

@@ -119,24 +119,6 @@ build_keys_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ 
     radix::hist_flush(sh, plan.npass, ghist);
 }
 
-// K6 for the multi-GPU path: the second key half was fetched from the position owners (r2[k], already +1 / 0)
-__global__ void __launch_bounds__(kPackThreads)
-build_keys_r2_kernel(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ r2, uint32_t a,
-                     uint64_t *__restrict__ keys, radix::PassPlan plan, uint32_t *__restrict__ ghist)
-{
-    DQ_DYN_SMEM(smem);
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
-    for (int i = threadIdx.x; i < plan.npass * radix::kRadix; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = ((uint64_t)rank[k] << 32) | r2[k];
-        keys[k] = key;
-        radix::hist_accumulate(sh, plan, key);
-    }
-    __syncthreads();
-    radix::hist_flush(sh, plan.npass, ghist);
-}
-
 // K0 for a slice of text positions [pos_begin, pos_begin + count): element k stands for suffix
 // pos_begin + count - 1 - k (descending, as in pack_keys_kernel).  T points at the slice (T[0] is text position
 // pos_begin), zero padded.  hist16 (65536 counters, may be null) receives the histogram of the keys' top 16 bits
@@ -162,39 +144,6 @@ pack_slice_kernel(const uint8_t *__restrict__ T, uint32_t pos_begin, uint32_t co
             const unsigned peers = __match_any_sync(kFullMask, bin);
             if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist16[bin], (unsigned long long)__popc(peers));
         }
-    }
-}
-
-// partition keys for the bucket exchange: dest[k] = lut[key >> 48] as a 64-bit radix key, idx[k] = k
-__global__ void __launch_bounds__(256)
-dest_keys_kernel(const uint64_t *__restrict__ keys, uint32_t count, const uint8_t *__restrict__ lut,
-                 uint64_t *__restrict__ dest, uint32_t *__restrict__ idx)
-{
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (uint64_t)gridDim.x * blockDim.x) {
-        dest[k] = lut[keys[k] >> 48];
-        idx[k] = (uint32_t)k;
-    }
-}
-
-// out[i] = in[perm[i]] for the (key, value) pairs
-__global__ void __launch_bounds__(256)
-gather_pairs_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin, const uint32_t *__restrict__ perm,
-                    uint32_t count, uint64_t *__restrict__ kout, uint32_t *__restrict__ vout)
-{
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t p = perm[i];
-        kout[i] = kin[p];
-        vout[i] = vin[p];
-    }
-}
-
-// ISA requests of the unresolved set: q[k] = sa[k] + h as a 64-bit radix key, idx[k] = k
-__global__ void __launch_bounds__(256)
-requests_kernel(const uint32_t *__restrict__ sa, uint32_t a, uint64_t h, uint64_t *__restrict__ q, uint32_t *__restrict__ idx)
-{
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
-        q[k] = (uint64_t)sa[k] + h;
-        idx[k] = (uint32_t)k;
     }
 }
 
@@ -362,18 +311,19 @@ __host__ __device__ __forceinline__ uint32_t rk_sum(uint64_t v) { return (uint32
 //   "slot of the last head at or before me" = shfl from the highest head bit at or below my lane,
 //   "survivors before me"                   = popc of the survivor ballot below my lane.
 //
-// DIST (multi-GPU, deltaq_b200/parallel.py): this GPU sorts one key bucket that owns the SA slots
+// DIST (multi-GPU, dq_dist.cuh / dq_group.inl): this GPU sorts one key bucket that owns the SA slots
 // [slot_base, slot_base + bucket size); ISA is partitioned by text position across the GPUs, so instead of
-// writing ISA the kernel emits one (position, rank) update per element (upd_pos/upd_rank, dense, in sorted
-// order) for the host side to route to the owners, and SA is the bucket-local array (index slot - slot_base).
+// writing ISA the kernel emits one update (rank << 32 | position) per element (upd, dense, in sorted order) for
+// the exchange pass to route to the owners, SA is the bucket-local array (index slot - slot_base), and the next
+// active set is written packed the same way (act_out) instead of as sa_out / rank_out.
 template <bool ROUND0, bool DIST = false>
 __global__ void __launch_bounds__(kRankThreads)
 rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ sa,
                     const uint32_t *__restrict__ slot_in, uint32_t a, uint32_t n, uint32_t *__restrict__ ISA,
                     int32_t *__restrict__ SA, uint32_t *__restrict__ sa_out, uint32_t *__restrict__ rank_out,
                     uint32_t *__restrict__ slot_out, uint64_t *__restrict__ lb, uint32_t *__restrict__ tile_ticket,
-                    uint32_t *__restrict__ count_out, uint32_t slot_base = 0, uint64_t *__restrict__ upd_pos = nullptr,
-                    uint32_t *__restrict__ upd_rank = nullptr, const uint32_t *__restrict__ depth_in = nullptr,
+                    uint32_t *__restrict__ count_out, uint32_t slot_base = 0, uint64_t *__restrict__ upd = nullptr,
+                    uint64_t *__restrict__ act_out = nullptr, const uint32_t *__restrict__ depth_in = nullptr,
                     uint32_t *__restrict__ depth_out = nullptr, uint32_t hmin = 0,
                     uint32_t *__restrict__ min_depth_inv = nullptr)
 {
@@ -504,16 +454,16 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         const uint32_t nr = le ? mine : carry;
         const bool valid = (vb[j] >> lane) & 1u;
         if (valid) {
-            if (DIST) {
-                const uint32_t k = wbase + j * 32 + lane;
-                upd_pos[k] = s[j];
-                upd_rank[k] = nr;
-            }
+            if (DIST) upd[wbase + j * 32 + lane] = ((uint64_t)nr << 32) | s[j];
             if ((sb[j] >> lane) & 1u) {
                 const uint32_t o = out + __popc(sb[j] & lanemask_lt());
                 if (!DIST && (ROUND0 || nr != (uint32_t)(key[j] >> 32))) ISA[s[j]] = nr;
-                sa_out[o] = s[j];
-                rank_out[o] = nr;
+                if (DIST) {
+                    act_out[o] = ((uint64_t)nr << 32) | s[j];
+                } else {
+                    sa_out[o] = s[j];
+                    rank_out[o] = nr;
+                }
                 slot_out[o] = sl[j];
                 if (depth_out) {
                     // bytes the (sub)group now shares: a run-length refined group shares exactly its run, any

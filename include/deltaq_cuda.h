@@ -12,7 +12,7 @@
  *
  * Conventions: plain pointers and sizes; every function returns a status (0 = DQ_OK, negative = error
  * class) and never throws; the text of the last error of a context is dq_cuda_last_error(ctx).  A context
- * owns one device, one stream and its scratch memory; it serves one call at a time (calls on one context
+ * owns one device (or a device group, see dq_cuda_create), its streams and scratch memory; it serves one call at a time (calls on one context
  * are serialised by an internal lock); contexts are independent.
  */
 #ifndef DELTAQ_CUDA_H
@@ -62,12 +62,21 @@ typedef struct dq_stats {
  *                         or from 1 MiB up out of the sort's round-0 keys once the context has searched;
  *                         DQ_PREFIX3_SORTED_MIN=n lowers that 1 MiB)
  *   DQ_MATCH_POLICY=0|1|2 which radix passes of a doubling round rank with MATCH.ANY
+ *   DQ_SHARD_MIN=bytes    device groups (dq_cuda_create with ndev > 1): smallest input that is sharded (default 128 MiB)
  */
 
 /* ---- context ------------------------------------------------------------------------------------ */
 
-/* devices/ndev: CUDA ordinals to use; NULL/0 = current device.  This build drives one device per context
- * (ndev must be <= 1); multi-GPU runs use one process and one context per GPU. */
+/* devices/ndev: CUDA ordinals to use; NULL/0 = current device.
+ * ndev > 1 (at most 16) makes a device GROUP: this one context, in this one process, drives all listed GPUs
+ * (peer access between them is required and enabled here).  Every entry point keeps its meaning; inputs of at
+ * least DQ_SHARD_MIN bytes (default 128 MiB) are worked on by all GPUs of the group:
+ *   dq_cuda_suffix_sort*     one text sorted by all GPUs -- distributed prefix doubling; every exchange between GPUs
+ *                            is a partition kernel that scatters straight into peer memory over NVLink;
+ *   dq_cuda_bsdiff_search*   scan positions sharded by new-data range over the index replicated by peer copies;
+ *   dq_cuda_bsdiff_streams   both of the above, then the host loop.
+ * Smaller inputs run on devices[0] alone.  The same ordinal may be listed more than once (logical shards on one
+ * GPU: how a single-GPU box exercises the group paths). */
 int dq_cuda_create(dq_ctx **out, const int *devices, int ndev);
 int dq_cuda_destroy(dq_ctx *ctx);
 const char *dq_cuda_last_error(dq_ctx *ctx); /* ctx may be NULL: last error of a failed dq_cuda_create */
@@ -131,39 +140,13 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
 int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                         const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out);
 
-/* ---- multi-GPU suffix sort building blocks (DEVICE pointers; orchestrated by deltaq_b200/parallel.py) -------
- * One context per GPU sorts one key bucket; ISA is partitioned by text position and lives with the caller; the
- * exchanges between GPUs are torch.distributed collectives.  See DESIGN.md section 6.
- *  dist_pack      keys/vals of the suffixes starting in [pos_begin, pos_begin+pos_count), descending position
- *                 order.  d_slice points at text position pos_begin and must be readable (zero padded past the end
- *                 of the text) for pos_count + 16 bytes.  d_hist16 (65536 x uint64, may be NULL) is INCREMENTED by
- *                 the histogram of the keys' top 16 bits.
- *  dist_partition stable partition of (key, val) tuples by destination lut[key >> 48] (lut: 65536 bytes, values
- *                 < 256) into d_keys_out/d_vals_out; counts_out_host[256] = tuples per destination.
- *  dist_round0    stable sort of the bucket's tuples + first rank assignment.  slot_base = number of suffixes in
- *                 lower buckets.  Writes the resolved slots of d_sa_local[0..count), one (position, rank) update per
- *                 tuple (d_upd_pos as 64-bit, d_upd_rank; count entries) and *active_out = unresolved suffixes,
- *                 which stay inside the context.
- *  dist_requests  q[k] = sa[k] + h (64-bit) and idx[k] = k for the unresolved set (active entries each).
- *  dist_round     one doubling round over the unresolved set with caller-fetched second keys d_r2[k] =
- *                 ISA[sa[k]+h]+1 (0 past the end); outputs as dist_round0 (one update per entry of the round's input). */
-int dq_cuda_dist_pack(dq_ctx *ctx, const uint8_t *d_slice, int32_t pos_begin, int32_t pos_count, uint64_t *d_keys,
-                      uint32_t *d_vals, uint64_t *d_hist16);
-int dq_cuda_dist_partition(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, int32_t count,
-                           const uint8_t *d_lut, uint64_t *d_keys_out, uint32_t *d_vals_out, int64_t *counts_out_host);
-int dq_cuda_dist_round0(dq_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, int32_t count, int32_t n,
-                        int32_t slot_base, int32_t *d_sa_local, uint64_t *d_upd_pos, uint32_t *d_upd_rank,
-                        int32_t *active_out);
-int dq_cuda_dist_requests(dq_ctx *ctx, int64_t h, uint64_t *d_q, uint32_t *d_idx);
-int dq_cuda_dist_round(dq_ctx *ctx, const uint32_t *d_r2, int32_t n, int32_t slot_base, int32_t *d_sa_local,
-                       uint64_t *d_upd_pos, uint32_t *d_upd_rank, int32_t *active_out);
+/* ---- building blocks, exported for tests and reuse -------------------------------------------------- */
 /* Stable LSD radix sort of device-resident (uint64 key, uint32 value) pairs on key bits [bit_lo, bit_lo+nbits),
  * in place.  hist_out_host (may be NULL): 256 counters of the FIRST digit (bits [bit_lo, bit_lo+min(nbits,8))). */
 int dq_cuda_radix_sort_pairs_device(dq_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, int32_t count, int32_t bit_lo,
                                     int32_t nbits, int64_t *hist_out_host);
 
-/* ---- building block, exported for tests and reuse ----------------------------------------------------
- * Stable LSD radix sort of (uint64 key, uint32 value) pairs on key bits [0, key_bits), host pointers. */
+/* Stable LSD radix sort of (uint64 key, uint32 value) pairs on key bits [0, key_bits), host pointers. */
 int dq_cuda_radix_sort_pairs(dq_ctx *ctx, uint64_t *keys, uint32_t *vals, int32_t count, int32_t key_bits);
 
 #ifdef __cplusplus

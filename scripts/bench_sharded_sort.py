@@ -1,8 +1,9 @@
-"""Suffix sort of ONE text sharded over the ranks of a torchrun job (BASELINE configs #4/#5 shape).
+"""Suffix sort of ONE text by a device group (BASELINE configs #4/#5 shape), one process driving G GPUs.
 
-    python -m torch.distributed.run --nproc-per-node N scripts/bench_sharded_sort.py c4 512   # MiB
-Prints one JSON line on rank 0: input MB/s through deltaq_b200.parallel.suffix_sort_sharded (host text in,
-per-rank SA buckets out; H2D of the text included), max over ranks, plus an O(n) sufcheck of the gathered SA.
+    python scripts/bench_sharded_sort.py c4 512 [reps] [nocheck] [G list, e.g. 1,2,4,8] [pageable]
+Prints one JSON line per G: input MB/s through dq_cuda_suffix_sort of a group context (host text in, host SA out --
+pinned buffers unless `pageable`), best of `reps`, an O(n) sufcheck of the result, and (DQ_TRACE=1) the phase times
+the library prints to stderr.
 """
 import json
 import os
@@ -11,57 +12,44 @@ import time
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("DQ_SHARD_MIN", "1")
 import oracle  # noqa: E402
 from deltaq_b200 import CudaSuffixSort, workloads as w  # noqa: E402
-from deltaq_b200.parallel import suffix_sort_sharded  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "c4"
 mib = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 check = (sys.argv[4] != "nocheck") if len(sys.argv) > 4 else True
-rank = int(os.environ.get("RANK", "0"))
-local = int(os.environ.get("LOCAL_RANK", "0"))
-world = int(os.environ.get("WORLD_SIZE", "1"))
-torch.cuda.set_device(local)
-if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ndev = torch.cuda.device_count()
+gs = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [g for g in (1, 2, 4, 8) if g <= ndev]
+pageable = len(sys.argv) > 6 and sys.argv[6] == "pageable"
 n = mib << 20
 t = {"c4": lambda: w.c4_genome(n), "uniform": lambda: w.c1_uniform(n, 7), "c3": lambda: w.c3_repetitive(n),
      "c2": lambda: w.c2_exe_pair(n, n + 1)[0]}[kind]()
-sorter = CudaSuffixSort(device=local)
-pin = sorter.context.pinned(t.size, np.int32)   # SA (N=1) or this rank's bucket (N>1) lands in pinned memory
-times = []
-prof = {}
-for it in range(reps + 1):
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    if world > 1:
-        prof = {}
-        base, mine = suffix_sort_sharded(t, sorter, gather=False, profile=prof, out=pin.array)
+for G in gs:
+    devs = [i % ndev for i in range(G)]
+    sorter = CudaSuffixSort(device=devs if G > 1 else devs[0])
+    ctx = sorter.context
+    if pageable:
+        text, sa = t, np.empty(t.size, np.int32)
     else:
-        sorter.context.suffix_sort(t, pin.array)
-        mine = pin.array
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    if it > 0:
-        times.append(float(dt))
-ok = None
-if check:
-    sa = suffix_sort_sharded(t, sorter) if world > 1 else np.asarray(mine)
-    if rank == 0:
-        ok = int(oracle.sufcheck(t, sa))
-if rank == 0:
+        ptext = ctx.pinned(t.size, np.uint8)
+        ptext.array[:] = t
+        psa = ctx.pinned(t.size, np.int32)
+        text, sa = ptext.array, psa.array
+    times = []
+    for it in range(reps + 1):
+        t0 = time.perf_counter()
+        ctx.suffix_sort(text, sa)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+    st = ctx.stats()
+    ok = int(oracle.sufcheck(t, sa)) if check else None
     best = min(times)
-    print(json.dumps({"workload": kind, "n": int(t.size), "n_gpus": world, "best_ms": best * 1e3,
-                      "input_MBps": t.size / best / 1e6, "all_ms": [x * 1e3 for x in times], "sufcheck": ok,
-                      "phases_ms_rank0": {k: round(v * 1e3, 2) for k, v in prof.items() if k != "rounds"},
-                      "rounds": prof.get("rounds")}), flush=True)
-if world > 1:
-    dist.destroy_process_group()
+    print(json.dumps({"workload": kind, "n": int(t.size), "n_gpus": G, "devices": devs, "best_ms": best * 1e3,
+                      "input_MBps": t.size / best / 1e6, "all_ms": [round(x * 1e3, 2) for x in times], "sufcheck": ok,
+                      "rounds": st["rounds"], "launches": st["kernel_launches"], "pinned": not pageable}), flush=True)
+    sorter.dispose()

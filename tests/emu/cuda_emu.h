@@ -46,7 +46,7 @@ static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long lon
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaHostRegisterDefault = 0, cudaHostAllocDefault = 0, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
@@ -309,6 +309,8 @@ static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }

@@ -1,75 +1,72 @@
-"""N > 1 path: match search sharded by new-range over a replicated suffix array.
-World size 2 over gloo on the CPU (contexts = the logic emulator, tests/emu); the same code runs over NCCL with
-device pointers on GPUs (test_search_sharded_nccl, needs >= 2 GPUs: `gpurun --gpus 2 -- pytest -m gpu ...`)."""
+"""N > 1 paths: one text sorted by all shards of a device group, and the match search
+sharded by new-data range over the replicated index -- both inside the library (csrc/dq_group.inl, dq_dist.cuh),
+reached through the ordinary C-ABI entry points of a context created over several devices.
+
+CPU (`-m "not gpu"`): the logic emulator (tests/emu) with 2..8 logical shards.
+GPU (`-m gpu`): the real library; on a one-GPU box the shards are logical (the same ordinal listed several times),
+so every kernel and every exchange of the group path runs there too; with >= 2 GPUs (gpurun --gpus 2) the exchanges
+cross NVLink.  DQ_SHARD_MIN=1 makes small inputs take the sharded path."""
 import os
-import socket
 import sys
 
 import numpy as np
 import pytest
 
+import oracle
+from conftest import adversarial_texts, load_asset, random_bytes
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+def _sort_texts():
+    t = adversarial_texts()
+    out = {k: t[k] for k in ("zeros_tail", "all_zero_1000", "period8_zero_end", "fibonacci", "binary_random",
+                             "repeated_paragraph", "period3_tail0", "runs_mixed", "runs_long_zero_islands")}
+    out["fuzz3"] = load_asset("fuzz3")
+    out["crash-gosais"] = load_asset("crash-gosais-force-alloc")
+    out["random_20000"] = random_bytes(20000)
+    out["tiny_5"] = np.array([3, 1, 2, 1, 0], np.uint8)
+    out["two_equal"] = np.array([1, 1], np.uint8)
+    out["single"] = np.array([9], np.uint8)
+    out["empty"] = np.zeros(0, np.uint8)
+    return out
 
 
-def _pair():
+def _pairs():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from search_cases import structured_pairs
-    old, new = structured_pairs()["zero_runs_with_islands"]
-    return old, new
+    p = structured_pairs()
+    return {k: p[k] for k in ("zero_runs_with_islands", "point_edits", "periodic_records", "new_is_suffix_of_old",
+                              "empty_old")}
 
 
-def _worker(rank, world, port, backend, use_emu, q):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    import torch.distributed as dist
-    from deltaq_b200 import CudaSuffixSort
+@pytest.fixture()
+def shard_everything(monkeypatch):
+    monkeypatch.setenv("DQ_SHARD_MIN", "1")
+
+
+def _check_sort(sorter):
+    for name, t in _sort_texts().items():
+        sa = np.full(t.size + 1, -7, dtype=np.int32)
+        sorter.sort(t, sa[:t.size])
+        assert sa[t.size] == -7, name
+        assert np.array_equal(sa[:t.size], oracle.sais(t)), name
+
+
+def _check_search(sorter):
     from deltaq_b200.parallel import search_sharded
-    if backend == "nccl":
-        torch.cuda.set_device(rank)
-    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    if use_emu:
-        import emu
-        sorter = CudaSuffixSort(_lib=emu.library())
-    elif backend == "nccl":
-        sorter = CudaSuffixSort(device=rank)
-    else:
-        torch.cuda.set_device(0)            # both ranks share GPU 0
-        sorter = CudaSuffixSort(device=0)
-    old, new = _pair()
-    pos, ln = search_sharded(old, new, sorter)
-    q.put((rank, pos, ln))
-    dist.barrier()
-    dist.destroy_process_group()
-    sorter.dispose()
-
-
-def _run(world, backend, use_emu):
-    import torch.multiprocessing as mp
-    import oracle
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, use_emu, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    old, new = _pair()
-    I = oracle.make_I(oracle.sais(old))
-    rp, rl = oracle.search_all(I, old, new)
-    for rank, pos, ln in results:
-        assert np.array_equal(pos, rp) and np.array_equal(ln, rl), rank
+    for name, (old, new) in _pairs().items():
+        I = oracle.make_I(oracle.sais(old))
+        rp, rl = oracle.search_all(I, old, new)
+        pos, ln = search_sharded(old, new, sorter)             # group sort, then search over the replicated index
+        assert np.array_equal(pos, rp) and np.array_equal(ln, rl), name
+        pos, ln = search_sharded(old, new, sorter, I=I)        # caller-supplied suffix array
+        assert np.array_equal(pos, rp) and np.array_equal(ln, rl), name
+        b, c = new.size // 3, new.size // 2                    # a sub-range of scan positions
+        p3 = np.empty(c, np.int32)
+        l3 = np.empty(c, np.int32)
+        sorter.context.bsdiff_search(old, I, new, b, c, p3, l3)
+        assert np.array_equal(p3, rp[b:b + c]) and np.array_equal(l3, rl[b:b + c]), name
 
 
 def test_shard_bounds_cover_everything():
@@ -82,105 +79,83 @@ def test_shard_bounds_cover_everything():
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
 
 
-def test_search_sharded_gloo_world2():
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_group_sort_emulator(shard_everything, shards):
     import emu
-    emu.build()
-    _run(2, "gloo", True)
-
-
-@pytest.mark.gpu
-def test_search_sharded_nccl():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    _run(2, "nccl", False)
-
-
-# ---- one text sorted by several ranks (distributed prefix doubling) ---------------------------------------
-
-def _sort_texts():
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from conftest import adversarial_texts, load_asset, random_bytes
-    t = adversarial_texts()
-    out = {k: t[k] for k in ("zeros_tail", "all_zero_1000", "period8_zero_end", "fibonacci", "binary_random",
-                             "repeated_paragraph", "period3_tail0")}
-    out["fuzz3"] = load_asset("fuzz3")
-    out["crash-gosais"] = load_asset("crash-gosais-force-alloc")
-    out["random_20000"] = random_bytes(20000)
-    out["tiny_5"] = np.array([3, 1, 2, 1, 0], np.uint8)
-    out["single"] = np.array([9], np.uint8)
-    out["empty"] = np.zeros(0, np.uint8)
-    return out
-
-
-def _sort_worker(rank, world, port, backend, use_emu, q):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    import torch.distributed as dist
     from deltaq_b200 import CudaSuffixSort
-    from deltaq_b200.parallel import suffix_sort_sharded
-    if backend == "nccl":
-        torch.cuda.set_device(rank)
-    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    if use_emu:
-        import emu
-        sorter = CudaSuffixSort(_lib=emu.library())
-    elif backend == "nccl":
-        sorter = CudaSuffixSort(device=rank)
-    else:
-        torch.cuda.set_device(0)            # several ranks share GPU 0, collectives staged through gloo
-        sorter = CudaSuffixSort(device=0)
-    res = {}
-    for name, t in _sort_texts().items():
-        res[name] = suffix_sort_sharded(t, sorter)
-    q.put((rank, res))
-    dist.barrier()
-    dist.destroy_process_group()
-    sorter.dispose()
+    with CudaSuffixSort(device=[0] * shards, _lib=emu.library()) as sorter:
+        _check_sort(sorter)
 
 
-def _run_sort(world, backend, use_emu):
-    import torch.multiprocessing as mp
-    import oracle
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_sort_worker, args=(r, world, port, backend, use_emu, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    texts = _sort_texts()
-    for rank, res in results:
-        for name, t in texts.items():
-            assert np.array_equal(res[name], oracle.sais(t)), (rank, name)
-
-
-@pytest.mark.parametrize("world", [2, 3])
-def test_suffix_sort_sharded_gloo(world):
+def test_group_search_emulator(shard_everything):
     import emu
-    emu.build()
-    _run_sort(world, "gloo", True)
+    from deltaq_b200 import CudaSuffixSort
+    with CudaSuffixSort(device=[0, 0, 0], _lib=emu.library()) as sorter:
+        _check_search(sorter)
 
 
-@pytest.mark.gpu
-def test_suffix_sort_sharded_nccl():
+def test_small_inputs_stay_on_one_device():
+    """Below DQ_SHARD_MIN a group context behaves like a single-device one (BASELINE: single-GPU-sized inputs stay
+    on one GPU)."""
+    import emu
+    from deltaq_b200 import CudaSuffixSort
+    t = random_bytes(5000)
+    with CudaSuffixSort(device=[0, 0], _lib=emu.library()) as sorter:
+        sa = np.empty(t.size, np.int32)
+        sorter.sort(t, sa)
+        assert np.array_equal(sa, oracle.sais(t))
+        # the plain path keeps the index on shard 0: a search with I=None finds it
+        pos = np.empty(t.size, np.int32)
+        ln = np.empty(t.size, np.int32)
+        sorter.context.bsdiff_search(t, None, t, 0, t.size, pos, ln)
+        assert np.array_equal(ln, np.arange(t.size, 0, -1, dtype=np.int32))
+
+
+def test_too_many_devices_is_an_error():
+    import emu
+    from deltaq_b200 import CudaSuffixSort, _native
+    with pytest.raises(_native.NativeError) as ei:
+        CudaSuffixSort(device=[0] * 17, _lib=emu.library())
+    assert ei.value.status == _native.DQ_ERR_INVALID_ARGUMENT
+
+
+# ---- the real library ----------------------------------------------------------------------------------------
+
+def _devices(shards):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    _run_sort(2, "nccl", False)
+    k = torch.cuda.device_count()
+    return [i % k for i in range(shards)]
 
 
 @pytest.mark.gpu
-def test_suffix_sort_sharded_two_ranks_one_gpu():
-    """The multi-rank sort on a single GPU: two processes share cuda:0 (gloo moves the exchanged tuples through the
-    host), so the distributed kernels and the exchange logic run in every single-GPU `-m gpu` pass."""
-    _run_sort(2, "gloo", False)
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_group_sort_gpu(shard_everything, shards):
+    """Logical shards on a one-GPU box; real peers (NVLink) when the box has several GPUs."""
+    from deltaq_b200 import CudaSuffixSort
+    with CudaSuffixSort(device=_devices(shards)) as sorter:
+        _check_sort(sorter)
 
 
 @pytest.mark.gpu
-def test_search_sharded_two_ranks_one_gpu():
-    _run(2, "gloo", False)
+def test_group_search_gpu(shard_everything):
+    from deltaq_b200 import CudaSuffixSort
+    with CudaSuffixSort(device=_devices(3)) as sorter:
+        _check_search(sorter)
+
+
+@pytest.mark.gpu
+def test_group_sort_gpu_midsize(shard_everything):
+    """A few MiB per shard: many tiles per pass, several doubling rounds, exchanges of millions of entries."""
+    from deltaq_b200 import CudaSuffixSort
+    rng = np.random.default_rng(11)
+    texts = {
+        "acgt_6M": np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 6_000_000)],
+        "uniform_5M": rng.integers(0, 256, 5_000_001, dtype=np.uint8),
+        "repeats_4M": np.tile(rng.integers(0, 256, 70_001, dtype=np.uint8), 60)[:4_000_000],
+    }
+    with CudaSuffixSort(device=_devices(4)) as sorter:
+        for name, t in texts.items():
+            sa = np.empty(t.size, np.int32)
+            sorter.sort(t, sa)
+            assert oracle.sufcheck(t, sa) == 0, name
+            assert sorter.stats()["n"] == t.size
