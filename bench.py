@@ -11,10 +11,15 @@ One step = one pass of the hot path over one (old, new) pair:
            search, D2H of the (pos, len) table, and the reference's greedy scan/emit loop on the host,
            returning the uncompressed ctrl/diff/extra streams (everything of Diff.Create except bzip2).
 Unit: MB/s = 1e6 bytes of `new` per second; whole-job aggregate over ranks.
-N > 1: every rank diffs its own pair (independent objects, no data-path collective) -> weak scaling.
+N > 1: every rank diffs its own pair (independent objects, no data-path collective) -> weak scaling.  The same line
+then carries a `sharded` record: rank 0 alone drives ALL N GPUs through one device-group context (dq_cuda_create
+with ndev = N) -- BASELINE config #4 (512 MiB genome-like text, one suffix sort by N GPUs, sufcheck asserted in the
+run), the match search of a 256 MiB executable-like pair sharded by new-range (table asserted equal to the one-GPU
+table), and at N = 8 BASELINE config #5's 1.9 GiB text; the other ranks hold no GPU work meanwhile.
 
---impl reference times the CPU restatement of the reference's path (oracle/: SA-IS sort + Diff.Create's
-loop with its inline Search) on one host core, on a bounded sample of the same recipe.
+--impl reference times the CPU restatement of the reference's path (oracle/: the faster of its LibDivSufSort and
+SA-IS restatements + Diff.Create's loop with its inline Search) on one host core -- the reference is single-threaded --
+on the same C2 pair at full size.
 """
 import argparse
 import json
@@ -32,18 +37,20 @@ sys.path.insert(0, ROOT)
 METRIC = "bsdiff Diff.Create hot path (ISuffixSort.Sort + Diff.Search at every scan position) input MB/s"
 UNIT = "MB/s"
 WORKLOAD = "C2: synthetic 16 MiB -> 17 MiB executable-like pair, ~13% mutated regions (workloads.c2_exe_pair)"
-SAMPLE_OLD = 2 << 20
-SAMPLE_NEW = (2 << 20) + (1 << 17)
+NOMINAL_HBM_GBS = 8000.0   # BASELINE.json north_star: "~8 TB/s"; reported beside the measured peak
+MIB = 1 << 20
 
 
 def pass_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one round-0 onesweep launch from the committed ncu --set full
-    capture (profiles/r01_onesweep_pass_full_v2.md); per launch, like `achieved`."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_pass_traffic.json")) as f:
-            return float(json.load(f)["traffic_bytes_round0_launch"])
-    except Exception:
-        return None
+    capture (profiles/); per launch, like `achieved`."""
+    for name in ("r02_pass_traffic.json", "r01_pass_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["traffic_bytes_round0_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak():
@@ -103,17 +110,61 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ---- CPU arm ---------------------------------------------------------------------------------------------------
+
+def cpu_sorters():
+    """The reference's sorters as restated in oracle/ (name -> callable).  LibDivSufSort is the reference's default
+    (Defaults.cs:9); SA-IS is what its bsdiff tests use."""
+    import oracle
+    out = {"sais": oracle.sais}
+    if hasattr(oracle, "divsufsort"):
+        out["divsufsort"] = oracle.divsufsort
+    return out
+
+
+def cpu_step_times(old, new, reps):
+    """Seconds per sorter for the sort, and for the Diff.Create loop (inline Search), best of `reps`."""
+    import oracle
+    sort_s = {}
+    sa = None
+    for name, fn in cpu_sorters().items():
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            sa = fn(old)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        sort_s[name] = best
+    I = oracle.make_I(sa)
+    loop = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.bsdiff_streams(old, new, I)
+        dt = time.perf_counter() - t0
+        loop = dt if loop is None else min(loop, dt)
+    return sort_s, loop
+
+
 def run_reference(args, rank):
-    """CPU arm: the oracle's restatement of the reference's path, one core, bounded sample."""
+    """CPU arm: the oracle's restatement of the reference's path on the full C2 pair, one core."""
     if rank != 0:
         return
     import oracle
     from deltaq_b200 import workloads as w
     oracle.build()
-    old, new = w.c2_exe_pair(SAMPLE_OLD, SAMPLE_NEW)
+    old, new = w.c2_exe_pair()
+    sorters = cpu_sorters()
+    # the faster of the reference's sorters on this input carries the arm (one untimed probe each)
+    probe = {}
+    for name, fn in sorters.items():
+        t0 = time.perf_counter()
+        fn(old)
+        probe[name] = time.perf_counter() - t0
+    best = min(probe, key=probe.get)
+    sort = sorters[best]
 
     def step():
-        sa = oracle.sais(old)
+        sa = sort(old)
         oracle.bsdiff_streams(old, new, oracle.make_I(sa))
 
     for _ in range(args.warmup):
@@ -123,15 +174,17 @@ def run_reference(args, rank):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = new.size / dt / 1e6
-    sample = (f"C2 recipe at 1/8 scale ({old.size} -> {new.size} bytes); per step: SA-IS sort of old "
-              "(oracle/sais.c ~ SAIS.cs) + Diff.Create loop with inline Search (oracle/bsdiff.c ~ Diff.cs:92-298), "
-              "no bzip2; gcc -O2, single thread as the reference is single-threaded")
+    sample = (f"the full C2 pair ({old.size} -> {new.size} bytes); per step: suffix sort of old with the faster of the "
+              f"reference's sorters as restated in oracle/ ({best}; one probe each: "
+              + ", ".join(f"{k} {v_:.2f} s" for k, v_ in probe.items()) +
+              ") + Diff.Create loop with inline Search (oracle/bsdiff.c ~ Diff.cs:92-298), no bzip2; gcc -O2, "
+              "single thread as the reference is single-threaded")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "old_bytes": int(old.size), "new_bytes": int(new.size), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sorter": best, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -140,21 +193,159 @@ def cpu_baseline_once():
     import oracle
     from deltaq_b200 import workloads as w
     oracle.build()
-    old, new = w.c2_exe_pair(SAMPLE_OLD, SAMPLE_NEW)
-    t0 = time.perf_counter()
-    reps = 0
-    sort_s = 0.0
-    while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 6):
-        t1 = time.perf_counter()
-        sa = oracle.sais(old)
-        sort_s += time.perf_counter() - t1
-        oracle.bsdiff_streams(old, new, oracle.make_I(sa))
-        reps += 1
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": new.size / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-            "sort_only_MBps": old.size / (sort_s / reps) / 1e6,
-            "sample": f"C2 recipe at 1/8 scale ({old.size} -> {new.size} bytes), {reps} reps; oracle SA-IS sort + "
-                      "Diff.Create loop with inline Search, no bzip2, gcc -O2, 1 thread"}
+    old, new = w.c2_exe_pair()
+    sort_s, loop = cpu_step_times(old, new, 2)
+    best = min(sort_s, key=sort_s.get)
+    dt = sort_s[best] + loop
+    return {"value": new.size / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "sorter": best,
+            "sort_only_MBps": {k: old.size / v / 1e6 for k, v in sort_s.items()},
+            "loop_only_MBps": new.size / loop / 1e6,
+            "sample": f"the full C2 pair ({old.size} -> {new.size} bytes), best of 2 per part; oracle restatements of the "
+                      "reference's sorters + Diff.Create loop with inline Search, no bzip2, gcc -O2, 1 thread"}
+
+
+# ---- per-round roofline (north_star: fraction of HBM bandwidth per doubling round) ----------------------------------
+
+def round_records(acc_rounds, steps, peak):
+    out = []
+    for r, (ms, active, passes) in enumerate(acc_rounds):
+        ms /= steps
+        alg = active * ((41 if r == 0 else 52) + 24 * passes)
+        gbs = alg / (ms * 1e-3) / 1e9 if ms > 0 else None
+        out.append({"round": r, "active": active, "passes": passes, "ms": ms, "algorithmic_bytes": alg, "GBps": gbs,
+                    "frac_measured_peak": gbs / peak if gbs else None,
+                    "frac_nominal_8TBps": gbs / NOMINAL_HBM_GBS if gbs else None})
+    return out
+
+
+def sort_config_record(ctx, torch, text, name, peak, reps=3):
+    """Device-resident sort of one of BASELINE's other single-GPU configs: ms, MB/s, per-round roofline."""
+    n = int(text.size)
+    d_t = torch.from_numpy(text).cuda()
+    d_sa = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    ctx.set_timing(True)
+    best, rounds = None, None
+    for it in range(reps + 1):
+        ctx.suffix_sort_device(d_t.data_ptr(), n, d_sa.data_ptr())
+        st = ctx.stats()
+        if it and (best is None or st["device_ms"] < best):
+            best, rounds = st["device_ms"], ctx.round_times()
+    st = ctx.stats()
+    ctx.set_timing(False)
+    del d_t, d_sa
+    return {"config": name, "n": n, "device_ms": best, "input_MBps_device": n / (best * 1e-3) / 1e6,
+            "rounds": st["rounds"], "launches": st["kernel_launches"],
+            "algorithmic_GBps": st["algorithmic_bytes"] / (best * 1e-3) / 1e9,
+            "per_round": round_records(rounds, 1, peak)}
+
+
+# ---- one device group over all GPUs, driven by rank 0 (N > 1) ---------------------------------------------------------
+
+def sharded_record(devices, workers, lib=None, scale=1.0):
+    """`lib`/`scale`: the CPU tests run this function on the logic emulator with tiny inputs."""
+    import oracle
+    from deltaq_b200 import CudaSuffixSort, workloads as w
+    G = len(devices)
+    rec = {"devices": devices,
+           "what": "ONE context over all GPUs (dq_cuda_create, ndev = N) in rank 0's process; host buffers (pinned) in and "
+                   "out through the ordinary C ABI calls; MB/s = 1e6 input bytes / wall second"}
+
+    def timed(fn, reps=2):
+        fn()
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best
+
+    one = CudaSuffixSort(device=devices[0], _lib=lib)
+    grp = CudaSuffixSort(device=devices, _lib=lib)
+    try:
+        # -- BASELINE config #4: 512 MiB genome-like text, one suffix sort
+        t = w.c4_genome(max(64, int(512 * MIB * scale)))
+        n = int(t.size)
+        p_t = grp.context.pinned(n, np.uint8)
+        p_t.array[:] = t
+        p_sa = grp.context.pinned(n, np.int32)
+        dt_g = timed(lambda: grp.context.suffix_sort(p_t.array, p_sa.array))
+        st = grp.stats()
+        bad = int(oracle.sufcheck(t, p_sa.array))
+        assert bad == 0, f"sharded C4 suffix array fails sufcheck ({bad})"
+        dt_1 = timed(lambda: one.context.suffix_sort(p_t.array, p_sa.array))
+        rec["sort_c4"] = {"config": "C4: 512 MiB iid {A,C,G,T} + 1 % tandem repeats (workloads.c4_genome)", "n": n,
+                          "ms": dt_g * 1e3, "input_MBps": n / dt_g / 1e6, "rounds": st["rounds"],
+                          "launches": st["kernel_launches"], "sufcheck": bad,
+                          "one_gpu_ms": dt_1 * 1e3, "one_gpu_input_MBps": n / dt_1 / 1e6,
+                          "speedup_vs_one_gpu": dt_1 / dt_g, "strong_scaling_efficiency": dt_1 / dt_g / G}
+        p_t.free()
+        p_sa.free()
+        del t
+
+        # -- match search sharded by new-range: 256 MiB executable-like pair (C5's recipe at 1/8 scale)
+        old, new = w.c5_pair(max(4096, int(256 * MIB * scale)), workers=workers)
+        n, m = int(old.size), int(new.size)
+        p_o = grp.context.pinned(n, np.uint8)
+        p_o.array[:] = old
+        p_n = grp.context.pinned(m, np.uint8)
+        p_n.array[:] = new
+        p_sa = grp.context.pinned(n, np.int32)
+        pos_g = grp.context.pinned(m, np.int32)
+        len_g = grp.context.pinned(m, np.int32)
+        pos_1 = grp.context.pinned(m, np.int32)
+        len_1 = grp.context.pinned(m, np.int32)
+
+        def both(c, pos, ln):
+            c.suffix_sort(p_o.array, p_sa.array)
+            c.bsdiff_search(p_o.array, None, p_n.array, 0, m, pos.array, ln.array)
+
+        dt_g = timed(lambda: both(grp.context, pos_g, len_g), reps=1)
+        sg = grp.stats()
+        dt_1 = timed(lambda: both(one.context, pos_1, len_1), reps=1)
+        s1 = one.stats()
+        same = bool(np.array_equal(pos_g.array, pos_1.array) and np.array_equal(len_g.array, len_1.array))
+        assert same, "sharded search table differs from the one-GPU table"
+        rec["sort_search_256MiB"] = {
+            "config": "C5 recipe at 1/8 scale: 256 MiB executable-like old -> 272 MiB new (workloads.c5_pair); sort(old) "
+                      "by all GPUs + Diff.Search at every scan position sharded by new-range",
+            "old_bytes": n, "new_bytes": m, "ms": dt_g * 1e3, "input_MBps": m / dt_g / 1e6,
+            "search_device_ms": sg["search_ms"], "one_gpu_ms": dt_1 * 1e3, "one_gpu_input_MBps": m / dt_1 / 1e6,
+            "one_gpu_search_device_ms": s1["search_ms"], "speedup_vs_one_gpu": dt_1 / dt_g,
+            "table_equals_one_gpu_table": same}
+        for p in (p_o, p_n, p_sa, pos_g, len_g, pos_1, len_1):
+            p.free()
+        del old, new
+
+        # -- BASELINE config #5's text (near the int32 suffix-array limit) over 8 GPUs
+        if G >= 8:
+            t = w.c5_old(max(4096, int(2_040_109_466 * scale)), workers=workers)
+            n = int(t.size)
+            p_t = grp.context.pinned(n, np.uint8)
+            p_t.array[:] = t
+            p_sa = grp.context.pinned(n, np.int32)
+            dt_g = timed(lambda: grp.context.suffix_sort(p_t.array, p_sa.array), reps=1)
+            st = grp.stats()
+            sa_g = np.array(p_sa.array, copy=True)
+            dt_1 = timed(lambda: one.context.suffix_sort(p_t.array, p_sa.array), reps=1)
+            same = bool(np.array_equal(sa_g, p_sa.array))
+            # a full sufcheck of 2 G suffixes takes minutes on one core (tests/ runs it at this size): here the result
+            # is compared with the one-GPU path's (different code: run-aware rounds, no exchanges) and sampled
+            idx = np.sort(np.random.default_rng(0).integers(0, max(1, n - 1), min(n, 200_000)))
+            sample_bad = int(oracle.verify_pairs(t, sa_g, idx))
+            assert same, "sharded C5 suffix array differs from the one-GPU suffix array"
+            assert sample_bad == 0, "sharded C5 suffix array has adjacent suffixes out of order"
+            rec["sort_c5"] = {"config": "C5 text: 2,040,109,466 B executable-like (workloads.c5_old)", "n": n,
+                              "ms": dt_g * 1e3, "input_MBps": n / dt_g / 1e6, "rounds": st["rounds"],
+                              "one_gpu_ms": dt_1 * 1e3, "one_gpu_input_MBps": n / dt_1 / 1e6,
+                              "speedup_vs_one_gpu": dt_1 / dt_g, "equals_one_gpu_suffix_array": same,
+                              "sampled_adjacent_pairs_out_of_order": sample_bad}
+    except Exception as e:  # the record reports, the bench line survives
+        rec["error"] = f"{type(e).__name__}: {e}"
+    finally:
+        one.dispose()
+        grp.dispose()
+    return rec
 
 
 def main():
@@ -164,6 +355,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="deltaq_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs / the sharded record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -182,8 +374,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: deltaq_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")   # host-side waits that keep the GPUs free
 
     def barrier():
         if world > 1:
@@ -205,10 +399,16 @@ def main():
     torch.cuda.synchronize()
 
     acc = {"launches": 0, "device_ms": 0.0, "pass_ms": 0.0, "pass_pairs": 0, "search_ms": 0.0, "passes": 0,
-           "rounds": 0, "alg_bytes": 0}
+           "rounds": 0, "alg_bytes": 0, "round_times": None}
 
     def step_device(record):
         ctx.suffix_sort_device(d_old.data_ptr(), n, d_sa.data_ptr())
+        if record:
+            rt = ctx.round_times()
+            if acc["round_times"] is None:
+                acc["round_times"] = [[0.0, a, p] for _, a, p in rt]
+            for slot, (ms, _, _) in zip(acc["round_times"], rt):
+                slot[0] += ms
         ctx.bsdiff_search_device(d_old.data_ptr(), n, None, d_new.data_ptr(), m, 0, m, d_pos.data_ptr(), d_len.data_ptr())
         if record:
             st = ctx.stats()
@@ -250,21 +450,57 @@ def main():
     barrier()
     dt_e2e = time.perf_counter() - t1
     e2e_stats = ctx.stats()
+    stream_sizes = [len(streams["ctrl"]), len(streams["diff"]), len(streams["extra"])]
+    streams = None
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device arm + e2e arm)
+
+    # the same call with ordinary (pageable) numpy buffers: what a managed caller's `fixed` spans are (Diff.cs:78,90)
+    for _ in range(2):
+        ctx.bsdiff_streams(old, new, copy=False)
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.bsdiff_streams(old, new, copy=False)
+    barrier()
+    dt_pageable = time.perf_counter() - t2
 
     # max over ranks
     if world > 1:
-        tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dt, dt_e2e, dt_pageable], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(tt[0]), float(tt[1])
+        dt, dt_e2e, dt_pageable = float(tt[0]), float(tt[1]), float(tt[2])
+
+    peak, peak_src = measured_peak()
+    extras = None
+    sharded = None
+    if not args.no_extras:
+        if world == 1:
+            # BASELINE's other single-GPU configs, device-resident sort only (bounded: a few hundred ms in all)
+            extras = [sort_config_record(ctx, torch, w.c1_uniform(), "C1: 1 MiB uniform random bytes", peak, reps=5),
+                      sort_config_record(ctx, torch, w.c3_repetitive(), "C3: 64 MiB repetitive text", peak, reps=2),
+                      sort_config_record(ctx, torch, w.c4_genome(64 * MIB), "C4 recipe, 64 MiB slice", peak, reps=2)]
+        else:
+            # free this rank's GPU memory, then rank 0 drives all GPUs; the others wait on the host
+            del d_old, d_new, d_sa, d_pos, d_len
+            p_old.free()
+            p_new.free()
+            sorter.dispose()
+            sorter = None
+            torch.cuda.empty_cache()
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)
+            if rank == 0:
+                os.environ["DQ_SHARD_MIN"] = str(32 * MIB)
+                sharded = sharded_record(list(range(world)), workers=min(8, max(1, (os.cpu_count() or 8) // 2)))
+            dist.barrier(group=host_group)
 
     if rank == 0:
         ms_step = dt / args.steps * 1e3
         value = world * m / (dt / args.steps) / 1e6
         e2e_value = world * m / (dt_e2e / args.steps) / 1e6
-        peak, peak_src = measured_peak()
         pass_gbs = acc["pass_pairs"] * 24 / (acc["pass_ms"] * 1e-3) / 1e9 if acc["pass_ms"] > 0 else None
         cpu = None if args.no_cpu_baseline else cpu_baseline_once()
+        sort_ms = acc["device_ms"] / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -280,25 +516,37 @@ def main():
                     "includes": "H2D old+new, sort, search, D2H of the coded (pos,len) table in slices, host greedy "
                                 "scan/extend/emit loop on host threads overlapped with the slices; result = "
                                 "context-owned ctrl/diff/extra buffers; streams "
-                                f"ctrl/diff/extra = {len(streams['ctrl'])}/{len(streams['diff'])}/{len(streams['extra'])} B"},
+                                f"ctrl/diff/extra = {stream_sizes[0]}/{stream_sizes[1]}/{stream_sizes[2]} B",
+                    "pageable_buffers": {"value": world * m / (dt_pageable / args.steps) / 1e6, "unit": UNIT,
+                                         "ms_per_step": dt_pageable / args.steps * 1e3,
+                                         "note": "the same call with ordinary numpy (pageable) old/new buffers"}},
             "gpu_launches": acc["launches"],
             "roofline": {"bound": "hbm", "kernel": "dq::radix::onesweep_pass_kernel",
                          "achieved": pass_gbs, "peak": peak, "unit": "GB/s",
                          "frac": (pass_gbs / peak) if pass_gbs else None, "peak_source": peak_src,
+                         "frac_nominal_8TBps": (pass_gbs / NOMINAL_HBM_GBS) if pass_gbs else None,
                          "algorithmic_bytes_per_pair": 24, "launches_timed": acc["passes"],
                          "share_of_device_time": acc["pass_ms"] / (acc["device_ms"] + acc["search_ms"])
                          if acc["device_ms"] else None,
                          "traffic": pass_traffic(),
                          "traffic_note": "ncu capture of a round-0 launch (16,777,216 pairs, 402,653,184 algorithmic B); "
-                                         "achieved averages all launches of the step (round 0 and the smaller doubling rounds)"},
-            "device_ms_per_step": {"sort": acc["device_ms"] / args.steps, "search": acc["search_ms"] / args.steps},
+                                         "achieved averages all launches of the step (round 0 and the smaller doubling rounds)",
+                         "per_round": round_records(acc["round_times"] or [], args.steps, peak),
+                         "per_round_note": "north_star's yardstick: SURVEY 8(d) algorithmic bytes of the round / CUDA-event "
+                                           "time from the round's first launch to the next round's (all kernels of the "
+                                           "round, not only the radix passes)"},
+            "device_ms_per_step": {"sort": sort_ms, "search": acc["search_ms"] / args.steps},
             "sort": {"rounds": acc["rounds"], "algorithmic_bytes": acc["alg_bytes"],
-                     "input_MBps_device": n / (acc["device_ms"] / args.steps * 1e-3) / 1e6 if acc["device_ms"] else None,
-                     "algorithmic_GBps": acc["alg_bytes"] / (acc["device_ms"] / args.steps * 1e-3) / 1e9
-                     if acc["device_ms"] else None},
+                     "input_MBps_device": n / (sort_ms * 1e-3) / 1e6 if sort_ms else None,
+                     "algorithmic_GBps": acc["alg_bytes"] / (sort_ms * 1e-3) / 1e9 if sort_ms else None,
+                     "algorithmic_frac_measured_peak": acc["alg_bytes"] / (sort_ms * 1e-3) / 1e9 / peak if sort_ms else None},
             "clocks": clocks,
             "cpu_baseline": cpu,
         }
+        if extras is not None:
+            line["other_configs"] = extras
+        if sharded is not None:
+            line["sharded"] = sharded
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

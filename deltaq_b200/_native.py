@@ -18,6 +18,7 @@ DQ_ERR_OUT_OF_MEMORY = -2
 DQ_ERR_CUDA = -3
 DQ_ERR_NO_DEVICE = -4
 DQ_ERR_INTERNAL = -5
+DQ_ERR_CORRUPT_PATCH = -6
 
 
 class DqStats(ctypes.Structure):
@@ -47,9 +48,10 @@ class NativeError(RuntimeError):
 
 EXPORTS = [
     "dq_cuda_create", "dq_cuda_destroy", "dq_cuda_last_error", "dq_cuda_get_stats", "dq_cuda_set_timing",
-    "dq_cuda_get_pass_times",
+    "dq_cuda_get_pass_times", "dq_cuda_get_round_times",
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
     "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
+    "dq_cuda_patch_apply",
     "dq_cuda_radix_sort_pairs", "dq_cuda_radix_sort_pairs_device",
 ]
 
@@ -72,6 +74,7 @@ class Library:
         L.dq_cuda_get_stats.argtypes = [vp, ctypes.POINTER(DqStats)]
         L.dq_cuda_set_timing.argtypes = [vp, ctypes.c_int]
         L.dq_cuda_get_pass_times.argtypes = [vp, vp, vp, vp, ctypes.c_int]
+        L.dq_cuda_get_round_times.argtypes = [vp, vp, vp, vp, ctypes.c_int]
         L.dq_cuda_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         L.dq_cuda_host_free.argtypes = [vp]
         L.dq_cuda_suffix_sort.argtypes = [vp, vp, i32, vp]
@@ -80,6 +83,7 @@ class Library:
         L.dq_cuda_bsdiff_search_device.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
         L.dq_cuda_bsdiff_streams.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_greedy_emit.argtypes = [vp, vp, i32, vp, i32, vp, vp, ctypes.POINTER(DqDiffStreams)]
+        L.dq_cuda_patch_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64]
         L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
         L.dq_cuda_radix_sort_pairs_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         for name in EXPORTS:
@@ -102,6 +106,24 @@ def _addr(a):
     if a is None:
         return None
     return ctypes.c_void_p(a.ctypes.data) if a.size else ctypes.c_void_p(0)
+
+
+def patch_apply(old, ctrl, diff, extra, new_size, lib=None):
+    """dq_cuda_patch_apply: Patch.ApplyInternal on uncompressed streams -> bytes of the new file (numpy uint8).
+    Raises RuntimeError("Corrupt patch") where the reference throws InvalidOperationException."""
+    lib = lib or default_library()
+    o, c, d, e = (np.ascontiguousarray(np.frombuffer(x, dtype=np.uint8) if not isinstance(x, np.ndarray) else x)
+                  for x in (old, ctrl, diff, extra))
+    if new_size < 0:
+        raise RuntimeError("Corrupt patch")
+    out = np.empty(int(new_size), dtype=np.uint8)
+    rc = lib.L.dq_cuda_patch_apply(_addr(o), o.size, _addr(c), c.size, _addr(d), d.size, _addr(e), e.size, _addr(out),
+                                   int(new_size))
+    if rc == DQ_ERR_CORRUPT_PATCH:
+        raise RuntimeError("Corrupt patch")
+    if rc != DQ_OK:
+        raise NativeError(rc, "dq_cuda_patch_apply: bad arguments")
+    return out
 
 
 class PinnedArray:
@@ -187,6 +209,18 @@ class Context:
             self._check(n)
         n = min(n, cap)
         return [(float(ms[i]), int(pairs[i]), int(shift[i])) for i in range(n)]
+
+    def round_times(self):
+        """[(ms, active, passes)] of every doubling round of the last single-device sort (timing must be on)."""
+        cap = 256
+        ms = np.zeros(cap, dtype=np.float32)
+        active = np.zeros(cap, dtype=np.int64)
+        passes = np.zeros(cap, dtype=np.int32)
+        n = self.lib.L.dq_cuda_get_round_times(self._h, _addr(ms), _addr(active), _addr(passes), cap)
+        if n < 0:
+            self._check(n)
+        n = min(n, cap)
+        return [(float(ms[i]), int(active[i]), int(passes[i])) for i in range(n)]
 
     def set_timing(self, on):
         self._check(self.lib.L.dq_cuda_set_timing(self._h, 1 if on else 0))

@@ -19,6 +19,7 @@ import io
 
 import numpy as np
 
+from . import _native
 from .suffix_sort import CudaSuffixSort, as_bytes_array
 
 HEADER_SIZE = 32                      # Constants.cs:7
@@ -156,28 +157,8 @@ class Patch:
             output.flush()
 
 
-def apply_streams(old, ctrl, diff, extra, new_size):
-    """Patch.ApplyInternal (Patch.cs:95-168) on uncompressed streams."""
+def apply_streams(old, ctrl, diff, extra, new_size, lib=None):
+    """Patch.ApplyInternal (Patch.cs:95-168) on uncompressed streams: the native add loop (dq_cuda_patch_apply).
+    Returns the bytes of the new file; raises RuntimeError("Corrupt patch") like the reference."""
     o = as_bytes_array(old, "input")
-    d = np.frombuffer(diff, dtype=np.uint8)
-    out = io.BytesIO()
-    old_pos = cp = dp = ep = 0
-    while out.tell() < new_size:
-        add = read_packed_long(ctrl[cp:cp + 8])
-        copy = read_packed_long(ctrl[cp + 8:cp + 16])
-        seek = read_packed_long(ctrl[cp + 16:cp + 24])
-        cp += 24
-        if out.tell() + add > new_size:
-            raise RuntimeError("Corrupt patch")
-        seg_old = o[old_pos:old_pos + add]
-        if seg_old.size != add or dp + add > d.size:
-            raise RuntimeError("Corrupt patch")
-        out.write((d[dp:dp + add] + seg_old).astype(np.uint8).tobytes())
-        dp += add
-        old_pos += add
-        if out.tell() + copy > new_size:
-            raise RuntimeError("Corrupt patch")
-        out.write(extra[ep:ep + copy])
-        ep += copy
-        old_pos += seek
-    return out.getvalue()
+    return _native.patch_apply(o, ctrl, diff, extra, new_size, lib=lib).tobytes()

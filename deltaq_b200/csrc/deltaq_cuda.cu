@@ -19,6 +19,7 @@
 #include "dq_search.cuh"
 #include "dq_dist.cuh"
 #include "dq_diff_host.h"
+#include "dq_patch_host.h"
 
 namespace {
 
@@ -40,6 +41,14 @@ struct EventPair {
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
+};
+
+// one doubling round of the last sort (timing on): event at its start, what entered it, how many radix passes
+struct RoundRec {
+    cudaEvent_t begin;
+    uint64_t active;
+    int passes;
+    float ms;
 };
 
 struct Group;  // dq_group.inl: the shards of a context created with ndev > 1
@@ -65,6 +74,8 @@ struct dq_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<EventPair> pass_events;
     size_t pass_events_used = 0;
+    std::vector<RoundRec> round_recs;
+    size_t rounds_used = 0;
 
     // search state (device)
     DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
@@ -219,6 +230,23 @@ int run_passes(dq_ctx *ctx, SortBufs &s, uint32_t count, const rx::PassPlan &pla
     return DQ_OK;
 }
 
+// timing on: the round that starts now (active suffixes entering it, radix passes it will run)
+int mark_round(dq_ctx *ctx, uint64_t active, int passes)
+{
+    if (!ctx->timing) return DQ_OK;
+    if (ctx->rounds_used == ctx->round_recs.size()) {
+        RoundRec r{};
+        DQ_CK(ctx, cudaEventCreate(&r.begin));
+        ctx->round_recs.push_back(r);
+    }
+    RoundRec &r = ctx->round_recs[ctx->rounds_used++];
+    r.active = active;
+    r.passes = passes;
+    r.ms = 0.f;
+    DQ_CK(ctx, cudaEventRecord(r.begin, ctx->stream));
+    return DQ_OK;
+}
+
 int zero_hist(dq_ctx *ctx)
 {
     DQ_TRY(ensure(ctx, ctx->hist, (size_t)2 * rx::kMaxPasses * rx::kRadix * 4 + 256));
@@ -307,6 +335,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     st = dq_stats{};
     st.n = (int32_t)n;
     ctx->pass_events_used = 0;
+    ctx->rounds_used = 0;
     ctx->lcp_valid = false;
     ctx->pre3_valid = false;
     ctx->runend_valid_n = -1;
@@ -345,6 +374,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     // ---- round 0: all suffixes by their first 8 bytes
     rx::PassPlan plan{};
     rx::plan_add_field(plan, 0, 64);
+    DQ_TRY(mark_round(ctx, n, plan.npass));
     DQ_TRY(zero_hist(ctx));
     // counter of suffixes inside equal-byte runs, kept behind the histogram tables
     uint32_t *uniform_count = ctx->hist.as<uint32_t>() + 2 * rx::kMaxPasses * rx::kRadix + 32;
@@ -408,6 +438,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         rx::PassPlan rp{};
         rx::plan_add_field(rp, 0, (first && run_aware) ? 32 : bits_r2);
         rx::plan_add_field(rp, 32, bits_rank);
+        DQ_TRY(mark_round(ctx, a, rp.npass));
         DQ_TRY(zero_hist(ctx));
         if (first && run_aware) {
             auto k = sx::build_keys_round1_kernel;
@@ -472,6 +503,9 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         }
         st.pass_ms = tot;
         st.pass_pairs = (int64_t)pairs;
+        for (size_t i = 0; i < ctx->rounds_used; ++i)
+            DQ_CK(ctx, cudaEventElapsedTime(&ctx->round_recs[i].ms, ctx->round_recs[i].begin,
+                                            i + 1 < ctx->rounds_used ? ctx->round_recs[i + 1].begin : ctx->ev1));
     }
     return DQ_OK;
 }
@@ -529,6 +563,7 @@ int destroy_single(dq_ctx *ctx)
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    for (auto &r : ctx->round_recs) cudaEventDestroy(r.begin);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     if (ctx->h_pos.p) cudaFreeHost(ctx->h_pos.p);
     if (ctx->h_len.p) cudaFreeHost(ctx->h_len.p);
@@ -681,6 +716,19 @@ int dq_cuda_get_pass_times(dq_ctx *ctx, float *ms, int64_t *pairs, int32_t *shif
         if (ms) ms[i] = ctx->pass_events[i].ms;
         if (pairs) pairs[i] = (int64_t)ctx->pass_events[i].pairs;
         if (shift) shift[i] = ctx->pass_events[i].shift;
+    }
+    return n;
+}
+
+int dq_cuda_get_round_times(dq_ctx *ctx, float *ms, int64_t *active, int32_t *passes, int cap)
+{
+    if (!ctx || cap < 0) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const int n = (int)ctx->rounds_used;
+    for (int i = 0; i < n && i < cap; ++i) {
+        if (ms) ms[i] = ctx->round_recs[i].ms;
+        if (active) active[i] = (int64_t)ctx->round_recs[i].active;
+        if (passes) passes[i] = ctx->round_recs[i].passes;
     }
     return n;
 }
@@ -911,6 +959,17 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     }
     export_streams(ctx, out);
     return DQ_OK;
+}
+
+int dq_cuda_patch_apply(const uint8_t *old_, int64_t n, const uint8_t *ctrl, int64_t ctrl_len, const uint8_t *diff,
+                        int64_t diff_len, const uint8_t *extra, int64_t extra_len, uint8_t *out, int64_t new_size)
+{
+    if (n < 0 || ctrl_len < 0 || diff_len < 0 || extra_len < 0 || new_size < 0) return DQ_ERR_INVALID_ARGUMENT;
+    if ((n && !old_) || (ctrl_len && !ctrl) || (diff_len && !diff) || (extra_len && !extra) || (new_size && !out))
+        return DQ_ERR_INVALID_ARGUMENT;
+    return dq::patchhost::apply_streams(old_, n, ctrl, ctrl_len, diff, diff_len, extra, extra_len, out, new_size) == 0
+               ? DQ_OK
+               : DQ_ERR_CORRUPT_PATCH;
 }
 
 int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,

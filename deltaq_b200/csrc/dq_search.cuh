@@ -708,11 +708,32 @@ __device__ __forceinline__ Carry reference_result(const Texts &t, const Index &i
 
 // ---- kernels ---------------------------------------------------------------------------------------------
 
+// ISA[SA[r]] = r for a suffix array that came from the caller (any ISuffixSort provider, Diff.cs:90): nothing about
+// it is trusted.  ISA starts as all kUnset; entries outside [0, n) are counted in *bad instead of being followed, and
+// check_inverse_kernel counts the positions no entry named -- n values in n slots, so a duplicate leaves a gap.
+constexpr uint32_t kUnset = 0xffffffffu;
+
 __global__ void __launch_bounds__(256) invert_sa_kernel(const int32_t *__restrict__ SA, uint32_t n,
-                                                         uint32_t *__restrict__ ISA)
+                                                         uint32_t *__restrict__ ISA, uint32_t *__restrict__ bad)
 {
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
-        ISA[SA[r]] = (uint32_t)r;
+    uint32_t wrong = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)SA[r];
+        if (p < n)
+            ISA[p] = (uint32_t)r;
+        else
+            ++wrong;
+    }
+    if (wrong) atomicAdd(bad, wrong);
+}
+
+__global__ void __launch_bounds__(256) check_inverse_kernel(const uint32_t *__restrict__ ISA, uint32_t n,
+                                                             uint32_t *__restrict__ bad)
+{
+    uint32_t wrong = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        wrong += ISA[i] == kUnset ? 1u : 0u;
+    if (wrong) atomicAdd(bad, wrong);
 }
 
 // 2-byte bucket bounds of the suffix array.  Suffix p has the 17-bit key 2*pair+1 (pair = T[p]<<8 | T[p+1]),

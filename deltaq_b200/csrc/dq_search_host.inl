@@ -274,12 +274,26 @@ int adopt_index(dq_ctx *ctx, const uint8_t *old_, uint32_t n, const int32_t *I, 
     DQ_TRY(ensure(ctx, ctx->sa, (size_t)n * 4));
     DQ_TRY(ensure(ctx, ctx->isa, (size_t)n * 4));
     if (n) {
+        // the caller's array is checked before anything follows its entries: it must be a permutation of [0, n)
+        DQ_TRY(ensure(ctx, ctx->d_headcount, 256));
+        uint32_t *bad = ctx->d_headcount.as<uint32_t>() + 8;
+        DQ_CK(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
+        DQ_CK(ctx, cudaMemsetAsync(ctx->isa.p, 0xff, (size_t)n * 4, ctx->stream));
         DQ_CK(ctx, cudaMemcpyAsync(ctx->sa.p, I, (size_t)n * 4, kind, ctx->stream));
-        auto k = sr::invert_sa_kernel;
         const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n, 256), (uint64_t)ctx->sm_count * 16));
-        DQ_LAUNCH(k, g, 256, 0, ctx->stream, ctx->sa.as<int32_t>(), n, ctx->isa.as<uint32_t>());
-        ctx->stats.kernel_launches++;
+        auto k = sr::invert_sa_kernel;
+        DQ_LAUNCH(k, g, 256, 0, ctx->stream, ctx->sa.as<int32_t>(), n, ctx->isa.as<uint32_t>(), bad);
+        auto kc = sr::check_inverse_kernel;
+        DQ_LAUNCH(kc, g, 256, 0, ctx->stream, ctx->isa.as<uint32_t>(), n, bad);
+        ctx->stats.kernel_launches += 2;
         DQ_CK(ctx, cudaGetLastError());
+        DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count + 8, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_count[8] != 0) {
+            ctx->err = "bsdiff_search: the suffix array passed as I is not a permutation of [0, n) (" +
+                       std::to_string(ctx->h_count[8]) + " entries out of range or positions never named)";
+            return DQ_ERR_INVALID_ARGUMENT;
+        }
     }
     ctx->resident_n = (int32_t)n;
     return DQ_OK;

@@ -128,8 +128,32 @@ def c4_genome(n=512 * MIB, seed=4):
     return text
 
 
-def c5_pair(n_old=2_040_109_466, seed=5):
-    """C5: C2's generator scaled to ~1.9 GiB (near the int32 suffix-array limit)."""
-    old = _exe_like(n_old, np.random.default_rng(seed))
+C5_PIECES = 8
+
+
+def _c5_piece(args):
+    n, seed, i = args
+    return _exe_like(n, np.random.default_rng([seed, i]))
+
+
+def c5_old(n_old=2_040_109_466, seed=5, workers=1):
+    """C5's old file: C2's generator scaled to ~1.9 GiB (near the int32 suffix-array limit), built as C5_PIECES
+    independently seeded stretches of sections so that `workers` processes can generate it side by side (the bytes do
+    not depend on `workers`)."""
+    sizes = [n_old // C5_PIECES + (1 if i < n_old % C5_PIECES else 0) for i in range(C5_PIECES)]
+    jobs = [(sz, seed, i) for i, sz in enumerate(sizes)]
+    if workers > 1:
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
+            parts = list(ex.map(_c5_piece, jobs))
+    else:
+        parts = [_c5_piece(j) for j in jobs]
+    return np.concatenate(parts)
+
+
+def c5_pair(n_old=2_040_109_466, seed=5, workers=1):
+    """C5: (old, new) with new = old mutated like C2's pair, ~6 % longer."""
+    old = c5_old(n_old, seed, workers)
     new = _mutate(old, np.random.default_rng(seed + 100), n_old + n_old // 16, regions=2000)
     return old, new

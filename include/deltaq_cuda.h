@@ -33,7 +33,8 @@ enum {
     DQ_ERR_OUT_OF_MEMORY = -2,    /* maps to OutOfMemoryException */
     DQ_ERR_CUDA = -3,             /* maps to InvalidOperationException(dq_cuda_last_error) */
     DQ_ERR_NO_DEVICE = -4,        /* no CUDA device: there is NO CPU fallback */
-    DQ_ERR_INTERNAL = -5
+    DQ_ERR_INTERNAL = -5,
+    DQ_ERR_CORRUPT_PATCH = -6     /* maps to InvalidOperationException("Corrupt patch"), Patch.cs:68-70,128,151 */
 };
 
 /* Per-call statistics of the most recent dq_cuda_suffix_sort* / dq_cuda_bsdiff_search* on the context. */
@@ -88,6 +89,12 @@ int dq_cuda_set_timing(dq_ctx *ctx, int on);
  * entries of ms[] / pairs[] / shift[] in launch order and returns the number of launches (or a negative status). */
 int dq_cuda_get_pass_times(dq_ctx *ctx, float *ms, int64_t *pairs, int32_t *shift, int cap);
 
+/* Per-round CUDA-event times of the last single-device sort (timing must be on), round 0 first: ms[] from the start
+ * of the round to the start of the next (or the end of the sort), active[] = suffixes entering the round, passes[] =
+ * radix passes it ran.  SURVEY.md section 8(d) algorithmic bytes of a round: active * (41 + 24 * passes) for round 0,
+ * active * (52 + 24 * passes) after.  Returns the number of rounds (or a negative status). */
+int dq_cuda_get_round_times(dq_ctx *ctx, float *ms, int64_t *active, int32_t *passes, int cap);
+
 /* Pinned host buffers (the provider's IMemoryOwner<int> can sit on these: no staging copy on D2H). */
 int dq_cuda_host_alloc(void **out, size_t bytes);
 int dq_cuda_host_free(void *p);
@@ -139,6 +146,14 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
  * dq_cuda_bsdiff_search).  Pure host code (a few threads: scan, extensions, stream writers); no device work. */
 int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                         const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out);
+
+/* ---- Patch.Apply ------------------------------------------------------------------------------------
+ * Patch.ApplyInternal (Patch.cs:95-168) on the three UNCOMPRESSED streams (the caller has un-bzip2'ed them, as
+ * Patch.CreatePatchStreams :52-93 does): writes exactly new_size bytes to out.  Pure host code (the add loop of
+ * Patch.cs:143-144, 16 bytes per step); needs no context.  Returns DQ_ERR_CORRUPT_PATCH where the reference throws
+ * "Corrupt patch", and also for negative sizes, a short control stream, or reads past the end of old/diff/extra. */
+int dq_cuda_patch_apply(const uint8_t *old_, int64_t n, const uint8_t *ctrl, int64_t ctrl_len, const uint8_t *diff,
+                        int64_t diff_len, const uint8_t *extra, int64_t extra_len, uint8_t *out, int64_t new_size);
 
 /* ---- building blocks, exported for tests and reuse -------------------------------------------------- */
 /* Stable LSD radix sort of device-resident (uint64 key, uint32 value) pairs on key bits [bit_lo, bit_lo+nbits),

@@ -42,6 +42,8 @@ def lib():
         L.oracle_sufcheck.restype = ctypes.c_int
         L.oracle_verify_sorted.argtypes = [u8p, ctypes.c_int32, i32p]
         L.oracle_verify_sorted.restype = ctypes.c_int32
+        L.oracle_verify_pairs.argtypes = [u8p, ctypes.c_int32, i32p, ctypes.c_void_p, ctypes.c_int64]
+        L.oracle_verify_pairs.restype = ctypes.c_int64
         L.oracle_sa_naive.argtypes = [u8p, ctypes.c_int32, i32p]
         L.oracle_sa_naive.restype = None
         L.oracle_search.argtypes = [i32p, u8p, ctypes.c_int32, u8p, ctypes.c_int32,
@@ -108,6 +110,14 @@ def verify(text, sa):
     assert rc == 0, f"sufcheck returned {rc}"
     bad = lib().oracle_verify_sorted(_ptr(t), t.size, _ptr(s))
     assert bad < 0, f"Input was unsorted at i={bad}"
+
+
+def verify_pairs(text, sa, idx):
+    """Number of sampled adjacent pairs (sa[i], sa[i+1]), i in idx, that are out of order or out of range."""
+    t = _u8(text)
+    s = np.ascontiguousarray(sa, dtype=np.int32)
+    ix = np.ascontiguousarray(idx, dtype=np.int64)
+    return int(lib().oracle_verify_pairs(_ptr(t), t.size, _ptr(s), _ptr(ix), ix.size))
 
 
 def make_I(sa):

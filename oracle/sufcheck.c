@@ -98,6 +98,25 @@ int32_t oracle_verify_sorted(const uint8_t *T, int32_t n, const int32_t *SA)
     return -1;
 }
 
+/*
+ * The same comparison (LibDivSufSortTests.cs:46-59) at the k sampled indices idx[] only: number of pairs
+ * (SA[i], SA[i+1]) that are not strictly increasing or not in range.  For inputs where the full O(n) checks above
+ * take minutes (2 G suffixes), next to an exact comparison with an independently computed array.
+ */
+int64_t oracle_verify_pairs(const uint8_t *T, int32_t n, const int32_t *SA, const int64_t *idx, int64_t k)
+{
+    int64_t bad = 0;
+    for (int64_t j = 0; j < k; ++j) {
+        int64_t i = idx[j];
+        if (i < 0 || i + 1 >= n)
+            continue;
+        int32_t a = SA[i], b = SA[i + 1];
+        if (a < 0 || a >= n || b < 0 || b >= n || !(suffix_compare(T, n, a, b) < 0))
+            ++bad;
+    }
+    return bad;
+}
+
 /* definition-level sorter for tiny inputs: qsort with the comparison above */
 static const uint8_t *g_T;
 static int32_t g_n;

@@ -32,3 +32,21 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
     assert d["gpu_launches"] > 0 and d["n_gpus"] == 1 and abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+
+
+def test_sharded_record_on_the_emulator(monkeypatch):
+    """bench.py's `sharded` record (what rank 0 does at N > 1), run on the CPU logic emulator with tiny inputs and 8
+    logical shards: the C4 sort with its in-run sufcheck, the sharded search with its table comparison, the C5 text."""
+    import importlib.util
+    monkeypatch.setenv("DQ_SHARD_MIN", "1")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rec = bench.sharded_record([0] * 8, workers=1, lib=emu.library(), scale=2e-5)
+    assert "error" not in rec, rec.get("error")
+    assert rec["sort_c4"]["sufcheck"] == 0 and rec["sort_c4"]["input_MBps"] > 0
+    assert rec["sort_search_256MiB"]["table_equals_one_gpu_table"] is True
+    assert rec["sort_c5"]["equals_one_gpu_suffix_array"] is True
+    assert rec["sort_c5"]["sampled_adjacent_pairs_out_of_order"] == 0

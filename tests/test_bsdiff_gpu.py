@@ -196,3 +196,35 @@ def test_streams_identical_for_every_host_thread_shape(shape, monkeypatch):
     for k in ("ctrl", "diff", "extra"):
         assert got[k] == ref[k], (shape, k)
     assert got["search_visits"] == ref["search_calls"]
+
+
+def _broken_suffix_arrays(n):
+    """Suffix arrays a faulty ISuffixSort provider might hand to Diff.Create: in range but not a
+    permutation, an entry == n, a negative entry."""
+    good = np.arange(n, dtype=np.int32)
+    zeros = np.zeros(n + 1, np.int32)
+    too_big = np.concatenate([good, [0]]).astype(np.int32)
+    too_big[n // 2] = n
+    negative = np.concatenate([good, [0]]).astype(np.int32)
+    negative[3] = -5
+    dup = np.concatenate([good, [0]]).astype(np.int32)
+    dup[7] = dup[8]
+    return {"all_zero": zeros, "entry_eq_n": too_big, "negative": negative, "duplicate": dup}
+
+
+@pytest.mark.parametrize("kind", ["all_zero", "entry_eq_n", "negative", "duplicate"])
+def test_broken_provider_is_rejected(sorter, kind):
+    """The search validates a caller-supplied suffix array on the device before following its entries."""
+    from deltaq_b200 import _native
+    n = 5000
+    old, new = random_bytes(n), random_bytes(300, seed=3)
+    I = _broken_suffix_arrays(n)[kind]
+    pos = np.zeros(new.size, np.int32)
+    with pytest.raises(_native.NativeError) as ei:
+        sorter.context.bsdiff_search(old, I, new, 0, new.size, pos, pos.copy())
+    assert ei.value.status == _native.DQ_ERR_INVALID_ARGUMENT
+    assert "permutation" in str(ei.value)
+    # the context is still usable
+    sa = np.empty(n, np.int32)
+    sorter.sort(old, sa)
+    assert np.array_equal(sa, oracle.sais(old))

@@ -62,3 +62,44 @@ def test_streams_end_to_end_on_emulator_at_crew_sizes(pair, monkeypatch):
     for k in ("ctrl", "diff", "extra"):
         assert got[k] == ref[k], k
     assert got["search_visits"] == ref["search_calls"]
+
+
+# ---- Patch.Apply (native add loop, dq_cuda_patch_apply) --------------------------------------------------------
+
+def _patch_lib():
+    import emu
+    return emu.library()
+
+
+def test_patch_apply_round_trip_and_corrupt_streams():
+    """Patch.cs:95-168 on the oracle's streams; corrupt inputs raise "Corrupt patch" (Patch.cs:128,151) instead of
+    reading out of bounds."""
+    import numpy as np
+    import oracle
+    import pytest
+    from deltaq_b200 import _native
+    from search_cases import structured_pairs
+    lib = _patch_lib()
+    for name in ("point_edits", "shifted", "zero_runs_with_islands", "empty_old"):
+        old, new = structured_pairs()[name]
+        r = oracle.bsdiff_streams(old, new)
+        out = _native.patch_apply(old, r["ctrl"], r["diff"], r["extra"], new.size, lib=lib)
+        assert out.tobytes() == new.tobytes(), name
+    old, new = structured_pairs()["point_edits"]
+    r = oracle.bsdiff_streams(old, new)
+    ctrl = bytearray(r["ctrl"])
+    bad_cases = {
+        "short_ctrl": (bytes(ctrl[:-5]), r["diff"], r["extra"], new.size),
+        "short_diff": (bytes(ctrl), r["diff"][:-1], r["extra"], new.size),
+        "short_extra": (bytes(ctrl), r["diff"], r["extra"][:max(0, len(r["extra"]) - 1)] if r["extra"] else b"", new.size + 1),
+        "negative_add": (bytes(ctrl[:7]) + bytes([ctrl[7] | 0x80]) + bytes(ctrl[8:]), r["diff"], r["extra"], new.size),
+        "too_long": (bytes(ctrl), r["diff"], r["extra"], new.size + 10),
+    }
+    for name, (c, d, e, sz) in bad_cases.items():
+        with pytest.raises(RuntimeError, match="Corrupt patch"):
+            _native.patch_apply(old, c, d, e, sz, lib=lib)
+    # a seek that drives the old position below zero
+    import struct
+    bad = struct.pack("<q", 4) + struct.pack("<q", 0) + bytes([100, 0, 0, 0, 0, 0, 0, 0x80]) + struct.pack("<q", 4) + bytes(16)
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.patch_apply(np.zeros(50, np.uint8), bad, bytes(8), b"", 8, lib=lib)
