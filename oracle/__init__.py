@@ -14,7 +14,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("sais.c", "sufcheck.c", "bsdiff.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("sais.c", "divsufsort.c", "sufcheck.c", "bsdiff.c")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
@@ -38,6 +38,8 @@ def lib():
         i32p = ctypes.c_void_p
         L.oracle_sais.argtypes = [u8p, ctypes.c_int32, i32p]
         L.oracle_sais.restype = ctypes.c_int
+        L.oracle_divsufsort.argtypes = [u8p, ctypes.c_int32, i32p]
+        L.oracle_divsufsort.restype = ctypes.c_int
         L.oracle_sufcheck.argtypes = [u8p, ctypes.c_int32, i32p, ctypes.c_int32]
         L.oracle_sufcheck.restype = ctypes.c_int
         L.oracle_verify_sorted.argtypes = [u8p, ctypes.c_int32, i32p]
@@ -85,6 +87,16 @@ def sais(text):
     rc = lib().oracle_sais(_ptr(t), t.size, _ptr(sa))
     if rc != 0:
         raise MemoryError("oracle_sais failed")
+    return sa
+
+
+def divsufsort(text):
+    """LibDivSufSort.Sort(text) restated (oracle/divsufsort.c) -- the reference's default sorter."""
+    t = _u8(text)
+    sa = np.empty(t.size, dtype=np.int32)
+    rc = lib().oracle_divsufsort(_ptr(t), t.size, _ptr(sa))
+    if rc != 0:
+        raise MemoryError("oracle_divsufsort failed")
     return sa
 
 

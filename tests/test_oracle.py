@@ -144,3 +144,89 @@ def test_bsdiff_roundtrip(size):
     for new in (old.copy(), random_bytes(size + 7, seed=5)):
         r = oracle.bsdiff_streams(old, new)
         assert _apply_streams(old.tobytes(), r["ctrl"], r["diff"], r["extra"], new.size) == new.tobytes()
+
+
+# ---- LibDivSufSort restatement (oracle/divsufsort.c): the reference's DEFAULT sorter ---------------------------
+
+def _dss_texts():
+    from deltaq_b200 import workloads as w
+    out = dict(adversarial_texts())
+    for name in asset_names():
+        out[name] = load_asset(name)
+    for size in REF_RANDOM_SIZES:
+        out[f"random_{size}"] = random_bytes(size)
+    out["shruggy"] = np.frombuffer(SHRUGGY, dtype=np.uint8)
+    # sizes that reach the parts small fixtures do not: sssort's block merges (> 1024 B* suffixes per bucket),
+    # trsort's budget and tandem-repeat copies, the in-place merge with a small buffer
+    out["random_300k"] = random_bytes(300_000, seed=5)
+    out["repetitive_1m"] = w.c3_repetitive(1 << 20)
+    out["genome_2m"] = w.c4_genome(2 << 20)
+    out["exe_like_2m"] = w.c2_exe_pair(2 << 20, (2 << 20) + 100)[0]
+    out["fibonacci_300k"] = w.c3_fibonacci(300_000)
+    out["two_letters_200k"] = np.random.default_rng(3).integers(0, 2, 200_000, dtype=np.uint8)
+    return out
+
+
+def test_divsufsort_matches_the_reference_checkers_and_sais():
+    """LibDivSufSortTests.cs: every fixture, the shruggy string and the random sizes pass Verify (sufcheck + strictly
+    increasing adjacent suffixes); the result equals the SA-IS restatement's (the suffix array is unique)."""
+    for name, t in _dss_texts().items():
+        sa = oracle.divsufsort(t)
+        assert sa.size == t.size, name
+        oracle.verify(t, sa)
+        assert np.array_equal(sa, oracle.sais(t)), name
+
+
+def test_divsufsort_does_not_need_a_zeroed_buffer_and_writes_n_entries():
+    # LibDivSufSort.cs:14 allocates without clearing; Diff.cs:90 relies on I[n] staying untouched
+    import ctypes
+    t = random_bytes(5000)
+    buf = np.full(t.size + 1, -7, dtype=np.int32)
+    assert oracle.lib().oracle_divsufsort(ctypes.c_void_p(t.ctypes.data), t.size, ctypes.c_void_p(buf.ctypes.data)) == 0
+    assert buf[t.size] == -7 and np.array_equal(buf[:t.size], oracle.sais(t))
+
+
+# ---- second pin of the delta streams: literal Python transliteration of Diff.cs (tests/diff_transliteration.py) -----
+
+def test_python_transliteration_of_diff_cs_agrees_with_the_oracle_on_the_golden_cases():
+    import os
+    from conftest import GOLDEN
+    import diff_transliteration as dt
+    g = np.load(os.path.join(GOLDEN, "bsdiff_cases.npz"))
+    checked = 0
+    for k in range(int(g["count"])):
+        old, new = g[f"c{k}_old"], g[f"c{k}_new"]
+        if old.size > 6000:
+            continue                      # the literal per-byte Python loops are for small cases
+        ctrl, diff, extra, trace = dt.diff_streams(old.tobytes(), new.tobytes())
+        assert ctrl == g[f"c{k}_ctrl"].tobytes(), k
+        assert diff == g[f"c{k}_diff"].tobytes(), k
+        assert extra == g[f"c{k}_extra"].tobytes(), k
+        tp = np.full(new.size, -1, np.int32)          # the golden trace: (pos, len) at the visited scan positions
+        tl = np.full(new.size, -1, np.int32)
+        for scan, p, ln in trace:
+            tp[scan], tl[scan] = p, ln
+        assert np.array_equal(tp, g[f"c{k}_trace_pos"]) and np.array_equal(tl, g[f"c{k}_trace_len"]), k
+        r = oracle.bsdiff_streams(old, new)
+        assert (r["ctrl"], r["diff"], r["extra"]) == (ctrl, diff, extra), k
+        checked += 1
+    assert checked >= 8
+
+
+def test_python_transliteration_on_structured_pairs():
+    import diff_transliteration as dt
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 256, 1500, dtype=np.uint8)
+    pairs = {
+        "zero_runs": (np.concatenate([np.zeros(700, np.uint8), base[:300], np.zeros(500, np.uint8)]),
+                      np.concatenate([np.zeros(650, np.uint8), base[:310], np.zeros(540, np.uint8)])),
+        "shifted": (base, np.concatenate([rng.integers(0, 256, 37, dtype=np.uint8), base])),
+        "periodic": (np.tile(np.array([1, 2, 3, 4, 5], np.uint8), 300), np.tile(np.array([1, 2, 3, 4, 5], np.uint8), 280)[3:]),
+        "old_one_byte": (np.array([7], np.uint8), base[:200]),
+        "old_empty": (np.zeros(0, np.uint8), base[:100]),
+        "new_empty": (base[:100], np.zeros(0, np.uint8)),
+    }
+    for name, (old, new) in pairs.items():
+        ctrl, diff, extra, _ = dt.diff_streams(old.tobytes(), new.tobytes())
+        r = oracle.bsdiff_streams(old, new)
+        assert (r["ctrl"], r["diff"], r["extra"]) == (ctrl, diff, extra), name
