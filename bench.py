@@ -375,6 +375,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: deltaq_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     host_group = None
+    pinned_cores = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one process per GPU: every rank's host threads (the greedy loop's scan / extender / writers, the CUDA worker
+        # threads) stay on their own share of the cores, so the ranks do not preempt each other; the library sizes its
+        # thread crew by the CPUs the process may run on
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per >= 2:
+            pinned_cores = cores[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, pinned_cores)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         host_group = dist.new_group(backend="gloo")   # host-side waits that keep the GPUs free
@@ -490,6 +500,8 @@ def main():
             torch.cuda.synchronize()
             dist.barrier(group=host_group)
             if rank == 0:
+                if pinned_cores:
+                    os.sched_setaffinity(0, cores)   # this process now drives every GPU: all cores again
                 os.environ["DQ_SHARD_MIN"] = str(32 * MIB)
                 sharded = sharded_record(list(range(world)), workers=min(8, max(1, (os.cpu_count() or 8) // 2)))
             dist.barrier(group=host_group)
@@ -507,7 +519,8 @@ def main():
             "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "old_bytes": n, "new_bytes": m, "pairs_per_step": world,
                        "l2": "working set (>= 24 B x 16.7 M pairs per radix pass, 400 MB) exceeds the 126 MB L2; no flush",
-                       "parallelism": f"{world} x independent pairs (one process and context per GPU)"},
+                       "parallelism": f"{world} x independent pairs (one process and context per GPU)",
+                       "host_cores_per_rank": len(pinned_cores) if pinned_cores else (os.cpu_count() or 0)},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": n + m,
                     # the (pos,len) table crosses PCIe coded: 1 B/position + 12 B/match head + 8 B per 1024 positions

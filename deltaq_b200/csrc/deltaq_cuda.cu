@@ -266,7 +266,8 @@ template <bool ROUND0, bool DIST = false>
 int enqueue_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
                  uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, int32_t *sa_array = nullptr,
                  uint32_t slot_base = 0, uint64_t *upd = nullptr, uint64_t *act_out = nullptr,
-                 const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr, uint32_t hmin = 0)
+                 const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr, uint32_t hmin = 0,
+                 const sx::PeerIsa &peer_isa = sx::PeerIsa{})
 {
     const uint32_t tiles = (uint32_t)div_up(a, sx::kRankTile);
     const size_t bytes = 256 + (size_t)tiles * 8;
@@ -279,7 +280,7 @@ int enqueue_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const ui
     auto k = sx::rank_compact_kernel<ROUND0, DIST>;
     DQ_LAUNCH(k, tiles, sx::kRankThreads, 0, ctx->stream, keys, sa, slot_in, a, n, ctx->isa.as<uint32_t>(),
               sa_array ? sa_array : ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count, slot_base,
-              upd, act_out, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr);
+              upd, act_out, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr, peer_isa);
     ctx->stats.kernel_launches++;
     DQ_CK(ctx, cudaGetLastError());
     DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 8, cudaMemcpyDeviceToHost, ctx->stream));

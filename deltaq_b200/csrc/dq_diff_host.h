@@ -357,6 +357,24 @@ template <bool kWhole> inline Run walk_backward(const uint8_t *a_end, const uint
     return Run{cur, best, at};
 }
 
+// One step of waiting for another thread of the pipeline: pause for the first `pauses` steps (the hand-offs of a busy
+// pipeline are microseconds apart), then yield, and after a few hundred yields sleep, so that a stage with nothing to
+// do (a crew waiting for the next long extension, the stages of other processes sharing the cores when one process per
+// GPU runs this loop) leaves its core to the threads that have work.
+inline void wait_step(int &spins, int pauses)
+{
+    ++spins;
+    if (spins < pauses) {
+#if defined(__SSE2__)
+        _mm_pause();
+#endif
+    } else if (spins < pauses + 256) {
+        std::this_thread::yield();
+    } else {
+        std::this_thread::sleep_for(std::chrono::microseconds(40));
+    }
+}
+
 // ---- helper threads for the long stretches --------------------------------------------------------------------
 // fork-join over a fixed crew: run(f) calls f(part) for part in [0, parts()), part 0 on the calling thread
 class Crew {
@@ -365,16 +383,7 @@ class Crew {
     std::atomic<int> pending_{0};
     std::atomic<bool> quit_{false};
     std::function<void(int)> job_;
-    static void idle(int &spins)
-    {
-        if (++spins < 2048) {
-#if defined(__SSE2__)
-            _mm_pause();
-#endif
-        } else {
-            std::this_thread::yield();
-        }
-    }
+    static void idle(int &spins) { wait_step(spins, 2048); }
 
 public:
     explicit Crew(int helpers)
@@ -723,16 +732,7 @@ template <typename T, int kSlots = 1024> class Handoff {
     T slot_[kSlots];
     std::atomic<uint32_t> head_{0}, tail_{0};
     std::atomic<bool> closed_{false};
-    static void idle(int &spins)
-    {
-        if (++spins < 64) {
-#if defined(__SSE2__)
-            _mm_pause();
-#endif
-        } else {
-            std::this_thread::yield();
-        }
-    }
+    static void idle(int &spins) { wait_step(spins, 64); }
 
 public:
     void push(const T &v)

@@ -180,6 +180,39 @@ apply_kernel(const uint64_t *__restrict__ inbox, uint32_t cap, const RunMeta *__
     }
 }
 
+// ---- small rounds: straight peer accesses ------------------------------------------------------------------
+// Once few suffixes are unresolved, a round's exchanges cost more in launches and stream ordering than in bytes.  Such
+// rounds read ISA[sa + h] with ordinary loads from the owner's slice (peer memory, NVLink) while building the keys, and
+// the rank kernel stores changed ranks into the owner's slice the same way (rank_compact_kernel, DIST with isa_parts).
+struct IsaParts {
+    uint32_t *p[kMaxShards];  // shard o's ISA slice (peer memory): ISA[pos] = p[pos >> kb][pos & ((1 << kb) - 1)]
+    int kb;
+};
+
+__global__ void __launch_bounds__(suffix::kPackThreads)
+build_keys_peer_kernel(const uint64_t *__restrict__ act, uint32_t a, const IsaParts isa, uint32_t n, uint64_t h,
+                       uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, radix::PassPlan plan,
+                       uint32_t *__restrict__ ghist)
+{
+    DQ_DYN_SMEM(smem);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < plan.npass * radix::kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << isa.kb) - 1u;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = act[k];
+        const uint64_t q = (uint64_t)(uint32_t)e + h;
+        uint32_t r2 = 0;
+        if (q < n) r2 = isa.p[(uint32_t)q >> isa.kb][(uint32_t)q & mask] + 1u;
+        const uint64_t key = (e & 0xffffffff00000000ull) | r2;
+        keys[k] = key;
+        vals[k] = (uint32_t)e;
+        radix::hist_accumulate(sh, plan, key);
+    }
+    __syncthreads();
+    radix::hist_flush(sh, plan.npass, ghist);
+}
+
 // key[k] = rank << 32 | reply[k], val[k] = sa, from the regrouped active set and the owners' answers; histograms of
 // the round's digits on the way (as build_keys_kernel does on one GPU)
 __global__ void __launch_bounds__(suffix::kPackThreads)

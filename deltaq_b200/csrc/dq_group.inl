@@ -36,6 +36,8 @@ struct Group {
     bool replicated = false; // text/sa/isa of that text are complete on every shard's context
     bool trace = false;
     uint32_t shard_min = 128u << 20;  // inputs below this stay on shard 0 (DQ_SHARD_MIN overrides)
+    uint64_t direct_max = 8u << 20;   // rounds with at most this many unresolved suffixes in all use straight peer
+                                      // accesses instead of the request / reply / update exchanges (DQ_DIRECT_MAX)
     std::vector<GroupPhase> phases;
     std::chrono::steady_clock::time_point t_phase;
 };
@@ -81,6 +83,7 @@ int create_group(dq_ctx *top, const int *devices, int ndev)
     if (!g) return DQ_ERR_OUT_OF_MEMORY;
     top->group = g;
     if (const char *e = getenv("DQ_SHARD_MIN")) g->shard_min = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char *e = getenv("DQ_DIRECT_MAX")) g->direct_max = strtoull(e, nullptr, 10);
     g->sh.resize((size_t)ndev);
     g->sh[0].c = top;
     for (int i = 1; i < ndev; ++i) {
@@ -125,17 +128,21 @@ int group_sync(dq_ctx *top)
     return DQ_OK;
 }
 
-// every shard's stream waits for everything enqueued so far on every other shard's stream
+// every shard's stream waits for everything enqueued so far on every other shard's stream: shard 0 waits for all the
+// others and the others wait for shard 0 (3 (G - 1) + 1 stream operations instead of G (G - 1))
 int group_barrier(dq_ctx *top)
 {
     Group &g = *top->group;
-    for (Shard &s : g.sh) {
+    Shard &hub = g.sh[0];
+    for (size_t i = 1; i < g.sh.size(); ++i) {
+        Shard &s = g.sh[i];
         DQ_CK(top, cudaSetDevice(s.c->device));
         DQ_CK(top, cudaEventRecord(s.ev, s.c->stream));
+        DQ_CK(top, cudaStreamWaitEvent(hub.c->stream, s.ev, 0));
     }
-    for (Shard &s : g.sh)
-        for (Shard &t : g.sh)
-            if (&s != &t) DQ_CK(top, cudaStreamWaitEvent(s.c->stream, t.ev, 0));
+    DQ_CK(top, cudaSetDevice(hub.c->device));
+    DQ_CK(top, cudaEventRecord(hub.ev, hub.c->stream));
+    for (size_t i = 1; i < g.sh.size(); ++i) DQ_CK(top, cudaStreamWaitEvent(g.sh[i].c->stream, hub.ev, 0));
     return DQ_OK;
 }
 
@@ -385,6 +392,11 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     DQ_TRY(group_mark(top, "r0_partition_exchange"));
 
     // ---- round 0d: local sort of every bucket + first ranks
+    sx::PeerIsa peers{};
+    ds::IsaParts parts{};
+    for (size_t d = 0; d < G; ++d) peers.p[d] = parts.p[d] = g.sh[d].isa_local.as<uint32_t>();
+    peers.kb = parts.kb = kb;
+    const bool direct0 = n <= g.direct_max;  // a small text: ranks go straight to the owners' ISA slices
     rx::PassPlan plan0{};
     rx::plan_add_field(plan0, 0, 64);
     std::vector<uint32_t> entered(G, 0);
@@ -405,7 +417,8 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         s.slot_cur = c->slotA.as<uint32_t>();
         s.slot_nxt = c->slotB.as<uint32_t>();
         DQ_SUB(top, c, (enqueue_rank<true, true>(c, b.kin, b.vin, nullptr, s.cnt, n, nullptr, nullptr, s.slot_cur,
-                                         s.sa_local.as<int32_t>(), s.slot_base, s.upd.as<uint64_t>(), b.kout)));
+                                         s.sa_local.as<int32_t>(), s.slot_base,
+                                         direct0 ? nullptr : s.upd.as<uint64_t>(), b.kout, nullptr, nullptr, 0, peers)));
         s.act = b.kout;
         s.other = b.kin;
     }
@@ -418,7 +431,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     st.active_sum = n;
     st.algorithmic_bytes = (int64_t)n * (41 + 24 * plan0.npass);
     DQ_TRY(group_mark(top, "r0_local_sort_rank"));
-    DQ_TRY(group_route_updates(top, entered));
+    if (!direct0) DQ_TRY(group_route_updates(top, entered));
     DQ_TRY(group_mark(top, "r0_route_updates"));
 
     // ---- doubling rounds
@@ -428,6 +441,65 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     rx::plan_add_field(rp, 32, bits_rank);
     uint64_t h = 8;
     while (total_active > 0) {
+        if (total_active <= g.direct_max) {
+            // ---- a small round: ISA read and written through peer pointers (dq_dist.cuh, "small rounds")
+            DQ_TRY(group_barrier(top));  // every rank written so far is in place
+            std::vector<SortBufs> sorted(G);
+            for (size_t i = 0; i < G; ++i) {
+                Shard &s = g.sh[i];
+                dq_ctx *c = s.c;
+                entered[i] = s.a;
+                if (s.a == 0) continue;
+                DQ_CK(top, cudaSetDevice(c->device));
+                DQ_SUB(top, c, zero_hist(c));
+                auto k = ds::build_keys_peer_kernel;
+                DQ_LAUNCH(k, producer_grid(c, s.a), sx::kPackThreads, rp.npass * rx::kRadix * 4, c->stream, s.act, s.a,
+                          parts, n, h, s.other, c->valA.as<uint32_t>(), rp, c->hist.as<uint32_t>());
+                c->stats.kernel_launches++;
+                SortBufs b{s.other, s.act, c->valA.as<uint32_t>(), c->valB.as<uint32_t>()};
+                DQ_SUB(top, c, run_passes(c, b, s.a, rp, true));
+                sorted[i] = b;
+            }
+            DQ_TRY(group_barrier(top));  // every read of this round is done before any rank changes
+            for (size_t i = 0; i < G; ++i) {
+                Shard &s = g.sh[i];
+                dq_ctx *c = s.c;
+                if (s.a == 0) continue;
+                DQ_CK(top, cudaSetDevice(c->device));
+                SortBufs &b = sorted[i];
+                DQ_SUB(top, c, (enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
+                                                          s.sa_local.as<int32_t>(), s.slot_base, nullptr, b.kout, nullptr,
+                                                          nullptr, 0, peers)));
+                std::swap(s.slot_cur, s.slot_nxt);
+                s.act = b.kout;
+                s.other = b.kin;
+            }
+            st.rounds++;
+            st.active_sum += (int64_t)total_active;
+            st.algorithmic_bytes += (int64_t)total_active * (52 + 24 * rp.npass);
+            total_active = 0;
+            for (size_t i = 0; i < G; ++i) {
+                Shard &s = g.sh[i];
+                if (entered[i]) {
+                    uint32_t next_a = 0;
+                    DQ_SUB(top, s.c, finish_rank(s.c, &next_a, nullptr));
+                    if (next_a > s.a) {
+                        top->err = "internal: active set grew";
+                        return DQ_ERR_INTERNAL;
+                    }
+                    s.a = next_a;
+                }
+                total_active += s.a;
+            }
+            DQ_TRY(group_mark(top, "small_rounds"));
+            h *= 2;
+            if (h > ((uint64_t)1 << 31)) h = (uint64_t)1 << 31;
+            if (st.rounds > 200) {
+                top->err = "internal: doubling did not converge";
+                return DQ_ERR_INTERNAL;
+            }
+            continue;
+        }
         // requests: regroup the unresolved set by the owner of sa + h; the positions go to the owners' inboxes
         for (size_t i = 0; i < G; ++i) {
             Shard &s = g.sh[i];

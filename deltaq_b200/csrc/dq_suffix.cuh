@@ -290,6 +290,13 @@ hist_only_kernel(const uint64_t *__restrict__ keys, uint32_t count, radix::PassP
     radix::hist_flush(sh, plan.npass, ghist);
 }
 
+// ISA slices of a device group, as the rank kernel needs them in a small round (dq_dist.cuh, IsaParts): shard o owns
+// ISA[o << kb, (o + 1) << kb); p[0] == nullptr: not used
+struct PeerIsa {
+    uint32_t *p[16];
+    int kb;
+};
+
 // ---- K4+K5: group heads, new ranks, singleton retirement, compaction -- one pass, decoupled look-back ----
 constexpr int kRankThreads = 512;
 constexpr int kRankItems = 8;
@@ -325,7 +332,7 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     uint32_t *__restrict__ count_out, uint32_t slot_base = 0, uint64_t *__restrict__ upd = nullptr,
                     uint64_t *__restrict__ act_out = nullptr, const uint32_t *__restrict__ depth_in = nullptr,
                     uint32_t *__restrict__ depth_out = nullptr, uint32_t hmin = 0,
-                    uint32_t *__restrict__ min_depth_inv = nullptr)
+                    uint32_t *__restrict__ min_depth_inv = nullptr, const PeerIsa peer_isa = PeerIsa{})
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_wmax[kRankWarps], s_wsum[kRankWarps];
@@ -454,7 +461,14 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         const uint32_t nr = le ? mine : carry;
         const bool valid = (vb[j] >> lane) & 1u;
         if (valid) {
-            if (DIST) upd[wbase + j * 32 + lane] = ((uint64_t)nr << 32) | s[j];
+            if (DIST) {
+                if (upd) {
+                    upd[wbase + j * 32 + lane] = ((uint64_t)nr << 32) | s[j];
+                } else if (ROUND0 || nr != (uint32_t)(key[j] >> 32)) {
+                    // small round of a device group: the changed rank goes straight to the owner's slice
+                    peer_isa.p[s[j] >> peer_isa.kb][s[j] & ((1u << peer_isa.kb) - 1u)] = nr;
+                }
+            }
             if ((sb[j] >> lane) & 1u) {
                 const uint32_t o = out + __popc(sb[j] & lanemask_lt());
                 if (!DIST && (ROUND0 || nr != (uint32_t)(key[j] >> 32))) ISA[s[j]] = nr;

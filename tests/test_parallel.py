@@ -79,10 +79,15 @@ def test_shard_bounds_cover_everything():
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
 
 
-@pytest.mark.parametrize("shards", [2, 3, 8])
-def test_group_sort_emulator(shard_everything, shards):
+# DQ_DIRECT_MAX: rounds with at most that many unresolved suffixes read and write ISA through peer pointers, larger
+# ones use the request / reply / update exchanges -- 0: exchanges only, 3000: both kinds in one sort, default: all of
+# these small texts go the direct way
+@pytest.mark.parametrize("shards,direct_max", [(2, "0"), (3, "3000"), (8, "0"), (8, None), (5, "3000")])
+def test_group_sort_emulator(shard_everything, monkeypatch, shards, direct_max):
     import emu
     from deltaq_b200 import CudaSuffixSort
+    if direct_max is not None:
+        monkeypatch.setenv("DQ_DIRECT_MAX", direct_max)
     with CudaSuffixSort(device=[0] * shards, _lib=emu.library()) as sorter:
         _check_sort(sorter)
 
@@ -128,10 +133,12 @@ def _devices(shards):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shards", [2, 3, 8])
-def test_group_sort_gpu(shard_everything, shards):
+@pytest.mark.parametrize("shards,direct_max", [(2, "0"), (3, "3000"), (8, "0"), (8, None)])
+def test_group_sort_gpu(shard_everything, monkeypatch, shards, direct_max):
     """Logical shards on a one-GPU box; real peers (NVLink) when the box has several GPUs."""
     from deltaq_b200 import CudaSuffixSort
+    if direct_max is not None:
+        monkeypatch.setenv("DQ_DIRECT_MAX", direct_max)
     with CudaSuffixSort(device=_devices(shards)) as sorter:
         _check_sort(sorter)
 
@@ -144,7 +151,7 @@ def test_group_search_gpu(shard_everything):
 
 
 @pytest.mark.gpu
-def test_group_sort_gpu_midsize(shard_everything):
+def test_group_sort_gpu_midsize(shard_everything, monkeypatch):
     """A few MiB per shard: many tiles per pass, several doubling rounds, exchanges of millions of entries."""
     from deltaq_b200 import CudaSuffixSort
     rng = np.random.default_rng(11)
@@ -153,6 +160,7 @@ def test_group_sort_gpu_midsize(shard_everything):
         "uniform_5M": rng.integers(0, 256, 5_000_001, dtype=np.uint8),
         "repeats_4M": np.tile(rng.integers(0, 256, 70_001, dtype=np.uint8), 60)[:4_000_000],
     }
+    monkeypatch.setenv("DQ_DIRECT_MAX", str(1 << 20))   # big rounds by exchange, the small ones after them direct
     with CudaSuffixSort(device=_devices(4)) as sorter:
         for name, t in texts.items():
             sa = np.empty(t.size, np.int32)
