@@ -27,7 +27,8 @@ class DqStats(ctypes.Structure):
                 ("algorithmic_bytes", ctypes.c_int64), ("device_ms", ctypes.c_float),
                 ("pass_ms", ctypes.c_float), ("pass_pairs", ctypes.c_int64),
                 ("search_queries", ctypes.c_int32), ("search_ms", ctypes.c_float),
-                ("table_fallbacks", ctypes.c_int32), ("table_heads", ctypes.c_int32)]
+                ("table_fallbacks", ctypes.c_int32), ("table_heads", ctypes.c_int32),
+                ("search_index_ms", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -68,10 +68,10 @@ struct dq_ctx {
 
     // suffix-sort state (device)
     DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
-        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile;
+        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile, packed;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_index = nullptr;  // ev_index: the search's index of `old` is built
     std::vector<EventPair> pass_events;
     size_t pass_events_used = 0;
     std::vector<RoundRec> round_recs;
@@ -254,6 +254,57 @@ int zero_hist(dq_ctx *ctx)
     return DQ_OK;
 }
 
+// Small alphabets (dq_suffix.cuh): the order-preserving code for a text with the byte histogram `hist`, or bits == 8
+// when more than 16 byte values occur.  compact_min: shortest text that is recoded (DQ_COMPACT_MIN; the histogram costs
+// a host round trip, which only long texts amortise).
+uint32_t compact_min()
+{
+    const char *e = getenv("DQ_COMPACT_MIN");  // read per call: tests lower it
+    return e ? (uint32_t)strtoul(e, nullptr, 10) : (4u << 20);
+}
+
+sx::AlphabetCode choose_code(const uint64_t hist[256])
+{
+    sx::AlphabetCode ac{};
+    int sigma = 0;
+    for (int b = 0; b < 256; ++b) {
+        ac.code[b] = (uint8_t)(sigma & 255);
+        if (hist[b]) ++sigma;
+    }
+    ac.bits = sigma <= 2 ? 1 : sigma <= 4 ? 2 : sigma <= 16 ? 4 : 8;
+    return ac;
+}
+
+// recodes ctx-resident text T (n bytes) into P; returns the code (bits == 8: nothing done)
+int encode_text(dq_ctx *ctx, const uint8_t *T, uint32_t n, const sx::AlphabetCode &ac, DevBuf &P)
+{
+    const uint64_t out_bytes = (((uint64_t)n * ac.bits + 7) >> 3) + 64;  // zero tail: windows and aligned reads past the end
+    DQ_TRY(ensure(ctx, P, out_bytes + 16));
+    auto k = sx::encode_text_kernel;
+    const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(out_bytes, 256), (uint64_t)ctx->sm_count * 16));
+    DQ_LAUNCH(k, g, 256, 0, ctx->stream, T, n, ac, P.as<uint8_t>(), out_bytes + 16);
+    ctx->stats.kernel_launches++;
+    DQ_CK(ctx, cudaGetLastError());
+    return DQ_OK;
+}
+
+// byte histogram of T (n bytes) into hist[256] on the host (one stream synchronisation)
+int byte_histogram(dq_ctx *ctx, const uint8_t *T, uint32_t n, uint64_t hist[256])
+{
+    DQ_TRY(ensure(ctx, ctx->hist, (size_t)2 * rx::kMaxPasses * rx::kRadix * 4 + 256));
+    uint32_t *d = ctx->hist.as<uint32_t>();
+    DQ_CK(ctx, cudaMemsetAsync(d, 0, 256 * 4, ctx->stream));
+    auto k = sx::byte_hist_kernel;
+    const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n, 256 * 16), (uint64_t)ctx->sm_count * 8));
+    DQ_LAUNCH(k, g, 256, 0, ctx->stream, T, n, d);
+    ctx->stats.kernel_launches++;
+    uint32_t h32[256];
+    DQ_CK(ctx, cudaMemcpyAsync(h32, d, sizeof h32, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 256; ++b) hist[b] = h32[b];
+    return DQ_OK;
+}
+
 uint32_t producer_grid(const dq_ctx *ctx, uint64_t items)
 {
     uint64_t blocks = div_up(items, (uint64_t)sx::kPackThreads * sx::kPackItems);
@@ -372,10 +423,20 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
 
     DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 
-    // ---- round 0: all suffixes by their first 8 bytes
+    // ---- round 0: all suffixes by their first 8 bytes -- or, for a long text over at most 16 byte values, by their
+    // first 16 / 32 / 64 characters (dq_suffix.cuh, "small alphabets")
     rx::PassPlan plan{};
     rx::plan_add_field(plan, 0, 64);
     DQ_TRY(mark_round(ctx, n, plan.npass));
+    sx::AlphabetCode ac{};
+    ac.bits = 8;
+    if (n >= compact_min()) {
+        uint64_t bh[256];
+        DQ_TRY(byte_histogram(ctx, ctx->text.as<uint8_t>(), n, bh));
+        ac = choose_code(bh);
+        if (ac.bits < 8) DQ_TRY(encode_text(ctx, ctx->text.as<uint8_t>(), n, ac, ctx->packed));
+    }
+    const uint32_t key_chars = 64u / (uint32_t)ac.bits;
     DQ_TRY(zero_hist(ctx));
     // counter of suffixes inside equal-byte runs, kept behind the histogram tables
     uint32_t *uniform_count = ctx->hist.as<uint32_t>() + 2 * rx::kMaxPasses * rx::kRadix + 32;
@@ -384,7 +445,8 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
         auto k = sx::pack_keys_kernel;
         DQ_LAUNCH(k, producer_grid(ctx, n), sx::kPackThreads, plan.npass * rx::kRadix * 4, ctx->stream,
                   ctx->text.as<uint8_t>(), n, ctx->keyA.as<uint64_t>(), ctx->valA.as<uint32_t>(), plan,
-                  ctx->hist.as<uint32_t>(), uniform_count);
+                  ctx->hist.as<uint32_t>(), uniform_count, ac.bits < 8 ? ctx->packed.as<uint8_t>() : (const uint8_t *)nullptr,
+                  ac.bits);
         st.kernel_launches++;
     }
     DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count + 4, uniform_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -394,7 +456,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     {
         const char *min_env = getenv("DQ_PREFIX3_SORTED_MIN");  // tests: lets small inputs take this path
         const uint32_t min_n = min_env ? (uint32_t)atoi(min_env) : (1u << 20);
-        if (ctx->search_seen && n >= min_n && !getenv("DQ_PREFIX3")) DQ_TRY(build_prefix3_sorted(ctx, s.kin, n));
+        if (ctx->search_seen && n >= min_n && ac.bits == 8 && !getenv("DQ_PREFIX3")) DQ_TRY(build_prefix3_sorted(ctx, s.kin, n));
     }
     st.rounds = 1;
     st.active_sum = n;
@@ -403,18 +465,19 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     uint32_t *slot_cur = ctx->slotA.as<uint32_t>(), *slot_nxt = ctx->slotB.as<uint32_t>();
     uint32_t a = 0;
     // sorted pairs are in (s.kin, s.vin); (s.kout, s.vout) are free
-    DQ_TRY(run_rank<true>(ctx, s.kin, s.vin, nullptr, n, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_cur, &a));
+    DQ_TRY(run_rank<true>(ctx, s.kin, s.vin, nullptr, n, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_cur, &a,
+                          nullptr, nullptr, key_chars));
 
     // ---- doubling rounds over the unresolved suffixes.  Every group carries its own depth (bytes its members
     // share); h is the depth every rank in ISA is consistent to.  Round 1 refines equal-byte-run groups by run
     // length in one step (dq_suffix.cuh), so zero padding does not cost log2(run length) rounds.
     const int bits_r2 = bit_length(n);                      // ISA[.]+1 in [0, n]
     const int bits_rank = bit_length(n > 1 ? n - 1 : 1);    // rank in [0, n-1]
-    uint64_t h = 8;
+    uint64_t h = key_chars;
     uint32_t *depth_cur = nullptr, *depth_nxt = nullptr;
     // Run-length refinement pays when a visible share of the text sits in equal-byte runs (zero padding); without
     // such runs plain doubling (uniform depth, no depth arrays) is the shorter path.
-    const bool run_aware = a > 0 && (uint64_t)ctx->h_count[4] * 64 >= n;
+    const bool run_aware = a > 0 && ac.bits == 8 && (uint64_t)ctx->h_count[4] * 64 >= n;
     if (run_aware) {
         DQ_TRY(ensure(ctx, ctx->depthA, n4));
         DQ_TRY(ensure(ctx, ctx->depthB, n4));
@@ -556,7 +619,7 @@ int destroy_single(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
-                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->newtext, &ctx->s_pos,
+                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->packed, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -573,6 +636,7 @@ int destroy_single(dq_ctx *ctx)
     if (ctx->h_tiles.p) cudaFreeHost(ctx->h_tiles.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_index) cudaEventDestroy(ctx->ev_index);
     for (int i = 0; i < 8; ++i) {
         if (ctx->slice_ready[i]) cudaEventDestroy(ctx->slice_ready[i]);
         if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
@@ -617,6 +681,7 @@ int create_single(dq_ctx **out, int dev)
     }
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_index)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void **)&ctx->h_count, 64, cudaHostAllocDefault)) != cudaSuccess)
         return fail("cudaHostAlloc", e);
     if ((e = cudaFuncSetAttribute(rx::onesweep_pass_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -943,6 +1008,7 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     DQ_CK(ctx, werr);
     if (m) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_ms, ctx->ev0, ctx->ev1));
+    if (m) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_index_ms, ctx->ev0, ctx->ev_index));
     if (m) {
         uint32_t heads = 0;
         DQ_CK(ctx, cudaMemcpy(&heads, ctx->d_headcount.p, 4, cudaMemcpyDeviceToHost));

@@ -358,7 +358,7 @@ template <bool kWhole> inline Run walk_backward(const uint8_t *a_end, const uint
 }
 
 // One step of waiting for another thread of the pipeline: pause for the first `pauses` steps (the hand-offs of a busy
-// pipeline are microseconds apart), then yield, and after a few hundred yields sleep, so that a stage with nothing to
+// pipeline are microseconds apart), then yield, and after a few milliseconds of yields sleep, so that a stage with nothing to
 // do (a crew waiting for the next long extension, the stages of other processes sharing the cores when one process per
 // GPU runs this loop) leaves its core to the threads that have work.
 inline void wait_step(int &spins, int pauses)
@@ -368,10 +368,10 @@ inline void wait_step(int &spins, int pauses)
 #if defined(__SSE2__)
         _mm_pause();
 #endif
-    } else if (spins < pauses + 256) {
+    } else if (spins < pauses + 20000) {  // a few milliseconds of yields: longer than any gap inside one call
         std::this_thread::yield();
     } else {
-        std::this_thread::sleep_for(std::chrono::microseconds(40));
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
     }
 }
 

@@ -138,14 +138,13 @@ __global__ void publish_meta_kernel(const uint32_t *__restrict__ ghist, const ui
     if (d < shards) meta_of.p[d][self] = RunMeta{ghist[d], gbase[d]};
 }
 
-// sampled 8-byte keys of a text slice, for the splitters: position = a fixed odd multiplier walk over the slice
+// sampled keys of a slice, for the splitters: element = a fixed odd multiplier walk over the slice's key array
 __global__ void __launch_bounds__(256)
-sample_keys_kernel(const uint8_t *__restrict__ T, uint32_t count, uint32_t nsamples, uint64_t *__restrict__ out)
+sample_keys_kernel(const uint64_t *__restrict__ keys, uint32_t count, uint32_t nsamples, uint64_t *__restrict__ out)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nsamples) return;
-    const uint32_t off = (uint32_t)(((uint64_t)j * 0x9E3779B1ull + 12345u) % count);
-    out[j] = suffix::load_key8(T, off);
+    out[j] = keys[(uint32_t)(((uint64_t)j * 0x9E3779B1ull + 12345u) % count)];
 }
 
 // owner side of the ISA fetch: for every source s, answer its requests in order, straight into the requester's

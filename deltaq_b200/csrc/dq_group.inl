@@ -17,7 +17,7 @@ struct Shard {
     uint32_t own_begin = 0, own_cnt = 0;  // text positions whose ISA entries live here
     uint32_t cnt = 0, slot_base = 0;      // SA slots [slot_base, slot_base + cnt) are sorted here
     uint32_t a = 0;                       // unresolved suffixes entering the next round
-    DevBuf slice, isa_local, sa_local, upd, reply, inbox_req, inbox_upd, meta_req, meta_upd, samples;
+    DevBuf slice, packed, isa_local, sa_local, upd, reply, inbox_req, inbox_upd, meta_req, meta_upd, samples;
     uint64_t *act = nullptr, *other = nullptr;  // packed unresolved set and the free 64-bit buffer
     uint32_t *slot_cur = nullptr, *slot_nxt = nullptr;
     uint32_t *h_small = nullptr;  // pinned: [0..16) digit counts, [16..18) rank kernel's counters
@@ -63,7 +63,7 @@ void destroy_group(dq_ctx *top)
         if (!s.c) continue;
         cudaSetDevice(s.c->device);
         cudaStreamSynchronize(s.c->stream);
-        DevBuf *bufs[] = {&s.slice, &s.isa_local, &s.sa_local, &s.upd, &s.reply, &s.inbox_req, &s.inbox_upd,
+        DevBuf *bufs[] = {&s.slice, &s.packed, &s.isa_local, &s.sa_local, &s.upd, &s.reply, &s.inbox_req, &s.inbox_upd,
                           &s.meta_req, &s.meta_upd, &s.samples};
         for (DevBuf *b : bufs)
             if (b->p) cudaFree(b->p);
@@ -297,12 +297,38 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         total_samples += sample_cnt[i];
     }
 
-    // ---- round 0a: text slices up, 8-byte keys of every position, sampled keys for the splitters
+    // ---- round 0a: text slices up, keys of every position, sampled keys for the splitters
+    constexpr uint32_t kHalo = 64;  // a key reads at most 64 characters (small alphabets) past its position
     for (size_t i = 0; i < G; ++i) {
         Shard &s = g.sh[i];
         dq_ctx *c = s.c;
         DQ_CK(top, cudaSetDevice(c->device));
-        DQ_SUB(top, c, ensure(c, s.slice, (size_t)s.own_cnt + 64));
+        DQ_SUB(top, c, ensure(c, s.slice, (size_t)s.own_cnt + kHalo + 64));
+        if (s.own_cnt == 0) continue;
+        // the halo comes from the text, the rest is zero
+        const uint32_t halo = (uint32_t)(std::min<uint64_t>(n, (uint64_t)s.own_begin + s.own_cnt + kHalo) - s.own_begin);
+        DQ_CK(top, cudaMemcpyAsync(s.slice.p, text + s.own_begin, halo, cudaMemcpyDefault, c->stream));
+        DQ_CK(top, cudaMemsetAsync(s.slice.as<uint8_t>() + halo, 0, (size_t)s.own_cnt + kHalo + 64 - halo, c->stream));
+    }
+    // small alphabets (dq_suffix.cuh): every shard counts the byte values of its slice, the code is chosen once
+    sx::AlphabetCode ac{};
+    ac.bits = 8;
+    if (n >= compact_min()) {
+        uint64_t bh[256] = {};
+        for (Shard &s : g.sh) {
+            if (s.own_cnt == 0) continue;
+            DQ_CK(top, cudaSetDevice(s.c->device));
+            uint64_t part[256];
+            DQ_SUB(top, s.c, byte_histogram(s.c, s.slice.as<uint8_t>(), s.own_cnt, part));
+            for (int b = 0; b < 256; ++b) bh[b] += part[b];
+        }
+        ac = choose_code(bh);
+    }
+    const uint32_t key_chars = 64u / (uint32_t)ac.bits;
+    for (size_t i = 0; i < G; ++i) {
+        Shard &s = g.sh[i];
+        dq_ctx *c = s.c;
+        DQ_CK(top, cudaSetDevice(c->device));
         DQ_SUB(top, c, ensure(c, c->partK, (size_t)std::max<uint32_t>(s.own_cnt, 1) * 8));
         DQ_SUB(top, c, ensure(c, c->partV, (size_t)std::max<uint32_t>(s.own_cnt, 1) * 4));
         DQ_SUB(top, c, ensure(c, s.samples, (size_t)kSamplesPerShard * 8));
@@ -310,15 +336,18 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         DQ_SUB(top, c, ensure(c, s.meta_req, G * sizeof(ds::RunMeta)));
         DQ_SUB(top, c, ensure(c, s.meta_upd, G * sizeof(ds::RunMeta)));
         if (s.own_cnt == 0) continue;
-        // keys read up to 7 bytes past the slice: the halo comes from the text, the rest is zero
-        const uint32_t halo = (uint32_t)(std::min<uint64_t>(n, (uint64_t)s.own_begin + s.own_cnt + 8) - s.own_begin);
-        DQ_CK(top, cudaMemcpyAsync(s.slice.p, text + s.own_begin, halo, cudaMemcpyDefault, c->stream));
-        DQ_CK(top, cudaMemsetAsync(s.slice.as<uint8_t>() + halo, 0, (size_t)s.own_cnt + 64 - halo, c->stream));
+        const uint8_t *P = nullptr;
+        if (ac.bits < 8) {
+            // the slice and its halo recoded: position p of the slice is character p of this shard's stream
+            const uint32_t chars = (uint32_t)(std::min<uint64_t>(n, (uint64_t)s.own_begin + s.own_cnt + kHalo) - s.own_begin);
+            DQ_SUB(top, c, encode_text(c, s.slice.as<uint8_t>(), chars, ac, s.packed));
+            P = s.packed.as<uint8_t>();
+        }
         auto k = sx::pack_slice_kernel;
         DQ_LAUNCH(k, producer_grid(c, s.own_cnt), sx::kPackThreads, 0, c->stream, s.slice.as<uint8_t>(), s.own_begin,
-                  s.own_cnt, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), (unsigned long long *)nullptr);
+                  s.own_cnt, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), (unsigned long long *)nullptr, P, ac.bits);
         auto ks = ds::sample_keys_kernel;
-        DQ_LAUNCH(ks, (uint32_t)div_up(sample_cnt[i], 256), 256, 0, c->stream, s.slice.as<uint8_t>(), s.own_cnt,
+        DQ_LAUNCH(ks, (uint32_t)div_up(sample_cnt[i], 256), 256, 0, c->stream, c->partK.as<uint64_t>(), s.own_cnt,
                   sample_cnt[i], s.samples.as<uint64_t>());
         c->stats.kernel_launches += 2;
         DQ_CK(top, cudaMemcpyAsync(s.h_samples, s.samples.p, (size_t)sample_cnt[i] * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -418,7 +447,8 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         s.slot_nxt = c->slotB.as<uint32_t>();
         DQ_SUB(top, c, (enqueue_rank<true, true>(c, b.kin, b.vin, nullptr, s.cnt, n, nullptr, nullptr, s.slot_cur,
                                          s.sa_local.as<int32_t>(), s.slot_base,
-                                         direct0 ? nullptr : s.upd.as<uint64_t>(), b.kout, nullptr, nullptr, 0, peers)));
+                                         direct0 ? nullptr : s.upd.as<uint64_t>(), b.kout, nullptr, nullptr, key_chars,
+                                         peers)));
         s.act = b.kout;
         s.other = b.kin;
     }
@@ -439,7 +469,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     rx::PassPlan rp{};
     rx::plan_add_field(rp, 0, bits_r2);
     rx::plan_add_field(rp, 32, bits_rank);
-    uint64_t h = 8;
+    uint64_t h = key_chars;
     while (total_active > 0) {
         if (total_active <= g.direct_max) {
             // ---- a small round: ISA read and written through peer pointers (dq_dist.cuh, "small rounds")
@@ -678,16 +708,20 @@ int group_search(dq_ctx *top, uint32_t n, const uint8_t *new_, uint32_t m, uint3
         if (c->err.size() && c != top) top->err = c->err;
     }
     DQ_TRY(group_sync(top));
-    float worst = 0.f;
+    float worst = 0.f, worst_index = 0.f;
     for (size_t i = 0; i < G; ++i) {
         Shard &s = g.sh[i];
         if (begin[i + 1] == begin[i]) continue;
-        float ms = 0.f;
+        float ms = 0.f, ims = 0.f;
         DQ_CK(top, cudaSetDevice(s.c->device));
         DQ_CK(top, cudaEventElapsedTime(&ms, s.c->ev0, s.c->ev1));
+        DQ_CK(top, cudaEventElapsedTime(&ims, s.c->ev0, s.c->ev_index));
+        if (getenv("DQ_TRACE")) fprintf(stderr, "[dq trace] group search shard %zu: %u positions, %.2f ms (index %.2f ms)\n", i, begin[i + 1] - begin[i], ms, ims);
         worst = std::max(worst, ms);
+        worst_index = std::max(worst_index, ims);
         if (i) top->stats.kernel_launches += s.c->stats.kernel_launches;
     }
+    top->stats.search_index_ms = worst_index;
     (void)launches0;
     top->stats.search_ms = worst;
     top->stats.search_queries = (int32_t)count;

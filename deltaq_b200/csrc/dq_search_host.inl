@@ -161,6 +161,7 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
     if (count == 0) return DQ_OK;
     DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     DQ_TRY(build_lcp(ctx, n));
+    DQ_CK(ctx, cudaEventRecord(ctx->ev_index, ctx->stream));
     const uint32_t chunks = (uint32_t)div_up(count, sr::kChunk), supers = (uint32_t)div_up(count, sr::kSuper);
     DQ_TRY(ensure(ctx, ctx->s_pos, (size_t)count * 4));
     DQ_TRY(ensure(ctx, ctx->s_len, (size_t)count * 4));
@@ -329,5 +330,6 @@ int search_common(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I,
     }
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (count) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_ms, ctx->ev0, ctx->ev1));
+    if (count) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_index_ms, ctx->ev0, ctx->ev_index));
     return DQ_OK;
 }

@@ -44,12 +44,84 @@ __device__ __forceinline__ uint64_t load_key8(const uint8_t *__restrict__ T, uin
     return ((uint64_t)__byte_perm(a, 0, 0x0123) << 32) | (uint64_t)__byte_perm(b, 0, 0x0123);
 }
 
+// ---- small alphabets: more than 8 characters per 64-bit key ------------------------------------------------------
+// Round 0 sorts by as many leading characters as fit one key.  A text with at most 16 distinct byte values (DNA, binary
+// data) is first rewritten with order-preserving codes of b = 1, 2 or 4 bits per character, packed most significant
+// bit first; the key of suffix i is then the 64-bit window at bit i*b of that stream: 64, 32 or 16 characters instead of
+// 8, so round 0 alone resolves what plain keys need two or three more doubling rounds for (BASELINE config #4: iid
+// {A,C,G,T} -- everything outside the tandem repeats is unique after 32 characters).  Past the end the stream is zero,
+// which is also the code of the smallest character: the same tie, and the same resolution, as the zero padding of
+// plain keys (header comment; the rank kernel's "shorter than the key" rule takes the key length in characters).
+struct AlphabetCode {
+    uint8_t code[256];  // order-preserving code of every byte value that occurs
+    int bits;           // bits per character: 1, 2 or 4 (8 = no recoding, keys come from the text itself)
+};
+
+// 256-bin histogram of the text (which byte values occur).  grid-stride, 256 threads
+__global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restrict__ T, uint32_t n,
+                                                        uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t words = n >> 2;
+    const uint32_t *W = reinterpret_cast<const uint32_t *>(T);
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(W + w);
+        atomicAdd(&sh[v & 255u], 1u);
+        atomicAdd(&sh[(v >> 8) & 255u], 1u);
+        atomicAdd(&sh[(v >> 16) & 255u], 1u);
+        atomicAdd(&sh[v >> 24], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) atomicAdd(&sh[T[(words << 2) + threadIdx.x]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// P[j] = the codes of characters [j * 8/b, (j+1) * 8/b), first character in the most significant bits; characters at
+// or past n (and everything up to out_bytes) are zero.  T must be readable up to n.
+__global__ void __launch_bounds__(256) encode_text_kernel(const uint8_t *__restrict__ T, uint32_t n,
+                                                          const AlphabetCode ac, uint8_t *__restrict__ P,
+                                                          uint64_t out_bytes)
+{
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = ac.code[threadIdx.x];
+    __syncthreads();
+    const uint32_t per = 8u / (uint32_t)ac.bits;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < out_bytes; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        const uint64_t c0 = j * per;
+        for (uint32_t k = 0; k < per; ++k) {
+            const uint64_t c = c0 + k;
+            v = (v << ac.bits) | (c < n ? (uint32_t)lut[T[c]] : 0u);
+        }
+        P[j] = (uint8_t)v;
+    }
+}
+
+// 64-bit window of the packed stream at bit offset i * bits (bits in {1, 2, 4}); P is zero padded by >= 16 bytes
+__device__ __forceinline__ uint64_t load_window(const uint8_t *__restrict__ P, uint32_t i, int bits)
+{
+    const uint64_t bit = (uint64_t)i * (uint64_t)bits;
+    const uint32_t j = (uint32_t)(bit >> 3);
+    const unsigned s = (unsigned)(bit & 7u);
+    const uint64_t k0 = load_key8(P, j);
+    return s ? (k0 << s) | ((uint64_t)P[j + 8] >> (8u - s)) : k0;
+}
+
+// first characters of suffix i as one key: from the text (bits == 8) or from its packed recoding
+__device__ __forceinline__ uint64_t load_key(const uint8_t *__restrict__ T, const uint8_t *__restrict__ P, uint32_t i,
+                                            int bits)
+{
+    return bits == 8 ? load_key8(T, i) : load_window(P, i, bits);
+}
+
 // K0: element k stands for suffix i = n-1-k.  keys[k] = first 8 bytes, vals[k] = i; digit histograms of all
 // 8 passes are accumulated on the way.  grid-stride; dynamic smem = npass*256*4.
 __global__ void __launch_bounds__(kPackThreads)
 pack_keys_kernel(const uint8_t *__restrict__ T, uint32_t n, uint64_t *__restrict__ keys,
                  uint32_t *__restrict__ vals, radix::PassPlan plan, uint32_t *__restrict__ ghist,
-                 uint32_t *__restrict__ uniform_count)
+                 uint32_t *__restrict__ uniform_count, const uint8_t *__restrict__ P = nullptr, int bits = 8)
 {
     DQ_DYN_SMEM(smem);
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
@@ -63,7 +135,7 @@ pack_keys_kernel(const uint8_t *__restrict__ T, uint32_t n, uint64_t *__restrict
             uint64_t k = base + (uint64_t)j * kPackThreads + threadIdx.x;
             if (k < n) {
                 const uint32_t i = n - 1u - (uint32_t)k;
-                const uint64_t key = load_key8(T, i);
+                const uint64_t key = load_key(T, P, i, bits);
                 keys[k] = key;
                 vals[k] = i;
                 radix::hist_accumulate(sh, plan, key);
@@ -125,7 +197,8 @@ build_keys_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ 
 // (warp-aggregated atomics), from which the ranks agree on bucket splitters.
 __global__ void __launch_bounds__(kPackThreads)
 pack_slice_kernel(const uint8_t *__restrict__ T, uint32_t pos_begin, uint32_t count, uint64_t *__restrict__ keys,
-                  uint32_t *__restrict__ vals, unsigned long long *__restrict__ hist16)
+                  uint32_t *__restrict__ vals, unsigned long long *__restrict__ hist16,
+                  const uint8_t *__restrict__ P = nullptr, int bits = 8)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (count + stride - 1) / stride;
@@ -135,7 +208,7 @@ pack_slice_kernel(const uint8_t *__restrict__ T, uint32_t pos_begin, uint32_t co
         uint32_t bin = 0xffffffffu;
         if (valid) {
             const uint32_t off = count - 1u - (uint32_t)k;
-            const uint64_t key = load_key8(T, off);
+            const uint64_t key = load_key(T, P, off, bits);
             keys[k] = key;
             vals[k] = pos_begin + off;
             bin = (uint32_t)(key >> 48);
@@ -310,6 +383,7 @@ __host__ __device__ __forceinline__ uint32_t rk_max(uint64_t v) { return (uint32
 __host__ __device__ __forceinline__ uint32_t rk_sum(uint64_t v) { return (uint32_t)(v & kField31); }
 
 // keys/sa: the sorted active set (a entries).  slot_in == nullptr in round 0 (slot[k] = k).
+// hmin: in round 0 the number of characters a key holds (8 for plain keys); later the depth all ranks are consistent to.
 // Outputs: ISA, SA, the compacted next active set (sa_out, rank_out, slot_out) and *count_out = its size.
 //
 // Warp-striped: warp w of the tile owns 32*kRankItems consecutive positions, row j of lane l is position
@@ -370,7 +444,7 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                 if (ROUND0) ps = sa[k - 1];
             }
             hd = key[j] != pk;
-            if (ROUND0) hd = hd || (n - ps < 8u);  // the previous suffix is shorter than the key: it stands alone
+            if (ROUND0) hd = hd || (n - ps < hmin);  // the previous suffix is shorter than the key: it stands alone
         }
         hb[j] = __ballot_sync(kFullMask, hd);
         vb[j] = __ballot_sync(kFullMask, valid);
@@ -380,7 +454,7 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         bool hd = true;
         if (lane == 31 && k < a) {
             hd = keys[k] != key[kRankItems - 1];
-            if (ROUND0) hd = hd || (n - s[kRankItems - 1] < 8u);
+            if (ROUND0) hd = hd || (n - s[kRankItems - 1] < hmin);
         }
         hb[kRankItems] = __shfl_sync(kFullMask, hd ? 1u : 0u, 31);
     }

@@ -52,6 +52,8 @@ typedef struct dq_stats {
     float   search_ms;         /* CUDA-event time of the last search's device work (LCP build included when it ran) */
     int32_t table_fallbacks;   /* dq_cuda_bsdiff_streams: 1 if the coded (pos,len) table overflowed and the full one was used */
     int32_t table_heads;       /* dq_cuda_bsdiff_streams: match heads in the coded table (12 B each over PCIe, + 1 B/position) */
+    float   search_index_ms;   /* part of search_ms spent building the index of `old` (LCP array, block minima, bucket and
+                                  prefix tables) before the first query kernel; 0 when the index was already resident */
 } dq_stats;
 
 /* Environment variables read by the library (tests and tuning only; none changes a result):

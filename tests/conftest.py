@@ -93,3 +93,23 @@ def adversarial_texts():
     out["runs_long_zero_islands"] = np.zeros(30000, np.uint8)
     out["runs_long_zero_islands"][[5000, 5001, 12000, 20000, 20001, 20002, 29990]] = [9, 9, 1, 200, 0, 3, 7]
     return out
+
+
+def small_alphabet_texts():
+    """Texts over at most 16 byte values (the sorter then packs 16 / 32 / 64 characters per key: dq_suffix.cuh, "small
+    alphabets"), plus neighbours of the thresholds; ends in the smallest character exercise the end-of-text rule with
+    keys longer than 8 characters."""
+    rng = np.random.default_rng(5)
+    out = {}
+    out["bin_70000"] = rng.integers(0, 2, 70000, dtype=np.uint8)
+    out["acgt_50000"] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 50000)]
+    out["acgtn_30000"] = np.frombuffer(b"ACGNT", dtype=np.uint8)[rng.integers(0, 5, 30000)]
+    out["hex16_30000"] = rng.integers(100, 116, 30000, dtype=np.uint8)
+    out["sigma17_9000"] = rng.integers(0, 17, 9000, dtype=np.uint8)
+    out["one_value_5000"] = np.full(5000, 7, np.uint8)
+    out["bin_zero_tail"] = np.concatenate([rng.integers(0, 2, 6000, dtype=np.uint8), np.zeros(70, np.uint8)])
+    out["acgt_a_tail"] = np.concatenate([np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 7000)],
+                                         np.full(40, ord("A"), np.uint8)])
+    out["acgt_tandem"] = np.tile(np.frombuffer(b"ACGTTGCAAC", dtype=np.uint8), 900)
+    out["bin_4163"] = rng.integers(0, 2, 4163, dtype=np.uint8)
+    return out

@@ -71,3 +71,16 @@ def test_radix_sort_pairs(sorter):
         sorter.context.radix_sort_pairs(k2, v2, bits)
         order = np.argsort(keys, kind="stable")
         assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
+
+
+@pytest.mark.parametrize("name", sorted(__import__("conftest").small_alphabet_texts()))
+def test_small_alphabets(sorter, name, monkeypatch):
+    """Recoded keys (16 / 32 / 64 characters each) on small texts: DQ_COMPACT_MIN lowers the 4 MiB
+    from which the product recodes."""
+    from conftest import small_alphabet_texts
+    monkeypatch.setenv("DQ_COMPACT_MIN", "1")
+    t = small_alphabet_texts()[name]
+    sa = np.full(t.size + 1, -7, dtype=np.int32)
+    sorter.sort(t, sa[:t.size])
+    assert sa[t.size] == -7
+    assert np.array_equal(sa[:t.size], oracle.sais(t))

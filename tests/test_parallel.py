@@ -92,6 +92,21 @@ def test_group_sort_emulator(shard_everything, monkeypatch, shards, direct_max):
         _check_sort(sorter)
 
 
+def test_group_sort_small_alphabets_emulator(shard_everything, monkeypatch):
+    """Recoded keys (dq_suffix.cuh, "small alphabets") through the sharded path: one code for all shards, 64-character
+    halos."""
+    import emu
+    from conftest import small_alphabet_texts
+    from deltaq_b200 import CudaSuffixSort
+    monkeypatch.setenv("DQ_COMPACT_MIN", "1")
+    monkeypatch.setenv("DQ_DIRECT_MAX", "2000")
+    with CudaSuffixSort(device=[0] * 3, _lib=emu.library()) as sorter:
+        for name, t in small_alphabet_texts().items():
+            sa = np.empty(t.size, np.int32)
+            sorter.sort(t, sa)
+            assert np.array_equal(sa, oracle.sais(t)), name
+
+
 def test_group_search_emulator(shard_everything):
     import emu
     from deltaq_b200 import CudaSuffixSort
@@ -141,6 +156,19 @@ def test_group_sort_gpu(shard_everything, monkeypatch, shards, direct_max):
         monkeypatch.setenv("DQ_DIRECT_MAX", direct_max)
     with CudaSuffixSort(device=_devices(shards)) as sorter:
         _check_sort(sorter)
+
+
+@pytest.mark.gpu
+def test_group_sort_small_alphabets_gpu(shard_everything, monkeypatch):
+    from conftest import small_alphabet_texts
+    from deltaq_b200 import CudaSuffixSort
+    monkeypatch.setenv("DQ_COMPACT_MIN", "1")
+    monkeypatch.setenv("DQ_DIRECT_MAX", "2000")
+    with CudaSuffixSort(device=_devices(3)) as sorter:
+        for name, t in small_alphabet_texts().items():
+            sa = np.empty(t.size, np.int32)
+            sorter.sort(t, sa)
+            assert np.array_equal(sa, oracle.sais(t)), name
 
 
 @pytest.mark.gpu

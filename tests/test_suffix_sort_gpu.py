@@ -132,3 +132,16 @@ def test_stats_and_reuse(sorter):
     z = np.zeros(50_000, np.uint8)
     assert np.array_equal(_sort(sorter, z), np.arange(49_999, -1, -1, dtype=np.int32))
     assert np.array_equal(_sort(sorter, t), a)
+
+
+@pytest.mark.parametrize("name", sorted(__import__("conftest").small_alphabet_texts()))
+def test_small_alphabets(sorter, name, monkeypatch):
+    """Recoded keys (16 / 32 / 64 characters each) on small texts: DQ_COMPACT_MIN lowers the 4 MiB
+    from which the product recodes."""
+    from conftest import small_alphabet_texts
+    monkeypatch.setenv("DQ_COMPACT_MIN", "1")
+    t = small_alphabet_texts()[name]
+    sa = np.full(t.size + 1, -7, dtype=np.int32)
+    sorter.sort(t, sa[:t.size])
+    assert sa[t.size] == -7
+    assert np.array_equal(sa[:t.size], oracle.sais(t))
