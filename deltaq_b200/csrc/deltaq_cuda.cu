@@ -68,9 +68,10 @@ struct dq_ctx {
 
     // suffix-sort state (device)
     DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
-        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile, packed;
+        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile, packed, late;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
+    cudaEvent_t ev_copy = nullptr;  // early copy of the suffix array: started / landed
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_index = nullptr;  // ev_index: the search's index of `old` is built
     std::vector<EventPair> pass_events;
     size_t pass_events_used = 0;
@@ -318,7 +319,7 @@ int enqueue_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const ui
                  uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, int32_t *sa_array = nullptr,
                  uint32_t slot_base = 0, uint64_t *upd = nullptr, uint64_t *act_out = nullptr,
                  const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr, uint32_t hmin = 0,
-                 const sx::PeerIsa &peer_isa = sx::PeerIsa{})
+                 const sx::PeerIsa &peer_isa = sx::PeerIsa{}, uint64_t *late = nullptr, uint32_t *late_count = nullptr)
 {
     const uint32_t tiles = (uint32_t)div_up(a, sx::kRankTile);
     const size_t bytes = 256 + (size_t)tiles * 8;
@@ -331,7 +332,7 @@ int enqueue_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const ui
     auto k = sx::rank_compact_kernel<ROUND0, DIST>;
     DQ_LAUNCH(k, tiles, sx::kRankThreads, 0, ctx->stream, keys, sa, slot_in, a, n, ctx->isa.as<uint32_t>(),
               sa_array ? sa_array : ctx->sa.as<int32_t>(), sa_out, rank_out, slot_out, desc, ticket, count, slot_base,
-              upd, act_out, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr, peer_isa);
+              upd, act_out, depth_in, depth_out, hmin, depth_out ? count + 1 : nullptr, peer_isa, late, late_count);
     ctx->stats.kernel_launches++;
     DQ_CK(ctx, cudaGetLastError());
     DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count, count, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -351,11 +352,65 @@ template <bool ROUND0>
 int run_rank(dq_ctx *ctx, const uint64_t *keys, const uint32_t *sa, const uint32_t *slot_in, uint32_t a,
              uint32_t n, uint32_t *sa_out, uint32_t *rank_out, uint32_t *slot_out, uint32_t *next_a,
              const uint32_t *depth_in = nullptr, uint32_t *depth_out = nullptr, uint32_t hmin = 0,
-             uint32_t *min_depth = nullptr)
+             uint32_t *min_depth = nullptr, uint64_t *late = nullptr, uint32_t *late_count = nullptr)
 {
     DQ_TRY((enqueue_rank<ROUND0, false>(ctx, keys, sa, slot_in, a, n, sa_out, rank_out, slot_out, nullptr, 0, nullptr,
-                                        nullptr, depth_in, depth_out, hmin)));
+                                        nullptr, depth_in, depth_out, hmin, sx::PeerIsa{}, late, late_count)));
     return finish_rank(ctx, next_a, min_depth);
+}
+
+// Early copy of the suffix array (sort_resident / group_sort): once few suffixes are unresolved, the array as it stands
+// starts towards the host on the copy stream while the remaining rounds run; those rounds list the slots they
+// resolve, and the list is patched into the host array when the copy has landed.  Needs a host array the device can
+// write (pinned memory: dq_cuda_host_alloc, or anything cudaHostRegister'ed as mapped).
+struct EarlyCopy {
+    int32_t *host_sa = nullptr;  // device-visible address of the caller's array, or null: not available
+    bool started = false;
+    uint64_t *late = nullptr;
+    uint32_t *late_count = nullptr;
+};
+
+int32_t *device_visible_host(const void *p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? static_cast<int32_t *>(at.devicePointer) : nullptr;
+}
+
+// `a` suffixes of `total` are still unresolved: start the copy of src[0..count) -> dst if it has not started and the
+// rest is small.  The late list can take `a` entries.
+int early_copy_maybe_start(dq_ctx *ctx, EarlyCopy &ec, const int32_t *src, int32_t *dst, uint32_t count, uint32_t a,
+                           uint32_t total)
+{
+    const char *e = getenv("DQ_EARLY_COPY_MIN");  // tests lower it; 0 = never
+    const uint32_t min_total = e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 20);
+    if (ec.started || !ec.host_sa || a == 0 || (uint64_t)a * 8 > total || total < min_total || min_total == 0) return DQ_OK;
+    DQ_TRY(ensure(ctx, ctx->late, (size_t)a * 8 + 256));
+    ec.late_count = ctx->late.as<uint32_t>();
+    ec.late = reinterpret_cast<uint64_t *>(ctx->late.as<uint8_t>() + 256);
+    DQ_CK(ctx, cudaMemsetAsync(ec.late_count, 0, 4, ctx->stream));
+    DQ_CK(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    DQ_CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    if (count) DQ_CK(ctx, cudaMemcpyAsync(dst, src, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ec.started = true;
+    return DQ_OK;
+}
+
+// after the last round: wait for the copy, then patch the late slots into the host array
+int early_copy_finish(dq_ctx *ctx, EarlyCopy &ec)
+{
+    if (!ec.started) return DQ_OK;
+    DQ_CK(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    DQ_CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    auto k = sx::patch_host_sa_kernel;
+    DQ_LAUNCH(k, (uint32_t)ctx->sm_count * 4, 256, 0, ctx->stream, ec.late, ec.late_count, ec.host_sa);
+    ctx->stats.kernel_launches++;
+    DQ_CK(ctx, cudaGetLastError());
+    return DQ_OK;
 }
 
 // ctx->text holds n bytes followed by >= 16 zero bytes.  Produces ctx->sa (the suffix array) and ctx->isa.
@@ -381,8 +436,13 @@ int build_prefix3_sorted(dq_ctx *ctx, const uint64_t *sorted_keys, uint32_t n)
     return DQ_OK;
 }
 
-int sort_resident(dq_ctx *ctx, uint32_t n)
+// host_sa_out: when not null, the caller's host array (it must be device-visible, see EarlyCopy) receives the suffix
+// array here -- overlapped with the last rounds when they are small -- and *delivered says so
+int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool *delivered = nullptr)
 {
+    if (delivered) *delivered = false;
+    EarlyCopy ec{};
+    ec.host_sa = device_visible_host(host_sa_out);
     dq_stats &st = ctx->stats;
     st = dq_stats{};
     st.n = (int32_t)n;
@@ -498,6 +558,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     }
     bool first = true;
     while (a > 0) {
+        DQ_TRY(early_copy_maybe_start(ctx, ec, ctx->sa.as<int32_t>(), host_sa_out, n, a, n));
         // active set: sa = s.vout, rank = (uint32*)s.kout, slot = slot_cur, depth = depth_cur.  Keys go to s.kin.
         rx::PassPlan rp{};
         rx::plan_add_field(rp, 0, (first && run_aware) ? 32 : bits_r2);
@@ -525,7 +586,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
 
         uint32_t next_a = 0, min_depth = 0;
         DQ_TRY(run_rank<false>(ctx, s.kin, s.vin, slot_cur, a, n, s.vout, reinterpret_cast<uint32_t *>(s.kout), slot_nxt,
-                               &next_a, depth_cur, depth_nxt, (uint32_t)h, &min_depth));
+                               &next_a, depth_cur, depth_nxt, (uint32_t)h, &min_depth, ec.late, ec.late_count));
         std::swap(slot_cur, slot_nxt);
         std::swap(depth_cur, depth_nxt);
         if (next_a > a) {
@@ -553,6 +614,10 @@ int sort_resident(dq_ctx *ctx, uint32_t n)
     }
     st.algorithmic_bytes += (int64_t)n * 4;
     DQ_CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (ec.started) {
+        DQ_TRY(early_copy_finish(ctx, ec));
+        if (delivered) *delivered = true;
+    }
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     DQ_CK(ctx, cudaEventElapsedTime(&st.device_ms, ctx->ev0, ctx->ev1));
     if (ctx->timing) {
@@ -619,7 +684,7 @@ int destroy_single(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
-                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->packed, &ctx->newtext, &ctx->s_pos,
+                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->packed, &ctx->late, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -637,6 +702,7 @@ int destroy_single(dq_ctx *ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_index) cudaEventDestroy(ctx->ev_index);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     for (int i = 0; i < 8; ++i) {
         if (ctx->slice_ready[i]) cudaEventDestroy(ctx->slice_ready[i]);
         if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
@@ -682,6 +748,7 @@ int create_single(dq_ctx **out, int dev)
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_index)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void **)&ctx->h_count, 64, cudaHostAllocDefault)) != cudaSuccess)
         return fail("cudaHostAlloc", e);
     if ((e = cudaFuncSetAttribute(rx::onesweep_pass_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -829,8 +896,9 @@ int dq_cuda_suffix_sort(dq_ctx *ctx, const uint8_t *text, int32_t n, int32_t *sa
         if ((uint32_t)n >= ctx->group->shard_min) return group_sort(ctx, text, (uint32_t)n, sa_out);
     }
     DQ_TRY(upload_text(ctx, ctx->text, text, (uint32_t)n, cudaMemcpyHostToDevice));
-    DQ_TRY(sort_resident(ctx, (uint32_t)n));
-    if (n) DQ_CK(ctx, cudaMemcpyAsync(sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    bool delivered = false;
+    DQ_TRY(sort_resident(ctx, (uint32_t)n, sa_out, &delivered));
+    if (n && !delivered) DQ_CK(ctx, cudaMemcpyAsync(sa_out, ctx->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->resident_n = n;
     ctx->resident_rounds = ctx->stats.rounds;

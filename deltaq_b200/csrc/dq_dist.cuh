@@ -55,28 +55,36 @@ struct BucketPolicy {
     }
 };
 
+// The exchanges by POSITION (requests and updates) partition finer than by owner: the digit is the owner followed by
+// the next `sb` bits of the position, so that every owner receives its run ordered by sub-range of its ISA slice.  The
+// owner then gathers / scatters one sub-range at a time -- a window that fits the L2 -- instead of hitting its whole
+// slice at random (at 256 MiB of text per GPU that is the difference between DRAM-sector-bound and streaming).  The
+// pass costs the same whatever the number of digits.
+//
 // active element = (rank << 32 | sa)
 struct RequestPolicy {
     static constexpr bool kHasVal = false;
-    uint64_t *kout;              // local: the active set regrouped by position owner
+    uint64_t *kout;              // local: the active set regrouped by position owner (and sub-range)
     uint32_t *qout[kMaxShards];  // this source's region of owner d's request inbox (peer memory)
     const uint32_t *gbase;       // local exclusive digit offsets (the pass's own gbase)
     uint64_t h;
     uint32_t n;
-    int kb;
+    int kb;                      // owner = position >> kb
+    int sb;                      // sub-range bits: digit = position >> (kb - sb)
     uint32_t self;
     int bits;
     __device__ __forceinline__ uint32_t digit(uint64_t key) const
     {
         const uint64_t q = (uint64_t)(uint32_t)key + h;
-        return q < n ? (uint32_t)(q >> kb) : self;
+        return q < n ? (uint32_t)(q >> (kb - sb)) : (self << sb);
     }
     __device__ __forceinline__ int nbits() const { return bits; }
     __device__ __forceinline__ void store(uint32_t d, uint32_t dst, uint64_t key, uint32_t) const
     {
         kout[dst] = key;
         const uint64_t q = (uint64_t)(uint32_t)key + h;
-        qout[d][dst - gbase[d]] = q < n ? (uint32_t)(q - ((uint64_t)d << kb)) : kPastEnd;
+        const uint32_t o = d >> sb;
+        qout[o][dst - gbase[o << sb]] = q < n ? (uint32_t)(q - ((uint64_t)o << kb)) : kPastEnd;
     }
 };
 
@@ -86,23 +94,25 @@ struct UpdatePolicy {
     uint64_t *uout[kMaxShards];  // this source's region of owner d's update inbox (peer memory)
     const uint32_t *gbase;
     int kb;
+    int sb;
     int bits;
-    __device__ __forceinline__ uint32_t digit(uint64_t key) const { return (uint32_t)key >> kb; }
+    __device__ __forceinline__ uint32_t digit(uint64_t key) const { return (uint32_t)key >> (kb - sb); }
     __device__ __forceinline__ int nbits() const { return bits; }
     __device__ __forceinline__ void store(uint32_t d, uint32_t dst, uint64_t key, uint32_t) const
     {
-        uout[d][dst - gbase[d]] = key - ((uint64_t)d << kb);
+        const uint32_t o = d >> sb;
+        uout[o][dst - gbase[o << sb]] = key - ((uint64_t)o << kb);
     }
 };
 
-// counts of the policy's digits over keys[0..count) -> ghist[0..256) (zero before the launch).  The digits are few
-// (<= kMaxShards), so equal digits inside a warp are merged before they touch the shared counters.
+// counts of the policy's digits over keys[0..count) -> ghist[0..256) (zero before the launch).  Neighbouring keys
+// often share a digit, so equal digits inside a warp are merged before they touch the shared counters.
 template <typename Policy>
 __global__ void __launch_bounds__(256)
 hist_policy_kernel(const uint64_t *__restrict__ keys, uint32_t count, const Policy pol, uint32_t *__restrict__ ghist)
 {
-    __shared__ uint32_t sh[kMaxShards];
-    if (threadIdx.x < kMaxShards) sh[threadIdx.x] = 0;
+    __shared__ uint32_t sh[radix::kRadix];
+    sh[threadIdx.x] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (count + stride - 1) / stride;
@@ -114,7 +124,7 @@ hist_policy_kernel(const uint64_t *__restrict__ keys, uint32_t count, const Poli
         if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&sh[d], (uint32_t)__popc(peers));
     }
     __syncthreads();
-    if (threadIdx.x < kMaxShards && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+    if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
 }
 
 // what a destination needs to know about one source's run in its inbox
@@ -130,12 +140,17 @@ struct ReplyPtrs {
     uint32_t *p[kMaxShards];  // shard s's reply array (peer memory)
 };
 
-// after the digit scan: tell every destination d how many entries this source sends it.  One warp.
-__global__ void publish_meta_kernel(const uint32_t *__restrict__ ghist, const uint32_t *__restrict__ gbase,
-                                    const MetaPtrs meta_of, uint32_t self, uint32_t shards)
+// after the digit scan: tell every destination d how many entries this source sends it (the digits of owner d are
+// [d << sb, (d + 1) << sb); total = all entries of the pass).  One warp.
+__global__ void publish_meta_kernel(const uint32_t *__restrict__ gbase, uint32_t total, const MetaPtrs meta_of,
+                                    uint32_t self, uint32_t shards, int sb)
 {
     const unsigned d = threadIdx.x;
-    if (d < shards) meta_of.p[d][self] = RunMeta{ghist[d], gbase[d]};
+    if (d < shards) {
+        const uint32_t lo = gbase[d << sb];
+        const uint32_t hi = ((d + 1u) << sb) < (uint32_t)radix::kRadix ? gbase[(d + 1u) << sb] : total;
+        meta_of.p[d][self] = RunMeta{hi - lo, lo};
+    }
 }
 
 // sampled keys of a slice, for the splitters: element = a fixed odd multiplier walk over the slice's key array

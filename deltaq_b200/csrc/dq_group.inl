@@ -172,7 +172,7 @@ uint32_t light_grid(const dq_ctx *c, uint64_t items)
 // the destinations' meta arrays.  Leaves gbase/use_match in c->hist as run_passes does for pass 0.
 template <typename Policy>
 int digit_counts(dq_ctx *top, Shard &s, const uint64_t *keys, uint32_t count, const Policy &pol, bool publish,
-                 bool to_requests)
+                 bool to_requests, int sb = 0)
 {
     dq_ctx *c = s.c;
     Group &g = *top->group;
@@ -192,7 +192,7 @@ int digit_counts(dq_ctx *top, Shard &s, const uint64_t *keys, uint32_t count, co
         for (size_t d = 0; d < g.sh.size(); ++d)
             mp.p[d] = (to_requests ? g.sh[d].meta_req : g.sh[d].meta_upd).as<ds::RunMeta>();
         auto k = ds::publish_meta_kernel;
-        DQ_LAUNCH(k, 1, 32, 0, c->stream, ghist, gbase, mp, (uint32_t)(&s - &g.sh[0]), (uint32_t)g.sh.size());
+        DQ_LAUNCH(k, 1, 32, 0, c->stream, gbase, count, mp, (uint32_t)(&s - &g.sh[0]), (uint32_t)g.sh.size(), sb);
         c->stats.kernel_launches++;
     }
     DQ_CK(top, cudaGetLastError());
@@ -228,6 +228,16 @@ int bits_for(size_t shards)
     return b;
 }
 
+// sub-range bits of the exchanges by position (dq_dist.cuh): owner digits are padded to a power of two, the rest of
+// the 8 digit bits splits every owner's slice -- but never finer than 64 K positions (256 KiB of ISA) per sub-range
+int sub_bits(size_t shards, int kb)
+{
+    const int sb = rx::kRadixBits - bits_for(shards);
+    const char *e = getenv("DQ_SUB_MIN_LOG");  // tests: lets small texts use sub-ranges
+    const int min_log = e ? atoi(e) : 16;
+    return std::max(0, std::min(sb, kb - min_log));
+}
+
 // (rank << 32 | position) updates of every shard -> the position owners' ISA slices
 int group_route_updates(dq_ctx *top, const std::vector<uint32_t> &counts)
 {
@@ -242,8 +252,9 @@ int group_route_updates(dq_ctx *top, const std::vector<uint32_t> &counts)
         for (size_t d = 0; d < G; ++d) pol.uout[d] = g.sh[d].inbox_upd.as<uint64_t>() + (size_t)i * cap;
         pol.gbase = s.c->hist.as<uint32_t>() + rx::kMaxPasses * rx::kRadix;
         pol.kb = g.kb;
-        pol.bits = bits_for(G);
-        DQ_TRY(digit_counts(top, s, s.upd.as<uint64_t>(), counts[i], pol, true, false));
+        pol.sb = sub_bits(G, g.kb);
+        pol.bits = bits_for(G) + pol.sb;
+        DQ_TRY(digit_counts(top, s, s.upd.as<uint64_t>(), counts[i], pol, true, false, pol.sb));
         DQ_TRY(policy_pass(top, s, s.upd.as<uint64_t>(), nullptr, pol, counts[i]));
     }
     DQ_TRY(group_barrier(top));
@@ -457,6 +468,22 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         if (s.cnt) DQ_SUB(top, s.c, finish_rank(s.c, &s.a, nullptr));
         total_active += s.a;
     }
+    // early copy (deltaq_cuda.cu, EarlyCopy): every bucket starts towards its part of the host array as soon as few of
+    // its suffixes are unresolved; the slots resolved later are patched in at the end
+    std::vector<EarlyCopy> ec(G);
+    int32_t *host_sa = device_visible_host(sa_out);
+    for (EarlyCopy &e : ec) e.host_sa = host_sa;
+    auto start_early_copies = [&]() -> int {
+        for (size_t i = 0; i < G; ++i) {
+            Shard &s = g.sh[i];
+            if (!s.cnt || !sa_out) continue;
+            DQ_CK(top, cudaSetDevice(s.c->device));
+            DQ_SUB(top, s.c, early_copy_maybe_start(s.c, ec[i], s.sa_local.as<int32_t>(), sa_out + s.slot_base, s.cnt, s.a,
+                                                    s.cnt));
+        }
+        return DQ_OK;
+    };
+    DQ_TRY(start_early_copies());
     st.rounds = 1;
     st.active_sum = n;
     st.algorithmic_bytes = (int64_t)n * (41 + 24 * plan0.npass);
@@ -471,6 +498,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     rx::plan_add_field(rp, 32, bits_rank);
     uint64_t h = key_chars;
     while (total_active > 0) {
+        DQ_TRY(start_early_copies());
         if (total_active <= g.direct_max) {
             // ---- a small round: ISA read and written through peer pointers (dq_dist.cuh, "small rounds")
             DQ_TRY(group_barrier(top));  // every rank written so far is in place
@@ -499,7 +527,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
                 SortBufs &b = sorted[i];
                 DQ_SUB(top, c, (enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
                                                           s.sa_local.as<int32_t>(), s.slot_base, nullptr, b.kout, nullptr,
-                                                          nullptr, 0, peers)));
+                                                          nullptr, 0, peers, ec[i].late, ec[i].late_count)));
                 std::swap(s.slot_cur, s.slot_nxt);
                 s.act = b.kout;
                 s.other = b.kin;
@@ -542,9 +570,10 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             pol.h = h;
             pol.n = n;
             pol.kb = kb;
+            pol.sb = sub_bits(G, kb);
             pol.self = (uint32_t)i;
-            pol.bits = bits_for(G);
-            DQ_TRY(digit_counts(top, s, s.act, s.a, pol, true, true));
+            pol.bits = bits_for(G) + pol.sb;
+            DQ_TRY(digit_counts(top, s, s.act, s.a, pol, true, true, pol.sb));
             DQ_TRY(policy_pass(top, s, s.act, nullptr, pol, s.a));
         }
         DQ_TRY(group_barrier(top));
@@ -580,7 +609,8 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             SortBufs b{keys, s.other, c->valA.as<uint32_t>(), c->valB.as<uint32_t>()};
             DQ_SUB(top, c, run_passes(c, b, s.a, rp, true));
             DQ_SUB(top, c, (enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
-                                              s.sa_local.as<int32_t>(), s.slot_base, s.upd.as<uint64_t>(), b.kout)));
+                                              s.sa_local.as<int32_t>(), s.slot_base, s.upd.as<uint64_t>(), b.kout, nullptr,
+                                              nullptr, 0, sx::PeerIsa{}, ec[i].late, ec[i].late_count)));
             std::swap(s.slot_cur, s.slot_nxt);
             s.act = b.kout;
             s.other = b.kin;
@@ -616,10 +646,14 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
 
     // ---- the buckets are the suffix array
     if (sa_out) {
-        for (Shard &s : g.sh) {
+        for (size_t i = 0; i < G; ++i) {
+            Shard &s = g.sh[i];
             if (s.cnt == 0) continue;
             DQ_CK(top, cudaSetDevice(s.c->device));
-            DQ_CK(top, cudaMemcpyAsync(sa_out + s.slot_base, s.sa_local.p, (size_t)s.cnt * 4, cudaMemcpyDefault, s.c->stream));
+            if (ec[i].started)
+                DQ_SUB(top, s.c, early_copy_finish(s.c, ec[i]));
+            else
+                DQ_CK(top, cudaMemcpyAsync(sa_out + s.slot_base, s.sa_local.p, (size_t)s.cnt * 4, cudaMemcpyDefault, s.c->stream));
         }
     }
     DQ_TRY(group_sync(top));

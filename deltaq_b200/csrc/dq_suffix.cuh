@@ -406,7 +406,8 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     uint32_t *__restrict__ count_out, uint32_t slot_base = 0, uint64_t *__restrict__ upd = nullptr,
                     uint64_t *__restrict__ act_out = nullptr, const uint32_t *__restrict__ depth_in = nullptr,
                     uint32_t *__restrict__ depth_out = nullptr, uint32_t hmin = 0,
-                    uint32_t *__restrict__ min_depth_inv = nullptr, const PeerIsa peer_isa = PeerIsa{})
+                    uint32_t *__restrict__ min_depth_inv = nullptr, const PeerIsa peer_isa = PeerIsa{},
+                    uint64_t *__restrict__ late = nullptr, uint32_t *__restrict__ late_count = nullptr)
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_wmax[kRankWarps], s_wsum[kRankWarps];
@@ -572,6 +573,17 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                 if (!DIST) ISA[s[j]] = nr;
             }
         }
+        if (!ROUND0 && late) {
+            // the suffix array is already on its way to the host (see sort_resident, "early copy"): slots resolved from
+            // now on are listed as (slot << 32 | suffix) and patched into the host array once that copy has landed
+            const unsigned rb = vb[j] & ~sb[j];
+            if (rb) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(late_count, (uint32_t)__popc(rb));
+                base = __shfl_sync(kFullMask, base, 0);
+                if ((rb >> lane) & 1u) late[base + __popc(rb & lanemask_lt())] = ((uint64_t)sl[j] << 32) | s[j];
+            }
+        }
         out += __popc(sb[j]);
         if (hm) carry = __shfl_sync(kFullMask, sl[j], 31 - __clz((int)hm));
     }
@@ -579,6 +591,18 @@ rank_compact_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         // smallest depth among the unresolved groups = the depth every rank is consistent to next round
         inv_min = __reduce_max_sync(kFullMask, inv_min);
         if (lane == 0 && inv_min) atomicMax(min_depth_inv, inv_min);
+    }
+}
+
+// host_sa[slot] = suffix for every listed pair: host_sa is pinned host memory mapped into the device's address space
+__global__ void __launch_bounds__(256) patch_host_sa_kernel(const uint64_t *__restrict__ late,
+                                                            const uint32_t *__restrict__ late_count,
+                                                            int32_t *__restrict__ host_sa)
+{
+    const uint32_t cnt = *late_count;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = late[i];
+        host_sa[(uint32_t)(v >> 32)] = (int32_t)(uint32_t)v;
     }
 }
 

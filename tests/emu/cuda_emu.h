@@ -51,6 +51,8 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDe
 enum { cudaStreamNonBlocking = 1, cudaHostRegisterDefault = 0, cudaHostAllocDefault = 0, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
 struct cudaDeviceProp { char name[256]; int multiProcessorCount; size_t totalGlobalMem; int major, minor; };
 
 namespace emu {
@@ -309,6 +311,8 @@ static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+// every buffer of the emulator is host memory the "device" can address
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) { a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = const_cast<void *>(p); a->hostPointer = const_cast<void *>(p); return cudaSuccess; }
 static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }

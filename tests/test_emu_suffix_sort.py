@@ -84,3 +84,34 @@ def test_small_alphabets(sorter, name, monkeypatch):
     sorter.sort(t, sa[:t.size])
     assert sa[t.size] == -7
     assert np.array_equal(sa[:t.size], oracle.sais(t))
+
+
+def _texts_with_repeats():
+    """Mostly-unique texts with a few per cent inside tandem repeats: round 0 resolves most suffixes, a few rounds
+    finish the rest -- the shape that takes the early copy of the suffix array (deltaq_cuda.cu, EarlyCopy)."""
+    rng = np.random.default_rng(9)
+
+    def make(n, frac, alphabet):
+        t = rng.integers(0, alphabet, n, dtype=np.uint8)
+        budget = int(n * frac)
+        while budget > 0:
+            unit = int(rng.integers(2, 40))
+            total = int(min(budget, rng.integers(200, 3000)))
+            p = int(rng.integers(0, n - total - unit))
+            t[p:p + total] = np.tile(t[p:p + unit], total // unit + 1)[:total]
+            budget -= total
+        return t
+    return {"rep5pct_100k": make(100_000, 0.05, 256), "rep10pct_60k": make(60_000, 0.10, 256),
+            "rep1pct_acgt_80k": make(80_000, 0.01, 4), "rep30pct_50k": make(50_000, 0.30, 256)}
+
+
+@pytest.mark.parametrize("name", sorted(_texts_with_repeats()))
+def test_early_copy_of_the_suffix_array(sorter, name, monkeypatch):
+    monkeypatch.setenv("DQ_EARLY_COPY_MIN", "1")
+    monkeypatch.setenv("DQ_COMPACT_MIN", "1")
+    t = _texts_with_repeats()[name]
+    with sorter.sort(t) as owner:                      # pinned host memory: the device can patch it
+        assert np.array_equal(owner.memory, oracle.sais(t))
+    sa = np.full(t.size + 1, -7, dtype=np.int32)       # pageable memory: the plain copy at the end
+    sorter.sort(t, sa[:t.size])
+    assert sa[t.size] == -7 and np.array_equal(sa[:t.size], oracle.sais(t))

@@ -43,6 +43,8 @@ def _pairs():
 @pytest.fixture()
 def shard_everything(monkeypatch):
     monkeypatch.setenv("DQ_SHARD_MIN", "1")
+    monkeypatch.setenv("DQ_SUB_MIN_LOG", "3")   # sub-ranges of the position exchanges from 8 positions up
+    monkeypatch.setenv("DQ_EARLY_COPY_MIN", "1")  # early copy of the suffix array whatever the text length
 
 
 def _check_sort(sorter):
