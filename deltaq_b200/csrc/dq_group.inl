@@ -40,7 +40,37 @@ struct Group {
                                       // accesses instead of the request / reply / update exchanges (DQ_DIRECT_MAX)
     std::vector<GroupPhase> phases;
     std::chrono::steady_clock::time_point t_phase;
+    // one host thread per shard for the per-shard stretches of a round (launches are cheap for the GPU and dear for one
+    // host thread driving eight of them); null: the calling thread does everything (DQ_GROUP_THREADS=0, the emulator)
+    std::unique_ptr<dq::diffhost::Crew> crew;
 };
+
+// fn(i) for every shard i, side by side when the group has its crew; the first failure is reported through `top`
+template <typename F> int for_shards(dq_ctx *top, F &&fn)
+{
+    Group &g = *top->group;
+    const size_t G = g.sh.size();
+    std::vector<int> rc(G, DQ_OK);
+    auto body = [&](int part) {
+        const size_t i = (size_t)part;
+        if (cudaSetDevice(g.sh[i].c->device) != cudaSuccess) {
+            g.sh[i].c->err = "cudaSetDevice failed";
+            rc[i] = DQ_ERR_CUDA;
+            return;
+        }
+        rc[i] = fn(i);
+    };
+    if (g.crew)
+        g.crew->run(body);
+    else
+        for (size_t i = 0; i < G; ++i) body((int)i);
+    for (size_t i = 0; i < G; ++i)
+        if (rc[i] != DQ_OK) {
+            if (g.sh[i].c != top) top->err = g.sh[i].c->err;
+            return rc[i];
+        }
+    return DQ_OK;
+}
 
 constexpr uint32_t kSamplesPerShard = 2048;
 
@@ -72,6 +102,7 @@ void destroy_group(dq_ctx *top)
         if (s.h_samples) cudaFreeHost(s.h_samples);
         if (i > 0) destroy_single(s.c);
     }
+    g->crew.reset();
     delete g;
     top->group = nullptr;
 }
@@ -84,6 +115,12 @@ int create_group(dq_ctx *top, const int *devices, int ndev)
     top->group = g;
     if (const char *e = getenv("DQ_SHARD_MIN")) g->shard_min = (uint32_t)strtoul(e, nullptr, 10);
     if (const char *e = getenv("DQ_DIRECT_MAX")) g->direct_max = strtoull(e, nullptr, 10);
+#ifndef DQ_EMU
+    {
+        const char *e = getenv("DQ_GROUP_THREADS");
+        if (!e || atoi(e) != 0) g->crew.reset(new dq::diffhost::Crew(ndev - 1));
+    }
+#endif
     g->sh.resize((size_t)ndev);
     g->sh[0].c = top;
     for (int i = 1; i < ndev; ++i) {
@@ -171,12 +208,11 @@ uint32_t light_grid(const dq_ctx *c, uint64_t items)
 // counts of pol's digits over keys[0..count), their exclusive scan, and the (count, base) of every run published to
 // the destinations' meta arrays.  Leaves gbase/use_match in c->hist as run_passes does for pass 0.
 template <typename Policy>
-int digit_counts(dq_ctx *top, Shard &s, const uint64_t *keys, uint32_t count, const Policy &pol, bool publish,
+int digit_counts(Group &g, Shard &s, const uint64_t *keys, uint32_t count, const Policy &pol, bool publish,
                  bool to_requests, int sb = 0)
 {
     dq_ctx *c = s.c;
-    Group &g = *top->group;
-    DQ_SUB(top, c, zero_hist(c));
+    DQ_TRY(zero_hist(c));
     uint32_t *ghist = c->hist.as<uint32_t>();
     uint32_t *gbase = ghist + rx::kMaxPasses * rx::kRadix;
     uint32_t *use_match = gbase + rx::kMaxPasses * rx::kRadix;
@@ -195,13 +231,13 @@ int digit_counts(dq_ctx *top, Shard &s, const uint64_t *keys, uint32_t count, co
         DQ_LAUNCH(k, 1, 32, 0, c->stream, gbase, count, mp, (uint32_t)(&s - &g.sh[0]), (uint32_t)g.sh.size(), sb);
         c->stats.kernel_launches++;
     }
-    DQ_CK(top, cudaGetLastError());
+    DQ_CK(c, cudaGetLastError());
     return DQ_OK;
 }
 
 // one partition + exchange pass (dq_radix.cuh, onesweep_policy_kernel)
 template <typename Policy>
-int policy_pass(dq_ctx *top, Shard &s, const uint64_t *kin, const uint32_t *vin, const Policy &pol, uint32_t count)
+int policy_pass(Shard &s, const uint64_t *kin, const uint32_t *vin, const Policy &pol, uint32_t count)
 {
     if (count == 0) return DQ_OK;
     dq_ctx *c = s.c;
@@ -209,15 +245,15 @@ int policy_pass(dq_ctx *top, Shard &s, const uint64_t *kin, const uint32_t *vin,
     uint32_t *use_match = gbase + rx::kMaxPasses * rx::kRadix;
     const uint32_t tiles = (uint32_t)div_up(count, rx::kTile);
     const size_t bytes = 256 + (size_t)tiles * rx::kRadix * 4;
-    DQ_SUB(top, c, ensure(c, c->lb, bytes));
+    DQ_TRY(ensure(c, c->lb, bytes));
     uint8_t *lbp = c->lb.as<uint8_t>();
-    DQ_CK(top, cudaMemsetAsync(lbp, 0, bytes, c->stream));
+    DQ_CK(c, cudaMemsetAsync(lbp, 0, bytes, c->stream));
     auto k = rx::onesweep_policy_kernel<Policy>;
     DQ_LAUNCH(k, tiles, rx::kThreads, rx::pass_smem_bytes(), c->stream, kin, vin, pol, count, gbase,
               reinterpret_cast<uint32_t *>(lbp + 256), reinterpret_cast<uint32_t *>(lbp), use_match);
     c->stats.kernel_launches++;
     c->stats.radix_passes++;
-    DQ_CK(top, cudaGetLastError());
+    DQ_CK(c, cudaGetLastError());
     return DQ_OK;
 }
 
@@ -245,29 +281,29 @@ int group_route_updates(dq_ctx *top, const std::vector<uint32_t> &counts)
     const size_t G = g.sh.size();
     uint32_t cap = 0;
     for (Shard &s : g.sh) cap = std::max(cap, s.cnt);
-    for (size_t i = 0; i < G; ++i) {
+    const int sb = sub_bits(G, g.kb);
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
         Shard &s = g.sh[i];
-        DQ_CK(top, cudaSetDevice(s.c->device));
         ds::UpdatePolicy pol{};
         for (size_t d = 0; d < G; ++d) pol.uout[d] = g.sh[d].inbox_upd.as<uint64_t>() + (size_t)i * cap;
         pol.gbase = s.c->hist.as<uint32_t>() + rx::kMaxPasses * rx::kRadix;
         pol.kb = g.kb;
-        pol.sb = sub_bits(G, g.kb);
-        pol.bits = bits_for(G) + pol.sb;
-        DQ_TRY(digit_counts(top, s, s.upd.as<uint64_t>(), counts[i], pol, true, false, pol.sb));
-        DQ_TRY(policy_pass(top, s, s.upd.as<uint64_t>(), nullptr, pol, counts[i]));
-    }
+        pol.sb = sb;
+        pol.bits = bits_for(G) + sb;
+        DQ_TRY(digit_counts(g, s, s.upd.as<uint64_t>(), counts[i], pol, true, false, sb));
+        return policy_pass(s, s.upd.as<uint64_t>(), nullptr, pol, counts[i]);
+    }));
     DQ_TRY(group_barrier(top));
-    for (Shard &s : g.sh) {
-        if (s.own_cnt == 0) continue;
-        DQ_CK(top, cudaSetDevice(s.c->device));
+    return for_shards(top, [&](size_t i) -> int {
+        Shard &s = g.sh[i];
+        if (s.own_cnt == 0) return DQ_OK;
         auto k = ds::apply_kernel;
         DQ_LAUNCH(k, (uint32_t)s.c->sm_count * 8, 256, 0, s.c->stream, s.inbox_upd.as<uint64_t>(), cap,
                   s.meta_upd.as<ds::RunMeta>(), s.isa_local.as<uint32_t>(), (uint32_t)G);
         s.c->stats.kernel_launches++;
-    }
-    DQ_CK(top, cudaGetLastError());
-    return DQ_OK;
+        DQ_CK(s.c, cudaGetLastError());
+        return DQ_OK;
+    });
 }
 
 // Sorts the n-byte text at `text` (host memory, or device memory of any GPU of the group: the copies are
@@ -382,7 +418,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     bp.bits = bits_for(G);
     for (Shard &s : g.sh) {
         DQ_CK(top, cudaSetDevice(s.c->device));
-        DQ_TRY(digit_counts(top, s, s.c->partK.as<uint64_t>(), s.own_cnt, bp, false, false));
+        DQ_SUB(top, s.c, digit_counts(g, s, s.c->partK.as<uint64_t>(), s.own_cnt, bp, false, false));
         DQ_CK(top, cudaMemcpyAsync(s.h_small, s.c->hist.p, ds::kMaxShards * 4, cudaMemcpyDeviceToHost, s.c->stream));
     }
     DQ_TRY(group_sync(top));
@@ -426,7 +462,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             for (size_t j = i + 1; j < G; ++j) off[d] += g.sh[j].h_small[d];
         uint32_t *gbase = c->hist.as<uint32_t>() + rx::kMaxPasses * rx::kRadix;
         DQ_CK(top, cudaMemcpyAsync(gbase, off, sizeof off, cudaMemcpyHostToDevice, c->stream));
-        DQ_TRY(policy_pass(top, s, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), bp, s.own_cnt));
+        DQ_SUB(top, c, policy_pass(s, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), bp, s.own_cnt));
     }
     DQ_TRY(group_barrier(top));
     DQ_TRY(group_mark(top, "r0_partition_exchange"));
@@ -503,52 +539,47 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             // ---- a small round: ISA read and written through peer pointers (dq_dist.cuh, "small rounds")
             DQ_TRY(group_barrier(top));  // every rank written so far is in place
             std::vector<SortBufs> sorted(G);
-            for (size_t i = 0; i < G; ++i) {
+            DQ_TRY(for_shards(top, [&](size_t i) -> int {
                 Shard &s = g.sh[i];
                 dq_ctx *c = s.c;
                 entered[i] = s.a;
-                if (s.a == 0) continue;
-                DQ_CK(top, cudaSetDevice(c->device));
-                DQ_SUB(top, c, zero_hist(c));
+                if (s.a == 0) return DQ_OK;
+                DQ_TRY(zero_hist(c));
                 auto k = ds::build_keys_peer_kernel;
                 DQ_LAUNCH(k, producer_grid(c, s.a), sx::kPackThreads, rp.npass * rx::kRadix * 4, c->stream, s.act, s.a,
                           parts, n, h, s.other, c->valA.as<uint32_t>(), rp, c->hist.as<uint32_t>());
                 c->stats.kernel_launches++;
                 SortBufs b{s.other, s.act, c->valA.as<uint32_t>(), c->valB.as<uint32_t>()};
-                DQ_SUB(top, c, run_passes(c, b, s.a, rp, true));
+                DQ_TRY(run_passes(c, b, s.a, rp, true));
                 sorted[i] = b;
-            }
+                return DQ_OK;
+            }));
             DQ_TRY(group_barrier(top));  // every read of this round is done before any rank changes
-            for (size_t i = 0; i < G; ++i) {
+            DQ_TRY(for_shards(top, [&](size_t i) -> int {
                 Shard &s = g.sh[i];
                 dq_ctx *c = s.c;
-                if (s.a == 0) continue;
-                DQ_CK(top, cudaSetDevice(c->device));
+                if (s.a == 0) return DQ_OK;
                 SortBufs &b = sorted[i];
-                DQ_SUB(top, c, (enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
-                                                          s.sa_local.as<int32_t>(), s.slot_base, nullptr, b.kout, nullptr,
-                                                          nullptr, 0, peers, ec[i].late, ec[i].late_count)));
+                DQ_TRY((enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
+                                                  s.sa_local.as<int32_t>(), s.slot_base, nullptr, b.kout, nullptr, nullptr, 0,
+                                                  peers, ec[i].late, ec[i].late_count)));
                 std::swap(s.slot_cur, s.slot_nxt);
                 s.act = b.kout;
                 s.other = b.kin;
-            }
+                uint32_t next_a = 0;
+                DQ_TRY(finish_rank(c, &next_a, nullptr));
+                if (next_a > s.a) {
+                    c->err = "internal: active set grew";
+                    return DQ_ERR_INTERNAL;
+                }
+                s.a = next_a;
+                return DQ_OK;
+            }));
             st.rounds++;
             st.active_sum += (int64_t)total_active;
             st.algorithmic_bytes += (int64_t)total_active * (52 + 24 * rp.npass);
             total_active = 0;
-            for (size_t i = 0; i < G; ++i) {
-                Shard &s = g.sh[i];
-                if (entered[i]) {
-                    uint32_t next_a = 0;
-                    DQ_SUB(top, s.c, finish_rank(s.c, &next_a, nullptr));
-                    if (next_a > s.a) {
-                        top->err = "internal: active set grew";
-                        return DQ_ERR_INTERNAL;
-                    }
-                    s.a = next_a;
-                }
-                total_active += s.a;
-            }
+            for (Shard &s : g.sh) total_active += s.a;
             DQ_TRY(group_mark(top, "small_rounds"));
             h *= 2;
             if (h > ((uint64_t)1 << 31)) h = (uint64_t)1 << 31;
@@ -559,10 +590,10 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             continue;
         }
         // requests: regroup the unresolved set by the owner of sa + h; the positions go to the owners' inboxes
-        for (size_t i = 0; i < G; ++i) {
+        const int sb = sub_bits(G, kb);
+        DQ_TRY(for_shards(top, [&](size_t i) -> int {
             Shard &s = g.sh[i];
             dq_ctx *c = s.c;
-            DQ_CK(top, cudaSetDevice(c->device));
             ds::RequestPolicy pol{};
             pol.kout = s.other;
             for (size_t d = 0; d < G; ++d) pol.qout[d] = g.sh[d].inbox_req.as<uint32_t>() + (size_t)i * cap;
@@ -570,36 +601,36 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             pol.h = h;
             pol.n = n;
             pol.kb = kb;
-            pol.sb = sub_bits(G, kb);
+            pol.sb = sb;
             pol.self = (uint32_t)i;
-            pol.bits = bits_for(G) + pol.sb;
-            DQ_TRY(digit_counts(top, s, s.act, s.a, pol, true, true, pol.sb));
-            DQ_TRY(policy_pass(top, s, s.act, nullptr, pol, s.a));
-        }
+            pol.bits = bits_for(G) + sb;
+            DQ_TRY(digit_counts(g, s, s.act, s.a, pol, true, true, sb));
+            return policy_pass(s, s.act, nullptr, pol, s.a);
+        }));
         DQ_TRY(group_barrier(top));
         // owners answer, in request order, into the requesters' reply arrays
         {
             ds::ReplyPtrs rp_{};
             for (size_t d = 0; d < G; ++d) rp_.p[d] = g.sh[d].reply.as<uint32_t>();
-            for (Shard &s : g.sh) {
-                DQ_CK(top, cudaSetDevice(s.c->device));
+            DQ_TRY(for_shards(top, [&](size_t i) -> int {
+                Shard &s = g.sh[i];
                 auto k = ds::reply_kernel;
                 DQ_LAUNCH(k, (uint32_t)s.c->sm_count * 8, 256, 0, s.c->stream, s.inbox_req.as<uint32_t>(), cap,
                           s.meta_req.as<ds::RunMeta>(), s.isa_local.as<uint32_t>(), rp_, (uint32_t)G);
                 s.c->stats.kernel_launches++;
-            }
-            DQ_CK(top, cudaGetLastError());
+                DQ_CK(s.c, cudaGetLastError());
+                return DQ_OK;
+            }));
         }
         DQ_TRY(group_barrier(top));
         DQ_TRY(group_mark(top, "rounds_fetch_isa"));
         // local: keys, sort, ranks
-        for (size_t i = 0; i < G; ++i) {
+        DQ_TRY(for_shards(top, [&](size_t i) -> int {
             Shard &s = g.sh[i];
             dq_ctx *c = s.c;
             entered[i] = s.a;
-            if (s.a == 0) continue;
-            DQ_CK(top, cudaSetDevice(c->device));
-            DQ_SUB(top, c, zero_hist(c));
+            if (s.a == 0) return DQ_OK;
+            DQ_TRY(zero_hist(c));
             // regrouped set is in s.other; keys go to s.act's buffer, values to valA
             uint64_t *keys = s.act;
             auto k = ds::build_keys_reply_kernel;
@@ -607,31 +638,27 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
                       s.reply.as<uint32_t>(), s.a, keys, c->valA.as<uint32_t>(), rp, c->hist.as<uint32_t>());
             c->stats.kernel_launches++;
             SortBufs b{keys, s.other, c->valA.as<uint32_t>(), c->valB.as<uint32_t>()};
-            DQ_SUB(top, c, run_passes(c, b, s.a, rp, true));
-            DQ_SUB(top, c, (enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
+            DQ_TRY(run_passes(c, b, s.a, rp, true));
+            DQ_TRY((enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
                                               s.sa_local.as<int32_t>(), s.slot_base, s.upd.as<uint64_t>(), b.kout, nullptr,
                                               nullptr, 0, sx::PeerIsa{}, ec[i].late, ec[i].late_count)));
             std::swap(s.slot_cur, s.slot_nxt);
             s.act = b.kout;
             s.other = b.kin;
-        }
+            uint32_t next_a = 0;
+            DQ_TRY(finish_rank(c, &next_a, nullptr));
+            if (next_a > s.a) {
+                c->err = "internal: active set grew";
+                return DQ_ERR_INTERNAL;
+            }
+            s.a = next_a;
+            return DQ_OK;
+        }));
         st.rounds++;
         st.active_sum += (int64_t)total_active;
         st.algorithmic_bytes += (int64_t)total_active * (52 + 24 * rp.npass);
         total_active = 0;
-        for (size_t i = 0; i < G; ++i) {
-            Shard &s = g.sh[i];
-            if (entered[i]) {
-                uint32_t next_a = 0;
-                DQ_SUB(top, s.c, finish_rank(s.c, &next_a, nullptr));
-                if (next_a > s.a) {
-                    top->err = "internal: active set grew";
-                    return DQ_ERR_INTERNAL;
-                }
-                s.a = next_a;
-            }
-            total_active += s.a;
-        }
+        for (Shard &s : g.sh) total_active += s.a;
         DQ_TRY(group_mark(top, "rounds_local_sort_rank"));
         DQ_TRY(group_route_updates(top, entered));
         DQ_TRY(group_mark(top, "rounds_route_updates"));
