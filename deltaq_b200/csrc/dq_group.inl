@@ -739,6 +739,69 @@ int group_replicate_index(dq_ctx *top)
     return DQ_OK;
 }
 
+// The search's index of `old` (LCP array, block minima, bucket and prefix tables) built by all shards: every shard
+// computes the LCP entries (and counts the 3-byte prefixes) of one text range into its own zeroed copy, the copies are
+// merged slice by slice through peer memory (dq_search.cuh, merge_copies_kernel), and every shard finishes its copy.
+// Needs text / SA / ISA complete on every shard (group_replicate_index, or adopt_index on every shard).
+int group_build_index(dq_ctx *top, uint32_t n)
+{
+    Group &g = *top->group;
+    const size_t G = g.sh.size();
+    bool all_valid = true;
+    for (Shard &s : g.sh) all_valid = all_valid && s.c->lcp_valid;
+    if (all_valid || n == 0) return DQ_OK;
+    const bool pre3 = want_prefix3(n);
+    // text ranges: whole supers, and whole warps of the seed level when that level runs (lcp_positions)
+    const uint32_t seeds = seeds_per_warp(g.sh[0].c, n, (uint32_t)div_up(n, sr::kSuper));
+    const uint64_t align = (uint64_t)sr::kSuper * std::max<uint32_t>(1, seeds);
+    const uint64_t per = div_up(div_up((uint64_t)n, G), align) * align;
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
+        dq_ctx *c = g.sh[i].c;
+        c->lcp_valid = false;
+        c->pre3_valid = false;
+        DQ_TRY(lcp_alloc(c, n));
+        DQ_CK(c, cudaMemsetAsync(c->lcp.p, 0, (size_t)n * 4, c->stream));
+        const uint64_t pb = std::min<uint64_t>(n, per * i), pe = std::min<uint64_t>(n, per * (i + 1));
+        DQ_TRY(lcp_positions(c, n, pb, pe));
+        if (pre3) DQ_TRY(prefix3_count(c, n, c->stream, pb, pe, true));
+        return DQ_OK;
+    }));
+    DQ_TRY(group_barrier(top));
+    sr::PeerArrays lcps{}, tabs{};
+    lcps.count = tabs.count = (int)G;
+    for (size_t d = 0; d < G; ++d) {
+        lcps.p[d] = g.sh[d].c->lcp.as<uint32_t>();
+        tabs.p[d] = g.sh[d].c->pre3.as<uint32_t>();
+    }
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
+        dq_ctx *c = g.sh[i].c;
+        const uint64_t sl = div_up((uint64_t)n, G);
+        const uint64_t b = std::min<uint64_t>(n, sl * i), e = std::min<uint64_t>(n, sl * (i + 1));
+        if (e > b) {
+            auto k = sr::merge_copies_kernel<false>;
+            DQ_LAUNCH(k, (uint32_t)c->sm_count * 8, 256, 0, c->stream, lcps, b, e);
+            c->stats.kernel_launches++;
+        }
+        if (pre3) {
+            const uint64_t ts = div_up((uint64_t)sr::kPrefix3Bins, G);
+            const uint64_t tb = std::min<uint64_t>(sr::kPrefix3Bins, ts * i), te = std::min<uint64_t>(sr::kPrefix3Bins, ts * (i + 1));
+            if (te > tb) {
+                auto k = sr::merge_copies_kernel<true>;
+                DQ_LAUNCH(k, (uint32_t)c->sm_count * 4, 256, 0, c->stream, tabs, tb, te);
+                c->stats.kernel_launches++;
+            }
+        }
+        DQ_CK(c, cudaGetLastError());
+        return DQ_OK;
+    }));
+    DQ_TRY(group_barrier(top));
+    return for_shards(top, [&](size_t i) -> int {
+        dq_ctx *c = g.sh[i].c;
+        if (pre3) DQ_TRY(prefix3_scan(c, n, c->stream));
+        return lcp_finish(c, n);
+    });
+}
+
 // Diff.Search for scan positions [scan_begin, scan_begin + count), sharded by new-data range: every shard answers a
 // contiguous share against its own copy of the index.  Needs group_replicate_index (or adopt on every shard) first.
 int group_search(dq_ctx *top, uint32_t n, const uint8_t *new_, uint32_t m, uint32_t scan_begin, uint32_t count,
@@ -818,5 +881,16 @@ int group_search_common(dq_ctx *top, const uint8_t *old_, int32_t n, const int32
     } else {
         DQ_TRY(group_replicate_index(top));
     }
+    // the index build spans all GPUs: timed on the host between two synchronisations, and added to the search's figures
+    DQ_TRY(group_sync(top));
+    const auto t0 = std::chrono::steady_clock::now();
+    DQ_TRY(group_build_index(top, (uint32_t)n));
+    DQ_TRY(group_sync(top));
+    const float index_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("DQ_TRACE")) fprintf(stderr, "[dq trace] group index build %.2f ms\n", index_ms);
+    DQ_TRY(group_search(top, (uint32_t)n, new_, (uint32_t)m, (uint32_t)scan_begin, (uint32_t)count, pos_out, len_out));
+    top->stats.search_index_ms += index_ms;
+    top->stats.search_ms += index_ms;
+    return DQ_OK;
     return group_search(top, (uint32_t)n, new_, (uint32_t)m, (uint32_t)scan_begin, (uint32_t)count, pos_out, len_out);
 }

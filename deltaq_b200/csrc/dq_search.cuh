@@ -770,15 +770,42 @@ __global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint8_t *__res
 // index of every 3-byte value is marked (one coalesced read of the keys) and the empty bins are filled from the right
 // (~0.06 ms) -- prefix3_mark_kernel + prefix3_fill_* below.
 __global__ void __launch_bounds__(256) prefix3_hist_kernel(const uint8_t *__restrict__ T, uint32_t n,
-                                                            uint32_t *__restrict__ hist)
+                                                            uint32_t *__restrict__ hist, uint64_t p_begin = 0,
+                                                            uint64_t p_end = ~0ull)
 {
-    const uint64_t total = n;  // every suffix; the text is zero padded, which is the padding the short ones need
-    const uint64_t span = (total + 31) & ~(uint64_t)31;  // whole warps: the match below is warp-wide
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < span; p += (uint64_t)gridDim.x * blockDim.x) {
+    // suffixes [p_begin, min(p_end, n)); the text is zero padded, which is the padding the short ones need
+    const uint64_t total = p_end < n ? p_end : n;
+    const uint64_t span = p_begin + ((total - min(total, p_begin) + 31) & ~(uint64_t)31);  // whole warps: the match below is warp-wide
+    for (uint64_t p = p_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < span; p += (uint64_t)gridDim.x * blockDim.x) {
         const bool valid = p < total;
         const uint32_t key = valid ? (((uint32_t)T[p] << 16) | ((uint32_t)T[p + 1] << 8) | T[p + 2]) : (0xff000000u + lane_id());
         const unsigned same = __match_any_sync(kFullMask, key);
         if (valid && (unsigned)(__ffs((int)same) - 1) == lane_id()) atomicAdd(hist + key, (uint32_t)__popc(same));
+    }
+}
+
+// ---- a device group builds the index by text range (dq_group.inl, group_build_index) -----------------------------
+// Every shard has filled, in its own zero-initialised copy of an array, the entries its text range produced; shard s
+// then combines elements [begin, end) of all copies (max for LCP values, sum for counts) and writes the result into
+// every copy.  Reads and writes of peer copies are plain coalesced loads and stores over NVLink.
+struct PeerArrays {
+    uint32_t *p[16];
+    int count;
+};
+template <bool SUM>
+__global__ void __launch_bounds__(256) merge_copies_kernel(const PeerArrays arr, uint64_t begin, uint64_t end)
+{
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < arr.count) {
+                const uint32_t x = arr.p[k][i];
+                v = SUM ? v + x : max(v, x);
+            }
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < arr.count) arr.p[k][i] = v;
     }
 }
 
@@ -1000,11 +1027,12 @@ __global__ void __launch_bounds__(kThreads)
 lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
                  const uint32_t *__restrict__ ISA, uint32_t *__restrict__ out_l,
                  const uint32_t *__restrict__ run_end, uint32_t stride, uint32_t per_warp,
-                 const uint32_t *__restrict__ seed_l)
+                 const uint32_t *__restrict__ seed_l, uint64_t w_begin = 0, uint64_t w_end = ~0ull)
 {
-    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // [w_begin, w_end): the warps of this launch (a device group builds the array by text range, dq_group.inl)
+    const uint64_t w = w_begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint64_t i0 = w * stride * per_warp;
-    if (i0 >= n) return;
+    if (w >= w_end || i0 >= n) return;
     uint32_t l = 0;
     for (uint32_t k = 0; k < per_warp; ++k) {
         const uint64_t i64 = i0 + (uint64_t)k * stride;
@@ -1062,11 +1090,12 @@ constexpr uint32_t kBackMin = 32;  // look at the next head only when it sits in
 // LCP array, level B: one thread per chunk, stride 1.  LCP[ISA[i]] = PLCP[i].
 __global__ void __launch_bounds__(kThreads)
 lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
-                 const uint32_t *__restrict__ ISA, const uint32_t *__restrict__ head_l, uint32_t *__restrict__ LCP)
+                 const uint32_t *__restrict__ ISA, const uint32_t *__restrict__ head_l, uint32_t *__restrict__ LCP,
+                 uint64_t c_begin = 0, uint64_t c_end = ~0ull)
 {
-    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t c = c_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // [c_begin, c_end): this launch's chunks
     const uint64_t i0 = c * kChunk;
-    if (i0 >= n) return;
+    if (c >= c_end || i0 >= n) return;
     DQ_DBG(unsigned long long b0 = g_dbg.cmp_bytes;)
     DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes - b0; g_dbg.thr_max[0] = max(g_dbg.thr_max[0], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[0][k]++; } } fin{b0};)
     uint32_t l = head_l[c];

@@ -39,68 +39,110 @@ bool want_prefix3(uint32_t n)
     return n >= (32u << 20);
 }
 
-int build_prefix3(dq_ctx *ctx, uint32_t n, cudaStream_t stream)
+// 3-byte prefix table from the text, in two steps so that a device group can count by text range and add the counts
+// up in between (dq_group.inl): counts of suffixes [p_begin, p_end) into the zeroed table, then the scans
+int prefix3_count(dq_ctx *ctx, uint32_t n, cudaStream_t stream, uint64_t p_begin, uint64_t p_end, bool zero)
 {
-    if (ctx->pre3_valid) return DQ_OK;
     DQ_TRY(ensure(ctx, ctx->pre3, ((size_t)sr::kPrefix3Bins + 4) * 4));
     DQ_TRY(ensure(ctx, ctx->pre3tile, (size_t)sr::kPrefix3Tiles * 4));
-    uint32_t *table = ctx->pre3.as<uint32_t>(), *tiles = ctx->pre3tile.as<uint32_t>();
-    DQ_CK(ctx, cudaMemsetAsync(table, 0, (size_t)sr::kPrefix3Bins * 4, stream));
-    const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n, 256), (uint64_t)ctx->sm_count * 8));
+    uint32_t *table = ctx->pre3.as<uint32_t>();
+    if (zero) DQ_CK(ctx, cudaMemsetAsync(table, 0, (size_t)sr::kPrefix3Bins * 4, stream));
+    const uint64_t hi = std::min<uint64_t>(p_end, n);
+    if (hi <= p_begin) return DQ_OK;
+    const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(hi - p_begin, 256), (uint64_t)ctx->sm_count * 8));
     auto k1 = sr::prefix3_hist_kernel;
-    DQ_LAUNCH(k1, g, 256, 0, stream, ctx->text.as<uint8_t>(), n, table);
+    DQ_LAUNCH(k1, g, 256, 0, stream, ctx->text.as<uint8_t>(), n, table, p_begin, p_end);
+    ctx->stats.kernel_launches++;
+    return DQ_OK;
+}
+
+int prefix3_scan(dq_ctx *ctx, uint32_t n, cudaStream_t stream)
+{
+    uint32_t *table = ctx->pre3.as<uint32_t>(), *tiles = ctx->pre3tile.as<uint32_t>();
     auto k2 = sr::prefix3_tile_sum_kernel;
     DQ_LAUNCH(k2, sr::kPrefix3Tiles, 256, 0, stream, table, tiles);
     auto k3 = sr::prefix3_tile_scan_kernel;
     DQ_LAUNCH(k3, 1, 1024, 0, stream, tiles, ctx->text.as<uint8_t>(), n, table);
     auto k4 = sr::prefix3_apply_kernel;
     DQ_LAUNCH(k4, sr::kPrefix3Tiles, 256, 0, stream, table, tiles);
-    ctx->stats.kernel_launches += 4;
+    ctx->stats.kernel_launches += 3;
     ctx->pre3_valid = true;
     return DQ_OK;
 }
 
-// LCP array + block minima of the resident (ctx->text, ctx->sa, ctx->isa) of length n
-int build_lcp(dq_ctx *ctx, uint32_t n)
+int build_prefix3(dq_ctx *ctx, uint32_t n, cudaStream_t stream)
 {
-    if (ctx->lcp_valid || n == 0) return DQ_OK;
+    if (ctx->pre3_valid) return DQ_OK;
+    DQ_TRY(prefix3_count(ctx, n, stream, 0, n, true));
+    return prefix3_scan(ctx, n, stream);
+}
+
+// LCP array + block minima of the resident (ctx->text, ctx->sa, ctx->isa) of length n, in three steps (a device group
+// runs the middle one by text range and merges the copies before the last one: dq_group.inl, group_build_index)
+int lcp_alloc(dq_ctx *ctx, uint32_t n)
+{
     const uint32_t chunks = (uint32_t)div_up(n, sr::kChunk), supers = (uint32_t)div_up(n, sr::kSuper);
     uint32_t size[sr::kMaxLevels];
     const int top = lcp_levels(n, size);
     size_t total = 0;
     for (int l = 0; l <= top; ++l) total += ((size_t)size[l] + 63) & ~(size_t)63;
     DQ_TRY(ensure(ctx, ctx->lcp, total * 4));
-    DQ_TRY(ensure(ctx, ctx->headl, (size_t)chunks * 4));
+    DQ_TRY(ensure(ctx, ctx->headl, ((size_t)chunks + 1) * 4));
+    DQ_TRY(ensure(ctx, ctx->seedl, ((size_t)supers + 1) * 4));
+    DQ_TRY(ensure(ctx, ctx->seedp, ((size_t)supers + 1) * 4));
+    DQ_TRY(ensure(ctx, ctx->bkt, (size_t)2 * 65536 * 4));
+    return DQ_OK;
+}
+
+// LCP[ISA[i]] for the text positions i in [pos_begin, pos_end) -- both multiples of kSuper * seeds_per_warp, or pos_end >= n
+int lcp_positions(dq_ctx *ctx, uint32_t n, uint64_t pos_begin, uint64_t pos_end)
+{
+    pos_end = std::min<uint64_t>(pos_end, n);
+    if (pos_begin >= pos_end) return DQ_OK;
+    const uint64_t chunks = div_up(n, sr::kChunk), supers = div_up(n, sr::kSuper);
     const uint8_t *T = ctx->text.as<uint8_t>();
     const int32_t *SA = ctx->sa.as<int32_t>();
     const uint32_t *ISA = ctx->isa.as<uint32_t>();
+    // the chains of the range need the head after their last chunk: one more super of heads (and the seed it starts from)
+    const uint64_t s0 = pos_begin / sr::kSuper, s1 = std::min<uint64_t>(div_up(pos_end, sr::kSuper) + 1, supers);
     {
         // level S then level A (see lcp_heads_kernel)
-        const uint32_t per = seeds_per_warp(ctx, n, supers);
-        DQ_TRY(ensure(ctx, ctx->seedl, (size_t)supers * 4));
-        DQ_TRY(ensure(ctx, ctx->seedp, (size_t)supers * 4));
+        const uint32_t per = seeds_per_warp(ctx, n, (uint32_t)supers);
         const uint32_t *run = ctx->runend_valid_n == (int32_t)n ? ctx->runend.as<uint32_t>() : nullptr;
         auto k = sr::lcp_heads_kernel;
-        if (per)
-            DQ_LAUNCH(k, (uint32_t)div_up(div_up(supers, per) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
-                      ctx->seedl.as<uint32_t>(), run, (uint32_t)sr::kSuper, per, (const uint32_t *)nullptr);
-        DQ_LAUNCH(k, (uint32_t)div_up((uint64_t)supers * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+        if (per) {
+            const uint64_t w0 = s0 / per, w1 = div_up(s1, per);
+            DQ_LAUNCH(k, (uint32_t)div_up((w1 - w0) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+                      ctx->seedl.as<uint32_t>(), run, (uint32_t)sr::kSuper, per, (const uint32_t *)nullptr, w0, w1);
+            ctx->stats.kernel_launches++;
+        }
+        DQ_LAUNCH(k, (uint32_t)div_up((s1 - s0) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
                   ctx->headl.as<uint32_t>(), run, (uint32_t)sr::kChunk, (uint32_t)sr::kHeads,
-                  per ? (const uint32_t *)ctx->seedl.as<uint32_t>() : (const uint32_t *)nullptr);
+                  per ? (const uint32_t *)ctx->seedl.as<uint32_t>() : (const uint32_t *)nullptr, s0, s1);
         ctx->stats.kernel_launches++;
     }
     {
+        const uint64_t c0 = pos_begin / sr::kChunk, c1 = std::min<uint64_t>(div_up(pos_end, sr::kChunk), chunks);
         auto k = sr::lcp_chain_kernel;
-        DQ_LAUNCH(k, (uint32_t)div_up(chunks, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
-                  ctx->headl.as<uint32_t>(), ctx->lcp.as<uint32_t>());
+        DQ_LAUNCH(k, (uint32_t)div_up(c1 - c0, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+                  ctx->headl.as<uint32_t>(), ctx->lcp.as<uint32_t>(), c0, c1);
+        ctx->stats.kernel_launches++;
     }
+    DQ_CK(ctx, cudaGetLastError());
+    return DQ_OK;
+}
+
+// bucket bounds and the block-minimum levels over a complete level 0
+int lcp_finish(dq_ctx *ctx, uint32_t n)
+{
     {
-        DQ_TRY(ensure(ctx, ctx->bkt, (size_t)2 * 65536 * 4));
         auto k = sr::bucket_bounds_kernel;
-        DQ_LAUNCH(k, 256, 256, 0, ctx->stream, T, n, SA, ctx->bkt.as<uint32_t>(), ctx->bkt.as<uint32_t>() + 65536);
+        DQ_LAUNCH(k, 256, 256, 0, ctx->stream, ctx->text.as<uint8_t>(), n, ctx->sa.as<int32_t>(), ctx->bkt.as<uint32_t>(),
+                  ctx->bkt.as<uint32_t>() + 65536);
+        ctx->stats.kernel_launches++;
     }
-    ctx->stats.kernel_launches += 3;
-    if (want_prefix3(n)) DQ_TRY(build_prefix3(ctx, n, ctx->stream));
+    uint32_t size[sr::kMaxLevels];
+    const int top = lcp_levels(n, size);
     uint32_t *lv = ctx->lcp.as<uint32_t>();
     for (int l = 1; l <= top; ++l) {
         uint32_t *nxt = lv + (((size_t)size[l - 1] + 63) & ~(size_t)63);
@@ -113,6 +155,15 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
     DQ_CK(ctx, cudaGetLastError());
     ctx->lcp_valid = true;
     return DQ_OK;
+}
+
+int build_lcp(dq_ctx *ctx, uint32_t n)
+{
+    if (ctx->lcp_valid || n == 0) return DQ_OK;
+    DQ_TRY(lcp_alloc(ctx, n));
+    DQ_TRY(lcp_positions(ctx, n, 0, n));
+    if (want_prefix3(n)) DQ_TRY(build_prefix3(ctx, n, ctx->stream));
+    return lcp_finish(ctx, n);
 }
 
 int ensure_pinned(dq_ctx *ctx, PinBuf &b, size_t bytes)
