@@ -220,8 +220,9 @@ int digit_counts(Group &g, Shard &s, const uint64_t *keys, uint32_t count, const
         auto k = ds::hist_policy_kernel<Policy>;
         DQ_LAUNCH(k, light_grid(c, count), 256, 0, c->stream, keys, count, pol, ghist);
     }
+    // few digits (bucket partition): rank with MATCH; position digits spread over all 256 values: let the scan decide
     auto scan = rx::scan_hist_kernel;
-    DQ_LAUNCH(scan, 1, rx::kRadix, 0, c->stream, ghist, gbase, use_match, count, 1u);
+    DQ_LAUNCH(scan, 1, rx::kRadix, 0, c->stream, ghist, gbase, use_match, count, sb > 0 ? 0u : 1u);
     c->stats.kernel_launches += 2;
     if (publish) {
         ds::MetaPtrs mp{};
