@@ -203,10 +203,11 @@ struct IsaParts {
     int kb;
 };
 
+// depth: per position of the unresolved set, the bytes its group shares (equal-byte runs, dq_suffix.cuh); null: all h
 __global__ void __launch_bounds__(suffix::kPackThreads)
 build_keys_peer_kernel(const uint64_t *__restrict__ act, uint32_t a, const IsaParts isa, uint32_t n, uint64_t h,
                        uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, radix::PassPlan plan,
-                       uint32_t *__restrict__ ghist)
+                       uint32_t *__restrict__ ghist, const uint32_t *__restrict__ depth = nullptr)
 {
     DQ_DYN_SMEM(smem);
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
@@ -215,12 +216,53 @@ build_keys_peer_kernel(const uint64_t *__restrict__ act, uint32_t a, const IsaPa
     const uint32_t mask = (1u << isa.kb) - 1u;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t e = act[k];
-        const uint64_t q = (uint64_t)(uint32_t)e + h;
+        const uint64_t q = (uint64_t)(uint32_t)e + (depth ? (uint64_t)depth[k] : h);
         uint32_t r2 = 0;
         if (q < n) r2 = isa.p[(uint32_t)q >> isa.kb][(uint32_t)q & mask] + 1u;
         const uint64_t key = (e & 0xffffffff00000000ull) | r2;
         keys[k] = key;
         vals[k] = (uint32_t)e;
+        radix::hist_accumulate(sh, plan, key);
+    }
+    __syncthreads();
+    radix::hist_flush(sh, plan.npass, ghist);
+}
+
+// Round 1 of a text full of equal-byte runs (build_keys_round1_kernel of the one-GPU path, for a device group): groups
+// whose 8-byte key is one repeated byte are refined by run length -- from this shard's own copy of the text and its
+// run ends, no rank is fetched -- every other group by ISA[sa + 8] + 1 read from the owner's slice.
+__global__ void __launch_bounds__(suffix::kPackThreads)
+build_keys_round1_peer_kernel(const uint64_t *__restrict__ act, uint32_t a, const IsaParts isa,
+                              const uint8_t *__restrict__ T, const uint32_t *__restrict__ run_end, uint32_t n,
+                              uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ depth,
+                              radix::PassPlan plan, uint32_t *__restrict__ ghist)
+{
+    DQ_DYN_SMEM(smem);
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < plan.npass * radix::kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << isa.kb) - 1u;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = act[k];
+        const uint32_t s = (uint32_t)e;
+        const uint64_t k8 = suffix::load_key8(T, s);
+        uint32_t r2, d;
+        if ((uint64_t)s + 8 <= n && k8 == (k8 & 0xffull) * 0x0101010101010101ull) {
+            const uint32_t end = run_end[s];
+            const uint32_t R = end - s;
+            const uint32_t bb = (uint32_t)(k8 & 0xffu);
+            const bool below = end >= n || T[end] < bb;
+            r2 = below ? R : (0x80000000u | (0x7fffffffu - R));
+            d = suffix::kDepthFromKey;
+        } else {
+            const uint64_t q = (uint64_t)s + 8;
+            r2 = q < n ? isa.p[(uint32_t)q >> isa.kb][(uint32_t)q & mask] + 1u : 0u;
+            d = 8;
+        }
+        const uint64_t key = (e & 0xffffffff00000000ull) | r2;
+        keys[k] = key;
+        vals[k] = s;
+        depth[k] = d;
         radix::hist_accumulate(sh, plan, key);
     }
     __syncthreads();

@@ -20,6 +20,7 @@ struct Shard {
     DevBuf slice, packed, isa_local, sa_local, upd, reply, inbox_req, inbox_upd, meta_req, meta_upd, samples;
     uint64_t *act = nullptr, *other = nullptr;  // packed unresolved set and the free 64-bit buffer
     uint32_t *slot_cur = nullptr, *slot_nxt = nullptr;
+    uint32_t *depth_cur = nullptr, *depth_nxt = nullptr;  // run-aware rounds: bytes the group of each position shares
     uint32_t *h_small = nullptr;  // pinned: [0..16) digit counts, [16..18) rank kernel's counters
     uint64_t *h_samples = nullptr;  // pinned
 };
@@ -34,6 +35,7 @@ struct Group {
     int kb = 0;
     uint32_t n = 0;          // length of the text whose buckets are resident on the shards (0: none)
     bool replicated = false; // text/sa/isa of that text are complete on every shard's context
+    uint32_t runend_n = 0;   // every shard's context holds the whole text of this length and its run ends (run-aware sort)
     bool trace = false;
     uint32_t shard_min = 128u << 20;  // inputs below this stay on shard 0 (DQ_SHARD_MIN overrides)
     uint64_t direct_max = 8u << 20;   // rounds with at most this many unresolved suffixes in all use straight peer
@@ -391,9 +393,15 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             DQ_SUB(top, c, encode_text(c, s.slice.as<uint8_t>(), chars, ac, s.packed));
             P = s.packed.as<uint8_t>();
         }
+        // suffixes inside equal-byte runs are counted on the way (plain keys only): many of them => run-aware rounds
+        DQ_SUB(top, c, ensure(c, c->hist, (size_t)2 * rx::kMaxPasses * rx::kRadix * 4 + 256));
+        uint32_t *uniform_count = c->hist.as<uint32_t>() + 2 * rx::kMaxPasses * rx::kRadix + 32;
+        DQ_CK(top, cudaMemsetAsync(uniform_count, 0, 4, c->stream));
         auto k = sx::pack_slice_kernel;
         DQ_LAUNCH(k, producer_grid(c, s.own_cnt), sx::kPackThreads, 0, c->stream, s.slice.as<uint8_t>(), s.own_begin,
-                  s.own_cnt, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), (unsigned long long *)nullptr, P, ac.bits);
+                  s.own_cnt, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), ac.bits == 8 ? uniform_count : nullptr, P,
+                  ac.bits);
+        DQ_CK(top, cudaMemcpyAsync(s.h_small + 32, uniform_count, 4, cudaMemcpyDeviceToHost, c->stream));
         auto ks = ds::sample_keys_kernel;
         DQ_LAUNCH(ks, (uint32_t)div_up(sample_cnt[i], 256), 256, 0, c->stream, c->partK.as<uint64_t>(), s.own_cnt,
                   sample_cnt[i], s.samples.as<uint64_t>());
@@ -528,6 +536,48 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     if (!direct0) DQ_TRY(group_route_updates(top, entered));
     DQ_TRY(group_mark(top, "r0_route_updates"));
 
+    // ---- equal-byte runs (dq_suffix.cuh): a text full of them (zero padding of executables) is refined by run length
+    // in round 1 and carries a depth per group from then on, like the one-GPU path.  Every shard then needs the whole
+    // text and its run ends (peer copies of the slices + three local kernels), and the rounds read ISA through peer
+    // pointers whatever their size: only the suffixes outside runs fetch a rank, and they fetch it at their own depth.
+    uint64_t uniform_total = 0;
+    for (Shard &s : g.sh) uniform_total += s.own_cnt ? s.h_small[32] : 0;
+    const bool run_aware = ac.bits == 8 && total_active > 0 && uniform_total * 64 >= n && !getenv("DQ_GROUP_NO_RUNS");
+    g.runend_n = 0;
+    if (run_aware) {
+        DQ_TRY(group_barrier(top));
+        DQ_TRY(for_shards(top, [&](size_t i) -> int {
+            Shard &t = g.sh[i];
+            dq_ctx *c = t.c;
+            DQ_TRY(ensure(c, c->text, (size_t)n + 64));
+            DQ_CK(c, cudaMemsetAsync(c->text.as<uint8_t>() + n, 0, 64, c->stream));
+            for (Shard &s : g.sh)
+                if (s.own_cnt)
+                    DQ_CK(c, cudaMemcpyAsync(c->text.as<uint8_t>() + s.own_begin, s.slice.p, s.own_cnt, cudaMemcpyDefault, c->stream));
+            const size_t n4 = (size_t)n * 4;
+            DQ_TRY(ensure(c, c->runend, n4));
+            const uint32_t ntiles = (uint32_t)div_up(n, sx::kRunTile);
+            DQ_TRY(ensure(c, c->runtile, (size_t)ntiles * 8));
+            uint32_t *tile_first = c->runtile.as<uint32_t>(), *next_after = tile_first + ntiles;
+            auto k1 = sx::run_tile_first_kernel;
+            DQ_LAUNCH(k1, ntiles, 256, 0, c->stream, c->text.as<uint8_t>(), n, tile_first);
+            auto k2 = sx::run_tile_scan_kernel;
+            DQ_LAUNCH(k2, 1, 1024, 0, c->stream, tile_first, ntiles, n, next_after);
+            auto k3 = sx::run_end_kernel;
+            DQ_LAUNCH(k3, ntiles, 256, 0, c->stream, c->text.as<uint8_t>(), n, next_after, c->runend.as<uint32_t>());
+            c->stats.kernel_launches += 3;
+            DQ_CK(c, cudaGetLastError());
+            DQ_TRY(ensure(c, c->depthA, (size_t)std::max<uint32_t>(t.cnt, 1) * 4));
+            DQ_TRY(ensure(c, c->depthB, (size_t)std::max<uint32_t>(t.cnt, 1) * 4));
+            t.depth_cur = c->depthA.as<uint32_t>();
+            t.depth_nxt = c->depthB.as<uint32_t>();
+            return DQ_OK;
+        }));
+        g.runend_n = n;
+        DQ_TRY(group_mark(top, "runs_text_and_run_ends"));
+    }
+    bool first_round = true;
+
     // ---- doubling rounds
     const int bits_r2 = bit_length(n), bits_rank = bit_length(n > 1 ? n - 1 : 1);
     rx::PassPlan rp{};
@@ -536,22 +586,37 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     uint64_t h = key_chars;
     while (total_active > 0) {
         DQ_TRY(start_early_copies());
-        if (total_active <= g.direct_max) {
-            // ---- a small round: ISA read and written through peer pointers (dq_dist.cuh, "small rounds")
+        if (run_aware || total_active <= g.direct_max) {
+            // ---- a small round (or any round of a run-aware sort): ISA read and written through peer pointers
+            // (dq_dist.cuh, "small rounds")
             DQ_TRY(group_barrier(top));  // every rank written so far is in place
             std::vector<SortBufs> sorted(G);
+            std::vector<uint32_t> min_depth(G, 0xffffffffu);
+            const bool runs_round = run_aware && first_round;
+            rx::PassPlan rp1{};  // the run-length keys of round 1 use all 32 low bits
+            rx::plan_add_field(rp1, 0, 32);
+            rx::plan_add_field(rp1, 32, bits_rank);
+            const rx::PassPlan &plan_now = runs_round ? rp1 : rp;
             DQ_TRY(for_shards(top, [&](size_t i) -> int {
                 Shard &s = g.sh[i];
                 dq_ctx *c = s.c;
                 entered[i] = s.a;
                 if (s.a == 0) return DQ_OK;
                 DQ_TRY(zero_hist(c));
-                auto k = ds::build_keys_peer_kernel;
-                DQ_LAUNCH(k, producer_grid(c, s.a), sx::kPackThreads, rp.npass * rx::kRadix * 4, c->stream, s.act, s.a,
-                          parts, n, h, s.other, c->valA.as<uint32_t>(), rp, c->hist.as<uint32_t>());
+                if (runs_round) {
+                    auto k = ds::build_keys_round1_peer_kernel;
+                    DQ_LAUNCH(k, producer_grid(c, s.a), sx::kPackThreads, plan_now.npass * rx::kRadix * 4, c->stream, s.act,
+                              s.a, parts, c->text.as<uint8_t>(), c->runend.as<uint32_t>(), n, s.other, c->valA.as<uint32_t>(),
+                              s.depth_cur, plan_now, c->hist.as<uint32_t>());
+                } else {
+                    auto k = ds::build_keys_peer_kernel;
+                    DQ_LAUNCH(k, producer_grid(c, s.a), sx::kPackThreads, plan_now.npass * rx::kRadix * 4, c->stream, s.act,
+                              s.a, parts, n, h, s.other, c->valA.as<uint32_t>(), plan_now, c->hist.as<uint32_t>(),
+                              run_aware ? (const uint32_t *)s.depth_cur : (const uint32_t *)nullptr);
+                }
                 c->stats.kernel_launches++;
                 SortBufs b{s.other, s.act, c->valA.as<uint32_t>(), c->valB.as<uint32_t>()};
-                DQ_TRY(run_passes(c, b, s.a, rp, true));
+                DQ_TRY(run_passes(c, b, s.a, plan_now, true));
                 sorted[i] = b;
                 return DQ_OK;
             }));
@@ -562,13 +627,15 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
                 if (s.a == 0) return DQ_OK;
                 SortBufs &b = sorted[i];
                 DQ_TRY((enqueue_rank<false, true>(c, b.kin, b.vin, s.slot_cur, s.a, n, nullptr, nullptr, s.slot_nxt,
-                                                  s.sa_local.as<int32_t>(), s.slot_base, nullptr, b.kout, nullptr, nullptr, 0,
-                                                  peers, ec[i].late, ec[i].late_count)));
+                                                  s.sa_local.as<int32_t>(), s.slot_base, nullptr, b.kout,
+                                                  run_aware ? s.depth_cur : nullptr, run_aware ? s.depth_nxt : nullptr,
+                                                  (uint32_t)h, peers, ec[i].late, ec[i].late_count)));
                 std::swap(s.slot_cur, s.slot_nxt);
+                std::swap(s.depth_cur, s.depth_nxt);
                 s.act = b.kout;
                 s.other = b.kin;
                 uint32_t next_a = 0;
-                DQ_TRY(finish_rank(c, &next_a, nullptr));
+                DQ_TRY(finish_rank(c, &next_a, run_aware ? &min_depth[i] : nullptr));
                 if (next_a > s.a) {
                     c->err = "internal: active set grew";
                     return DQ_ERR_INTERNAL;
@@ -578,9 +645,29 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             }));
             st.rounds++;
             st.active_sum += (int64_t)total_active;
-            st.algorithmic_bytes += (int64_t)total_active * (52 + 24 * rp.npass);
+            st.algorithmic_bytes += (int64_t)total_active * (52 + 24 * plan_now.npass);
             total_active = 0;
             for (Shard &s : g.sh) total_active += s.a;
+            first_round = false;
+            if (run_aware) {
+                // every rank is now consistent to the smallest depth of an unresolved group, on any shard
+                uint32_t md = 0xffffffffu;
+                for (size_t i = 0; i < G; ++i)
+                    if (g.sh[i].a) md = std::min(md, min_depth[i]);
+                DQ_TRY(group_mark(top, "small_rounds"));
+                if (total_active > 0) {
+                    if (md <= h && st.rounds > 2) {
+                        top->err = "internal: group depth did not grow";
+                        return DQ_ERR_INTERNAL;
+                    }
+                    h = md;
+                }
+                if (st.rounds > 200) {
+                    top->err = "internal: doubling did not converge";
+                    return DQ_ERR_INTERNAL;
+                }
+                continue;
+            }
             DQ_TRY(group_mark(top, "small_rounds"));
             h *= 2;
             if (h > ((uint64_t)1 << 31)) h = (uint64_t)1 << 31;
@@ -660,6 +747,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         st.algorithmic_bytes += (int64_t)total_active * (52 + 24 * rp.npass);
         total_active = 0;
         for (Shard &s : g.sh) total_active += s.a;
+        first_round = false;
         DQ_TRY(group_mark(top, "rounds_local_sort_rank"));
         DQ_TRY(group_route_updates(top, entered));
         DQ_TRY(group_mark(top, "rounds_route_updates"));
@@ -732,7 +820,7 @@ int group_replicate_index(dq_ctx *top)
         c->resident_rounds = rounds;
         c->lcp_valid = false;
         c->pre3_valid = false;
-        c->runend_valid_n = -1;
+        c->runend_valid_n = g.runend_n == n ? (int32_t)n : -1;  // a run-aware sort left the run ends on every shard
     }
     DQ_TRY(group_barrier(top));
     g.replicated = true;

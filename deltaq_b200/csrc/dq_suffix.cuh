@@ -193,30 +193,28 @@ build_keys_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ 
 
 // K0 for a slice of text positions [pos_begin, pos_begin + count): element k stands for suffix
 // pos_begin + count - 1 - k (descending, as in pack_keys_kernel).  T points at the slice (T[0] is text position
-// pos_begin), zero padded.  hist16 (65536 counters, may be null) receives the histogram of the keys' top 16 bits
-// (warp-aggregated atomics), from which the ranks agree on bucket splitters.
+// pos_begin), zero padded.  uniform_count (may be null) is incremented by the number of one-repeated-byte keys.
 __global__ void __launch_bounds__(kPackThreads)
 pack_slice_kernel(const uint8_t *__restrict__ T, uint32_t pos_begin, uint32_t count, uint64_t *__restrict__ keys,
-                  uint32_t *__restrict__ vals, unsigned long long *__restrict__ hist16,
+                  uint32_t *__restrict__ vals, uint32_t *__restrict__ uniform_count,
                   const uint8_t *__restrict__ P = nullptr, int bits = 8)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (count + stride - 1) / stride;
+    uint32_t uniform = 0;  // suffixes whose 8-byte key is one repeated byte (see pack_keys_kernel)
     for (uint64_t r = 0; r < rounds; ++r) {
         const uint64_t k = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = k < count;
-        uint32_t bin = 0xffffffffu;
-        if (valid) {
+        if (k < count) {
             const uint32_t off = count - 1u - (uint32_t)k;
             const uint64_t key = load_key(T, P, off, bits);
             keys[k] = key;
             vals[k] = pos_begin + off;
-            bin = (uint32_t)(key >> 48);
+            uniform += key == (key & 0xffull) * 0x0101010101010101ull;
         }
-        if (hist16) {
-            const unsigned peers = __match_any_sync(kFullMask, bin);
-            if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist16[bin], (unsigned long long)__popc(peers));
-        }
+    }
+    if (uniform_count) {
+        uniform = __reduce_add_sync(kFullMask, uniform);
+        if (lane_id() == 0 && uniform) atomicAdd(uniform_count, uniform);
     }
 }
 
