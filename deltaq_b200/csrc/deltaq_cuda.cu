@@ -88,7 +88,7 @@ struct dq_ctx {
     size_t rounds_used = 0;
 
     // search state (device)
-    DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt;
+    DevBuf newtext, s_pos, s_len, lcp, headp, headl, bkt, phi, plcp;
     int32_t resident_rounds = -1; // doubling rounds of the sort that produced the resident SA (-1: SA came from the caller)
     int32_t runend_new_m = -1;    // runend_new[] describes ctx->newtext of this length
     int32_t runend_valid_n = -1;  // runend[] describes the resident text of this length (set by a run-aware sort)
@@ -770,7 +770,7 @@ int destroy_single(dq_ctx *ctx)
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
                       &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->packed, &ctx->late, &ctx->newtext, &ctx->s_pos,
-                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->d_code, &ctx->d_headcount};
+                      &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->phi, &ctx->plcp, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->pass_events) {

@@ -851,7 +851,7 @@ int group_build_index(dq_ctx *top, uint32_t n)
         DQ_TRY(lcp_alloc(c, n));
         DQ_CK(c, cudaMemsetAsync(c->lcp.p, 0, (size_t)n * 4, c->stream));
         const uint64_t pb = std::min<uint64_t>(n, per * i), pe = std::min<uint64_t>(n, per * (i + 1));
-        DQ_TRY(lcp_positions(c, n, pb, pe));
+        DQ_TRY(lcp_positions(c, n, pb, pe, true));
         if (pre3) DQ_TRY(prefix3_count(c, n, c->stream, pb, pe, true));
         return DQ_OK;
     }));

@@ -1023,9 +1023,37 @@ __global__ void __launch_bounds__(256) prefix3_fill_apply_kernel(uint32_t *__res
 //                     number of such cold starts to a few thousand however long the text is;
 //   level A (heads):  stride = kChunk, per_warp = kHeads; the first head of super s is position s*kSuper, whose
 //                     value level S has already written to seed_l[s].
+// PHI[i] = the suffix that precedes suffix i in rank order (kNone for the smallest one), for i in [p_begin, p_end).
+// The LCP kernels below walk the text and need, at every position, "my rank predecessor": two dependent random reads
+// (ISA, then SA) in the middle of a latency-bound walk.  Done here instead, as one streaming pass -- coalesced ISA
+// reads, independent random SA reads, coalesced writes -- the walks then read PHI in text order.
+__global__ void __launch_bounds__(256) phi_kernel(const int32_t *__restrict__ SA, const uint32_t *__restrict__ ISA,
+                                                  uint32_t *__restrict__ PHI, uint64_t p_begin, uint64_t p_end)
+{
+    for (uint64_t i = p_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p_end; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = ISA[i];
+        PHI[i] = r ? (uint32_t)__ldg(SA + r - 1) : kNone;
+    }
+}
+
+// LCP[ISA[i]] = PLCP[i] for i in [p_begin, p_end) (a device group: every shard scatters its own text range), or
+// LCP[r] = PLCP[SA[r]] for every rank r (one GPU: coalesced writes, random reads)
+__global__ void __launch_bounds__(256) lcp_scatter_kernel(const uint32_t *__restrict__ ISA, const uint32_t *__restrict__ PLCP,
+                                                          uint32_t *__restrict__ LCP, uint64_t p_begin, uint64_t p_end)
+{
+    for (uint64_t i = p_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p_end; i += (uint64_t)gridDim.x * blockDim.x)
+        LCP[ISA[i]] = PLCP[i];
+}
+__global__ void __launch_bounds__(256) lcp_gather_kernel(const int32_t *__restrict__ SA, const uint32_t *__restrict__ PLCP,
+                                                         uint32_t *__restrict__ LCP, uint32_t n)
+{
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+        LCP[r] = __ldg(PLCP + SA[r]);
+}
+
 __global__ void __launch_bounds__(kThreads)
-lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
-                 const uint32_t *__restrict__ ISA, uint32_t *__restrict__ out_l,
+lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const uint32_t *__restrict__ PHI,
+                 uint32_t *__restrict__ out_l,
                  const uint32_t *__restrict__ run_end, uint32_t stride, uint32_t per_warp,
                  const uint32_t *__restrict__ seed_l, uint64_t w_begin = 0, uint64_t w_end = ~0ull)
 {
@@ -1041,11 +1069,10 @@ lcp_heads_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
         if (k == 0 && seed_l) {
             l = seed_l[w];
         } else {
-            const uint32_t r = ISA[i];
-            if (r == 0) {
+            const uint32_t q = PHI[i];
+            if (q == kNone) {
                 l = 0;
             } else {
-                const uint32_t q = (uint32_t)SA[r - 1];
                 uint32_t known = l > stride ? l - stride : 0;
                 // both suffixes inside runs of the same byte: the shorter run is common prefix, no need to read it
                 // (zero padding: without this one warp walks up to a megabyte here and the kernel waits for it)
@@ -1087,10 +1114,10 @@ __device__ __forceinline__ uint32_t common_suffix(const uint8_t *a, const uint8_
 
 constexpr uint32_t kBackMin = 32;  // look at the next head only when it sits inside a repeat at least this long
 
-// LCP array, level B: one thread per chunk, stride 1.  LCP[ISA[i]] = PLCP[i].
+// LCP array, level B: one thread per chunk, stride 1.  Writes PLCP[i] (the LCP entry of suffix i, in text order).
 __global__ void __launch_bounds__(kThreads)
-lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__restrict__ SA,
-                 const uint32_t *__restrict__ ISA, const uint32_t *__restrict__ head_l, uint32_t *__restrict__ LCP,
+lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const uint32_t *__restrict__ PHI,
+                 const uint32_t *__restrict__ head_l, uint32_t *__restrict__ PLCP,
                  uint64_t c_begin = 0, uint64_t c_end = ~0ull)
 {
     const uint64_t c = c_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // [c_begin, c_end): this launch's chunks
@@ -1099,7 +1126,7 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
     DQ_DBG(unsigned long long b0 = g_dbg.cmp_bytes;)
     DQ_DBG(struct Fin { unsigned long long b0; ~Fin() { unsigned long long d = g_dbg.cmp_bytes - b0; g_dbg.thr_max[0] = max(g_dbg.thr_max[0], d); int k = 0; while ((d >> k) > 1 && k < 23) ++k; g_dbg.thr_hist[0][k]++; } } fin{b0};)
     uint32_t l = head_l[c];
-    LCP[ISA[i0]] = l;
+    PLCP[i0] = l;
     // The next head ih shares nl bytes with its rank predecessor qh.  If the `back` bytes before ih and qh
     // agree too, then for d <= back suffix ih-d shares d+nl bytes with the smaller suffix qh-d, and its own
     // rank predecessor shares at least as much: a second lower bound, so a repeat that starts inside this
@@ -1109,15 +1136,11 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
     if (ih < n) {
         nl = head_l[c + 1];
         if (nl >= kBackMin) {
-            const uint32_t qh = (uint32_t)SA[ISA[ih] - 1];  // nl > 0 => the head has a predecessor
+            const uint32_t qh = PHI[ih];  // nl > 0 => the head has a predecessor
             back = common_suffix(T + ih, T + qh, min((uint32_t)kChunk - 1, qh), kChunk == 32 && qh >= 32);
         }
     }
-    uint32_t q_prev = kNone;  // rank predecessor of the position just done (kNone: it has none)
-    {
-        const uint32_t r0 = ISA[i0];
-        if (r0) q_prev = (uint32_t)SA[r0 - 1];
-    }
+    uint32_t q_prev = PHI[i0];  // rank predecessor of the position just done (kNone: it has none)
     for (int k = 1; k < kChunk; ++k) {
         // Reducible positions: if the rank predecessor of i+s is the rank predecessor of i moved s bytes on, the two
         // pairs of suffixes are the same strings minus their first s bytes, so PLCP[i+s] = PLCP[i] - s exactly (for
@@ -1130,18 +1153,16 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
             const uint64_t base = i0 + k - 1;  // the position just done
             const int room = (int)min((uint64_t)min(kBatch, kChunk - k), n - 1 - base);
             if (room <= 0 || l <= (uint32_t)room) break;
-            uint32_t rr[kBatch], qq[kBatch];
+            uint32_t qq[kBatch];
 #pragma unroll
-            for (int s = 1; s <= kBatch; ++s) rr[s - 1] = s <= room ? ISA[base + s] : 0u;
-#pragma unroll
-            for (int s = 1; s <= kBatch; ++s) qq[s - 1] = (s <= room && rr[s - 1]) ? (uint32_t)SA[rr[s - 1] - 1] : kNone;
+            for (int s = 1; s <= kBatch; ++s) qq[s - 1] = s <= room ? PHI[base + s] : kNone;
             int run = 0;
 #pragma unroll
             for (int s = 1; s <= kBatch; ++s)
                 if (run == s - 1 && s <= room && qq[s - 1] == q_prev + (uint32_t)s) run = s;
 #pragma unroll
             for (int s = 1; s <= kBatch; ++s)
-                if (s <= run) LCP[rr[s - 1]] = l - (uint32_t)s;
+                if (s <= run) PLCP[base + s] = l - (uint32_t)s;
             k += run;
             l -= (uint32_t)run;
             q_prev += (uint32_t)run;
@@ -1151,19 +1172,18 @@ lcp_chain_kernel(const uint8_t *__restrict__ T, uint32_t n, const int32_t *__res
         const uint64_t i64 = i0 + k;
         if (i64 >= n) break;
         const uint32_t i = (uint32_t)i64;
-        const uint32_t r = ISA[i];
-        if (r == 0) {
+        const uint32_t q = PHI[i];
+        if (q == kNone) {
             l = 0;
             q_prev = kNone;
         } else {
-            const uint32_t q = (uint32_t)SA[r - 1];
             uint32_t known = l > 0 ? l - 1 : 0;
             const uint32_t d = (uint32_t)(kChunk - k);
             if (d <= back) known = max(known, d + nl);
             l = known + common_prefix(T + i + known, n - i - known, T + q + known, n - q - known);
             q_prev = q;
         }
-        LCP[r] = l;
+        PLCP[i] = l;
     }
 }
 

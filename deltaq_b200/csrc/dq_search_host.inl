@@ -91,11 +91,15 @@ int lcp_alloc(dq_ctx *ctx, uint32_t n)
     DQ_TRY(ensure(ctx, ctx->seedl, ((size_t)supers + 1) * 4));
     DQ_TRY(ensure(ctx, ctx->seedp, ((size_t)supers + 1) * 4));
     DQ_TRY(ensure(ctx, ctx->bkt, (size_t)2 * 65536 * 4));
+    DQ_TRY(ensure(ctx, ctx->phi, ((size_t)n + 64) * 4));
+    DQ_TRY(ensure(ctx, ctx->plcp, ((size_t)n + 64) * 4));
     return DQ_OK;
 }
 
-// LCP[ISA[i]] for the text positions i in [pos_begin, pos_end) -- both multiples of kSuper * seeds_per_warp, or pos_end >= n
-int lcp_positions(dq_ctx *ctx, uint32_t n, uint64_t pos_begin, uint64_t pos_end)
+// LCP entries of the text positions i in [pos_begin, pos_end) -- both multiples of kSuper * seeds_per_warp, or
+// pos_end >= n: PLCP[i] along the text, then either LCP[ISA[i]] = PLCP[i] over the range (scatter: a device group, whose
+// shards merge their copies afterwards) or LCP[r] = PLCP[SA[r]] over all ranks (whole text on one GPU)
+int lcp_positions(dq_ctx *ctx, uint32_t n, uint64_t pos_begin, uint64_t pos_end, bool scatter)
 {
     pos_end = std::min<uint64_t>(pos_end, n);
     if (pos_begin >= pos_end) return DQ_OK;
@@ -103,20 +107,31 @@ int lcp_positions(dq_ctx *ctx, uint32_t n, uint64_t pos_begin, uint64_t pos_end)
     const uint8_t *T = ctx->text.as<uint8_t>();
     const int32_t *SA = ctx->sa.as<int32_t>();
     const uint32_t *ISA = ctx->isa.as<uint32_t>();
+    uint32_t *PHI = ctx->phi.as<uint32_t>(), *PLCP = ctx->plcp.as<uint32_t>();
     // the chains of the range need the head after their last chunk: one more super of heads (and the seed it starts from)
     const uint64_t s0 = pos_begin / sr::kSuper, s1 = std::min<uint64_t>(div_up(pos_end, sr::kSuper) + 1, supers);
+    const uint32_t per0 = seeds_per_warp(ctx, n, (uint32_t)supers);
+    {
+        // rank predecessors of every position the walks below touch (whole warps of the seed level included)
+        const uint64_t pb = per0 ? (s0 / per0) * per0 * sr::kSuper : s0 * sr::kSuper;
+        const uint64_t pe = std::min<uint64_t>(n, (per0 ? div_up(s1, per0) * per0 : s1) * sr::kSuper + sr::kChunk);
+        auto k = sr::phi_kernel;
+        const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(pe - pb, 256 * 4), (uint64_t)ctx->sm_count * 16));
+        DQ_LAUNCH(k, g, 256, 0, ctx->stream, SA, ISA, PHI, pb, pe);
+        ctx->stats.kernel_launches++;
+    }
     {
         // level S then level A (see lcp_heads_kernel)
-        const uint32_t per = seeds_per_warp(ctx, n, (uint32_t)supers);
+        const uint32_t per = per0;
         const uint32_t *run = ctx->runend_valid_n == (int32_t)n ? ctx->runend.as<uint32_t>() : nullptr;
         auto k = sr::lcp_heads_kernel;
         if (per) {
             const uint64_t w0 = s0 / per, w1 = div_up(s1, per);
-            DQ_LAUNCH(k, (uint32_t)div_up((w1 - w0) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+            DQ_LAUNCH(k, (uint32_t)div_up((w1 - w0) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, PHI,
                       ctx->seedl.as<uint32_t>(), run, (uint32_t)sr::kSuper, per, (const uint32_t *)nullptr, w0, w1);
             ctx->stats.kernel_launches++;
         }
-        DQ_LAUNCH(k, (uint32_t)div_up((s1 - s0) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
+        DQ_LAUNCH(k, (uint32_t)div_up((s1 - s0) * 32, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, PHI,
                   ctx->headl.as<uint32_t>(), run, (uint32_t)sr::kChunk, (uint32_t)sr::kHeads,
                   per ? (const uint32_t *)ctx->seedl.as<uint32_t>() : (const uint32_t *)nullptr, s0, s1);
         ctx->stats.kernel_launches++;
@@ -124,8 +139,20 @@ int lcp_positions(dq_ctx *ctx, uint32_t n, uint64_t pos_begin, uint64_t pos_end)
     {
         const uint64_t c0 = pos_begin / sr::kChunk, c1 = std::min<uint64_t>(div_up(pos_end, sr::kChunk), chunks);
         auto k = sr::lcp_chain_kernel;
-        DQ_LAUNCH(k, (uint32_t)div_up(c1 - c0, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, SA, ISA,
-                  ctx->headl.as<uint32_t>(), ctx->lcp.as<uint32_t>(), c0, c1);
+        DQ_LAUNCH(k, (uint32_t)div_up(c1 - c0, sr::kThreads), sr::kThreads, 0, ctx->stream, T, n, PHI,
+                  ctx->headl.as<uint32_t>(), PLCP, c0, c1);
+        ctx->stats.kernel_launches++;
+    }
+    {
+        const uint64_t count = scatter ? pos_end - pos_begin : n;
+        const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(count, 256 * 4), (uint64_t)ctx->sm_count * 16));
+        if (scatter) {
+            auto k = sr::lcp_scatter_kernel;
+            DQ_LAUNCH(k, g, 256, 0, ctx->stream, ISA, PLCP, ctx->lcp.as<uint32_t>(), pos_begin, pos_end);
+        } else {
+            auto k = sr::lcp_gather_kernel;
+            DQ_LAUNCH(k, g, 256, 0, ctx->stream, SA, PLCP, ctx->lcp.as<uint32_t>(), n);
+        }
         ctx->stats.kernel_launches++;
     }
     DQ_CK(ctx, cudaGetLastError());
@@ -161,7 +188,7 @@ int build_lcp(dq_ctx *ctx, uint32_t n)
 {
     if (ctx->lcp_valid || n == 0) return DQ_OK;
     DQ_TRY(lcp_alloc(ctx, n));
-    DQ_TRY(lcp_positions(ctx, n, 0, n));
+    DQ_TRY(lcp_positions(ctx, n, 0, n, false));
     if (want_prefix3(n)) DQ_TRY(build_prefix3(ctx, n, ctx->stream));
     return lcp_finish(ctx, n);
 }
