@@ -48,17 +48,22 @@ public static unsafe class CudaDiff
         long start = output.Position;
         output.Write(header);
 
-        DqDiffStreams s;
-        fixed (byte* o = oldData) fixed (byte* w = newData)
-            Native.Check(provider.Handle, Native.dq_cuda_bsdiff_streams(provider.Handle, o, oldData.Length, w, newData.Length, &s));
-        // the three buffers belong to the context and stay valid until its next call: compress them straight away
+        // The three buffers belong to the context and stay valid only until its next call, so the provider's gate is
+        // held across the native call AND the compression: a second Create / Sort / SearchAll on the same provider
+        // waits instead of overwriting streams that are still being read.
+        lock (provider.Gate)
+        {
+            DqDiffStreams s;
+            fixed (byte* o = oldData) fixed (byte* w = newData)
+                Native.Check(provider.Handle, Native.dq_cuda_bsdiff_streams(provider.Handle, o, oldData.Length, w, newData.Length, &s));
 
-        WriteSection(output, s.ctrl, s.ctrlLen);
-        WritePackedLong(header[8..], output.Position - start - HeaderSize);              // Diff.cs:226-233
-        long afterCtrl = output.Position;
-        WriteSection(output, s.diff, s.diffLen);
-        WritePackedLong(header[16..], output.Position - afterCtrl);
-        WriteSection(output, s.extra, s.extraLen);
+            WriteSection(output, s.ctrl, s.ctrlLen);
+            WritePackedLong(header[8..], output.Position - start - HeaderSize);              // Diff.cs:226-233
+            long afterCtrl = output.Position;
+            WriteSection(output, s.diff, s.diffLen);
+            WritePackedLong(header[16..], output.Position - afterCtrl);
+            WriteSection(output, s.extra, s.extraLen);
+        }
 
         long end = output.Position;
         output.Position = start;

@@ -32,6 +32,8 @@ internal static unsafe partial class Native
     [LibraryImport(Lib)] internal static partial int dq_cuda_suffix_sort(IntPtr ctx, byte* text, int n, int* saOut);
     [LibraryImport(Lib)] internal static partial int dq_cuda_bsdiff_search(IntPtr ctx, byte* old, int n, int* iOrNull,
         byte* @new, int m, int scanBegin, int count, int* posOut, int* lenOut);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_patch_apply(byte* old, long n, byte* ctrl, long ctrlLen,
+        byte* diff, long diffLen, byte* extra, long extraLen, byte* @out, long newSize);
 
     internal static void Check(IntPtr ctx, int status)
     {
@@ -41,6 +43,7 @@ internal static unsafe partial class Native
         {
             -1 => new ArgumentException(msg),
             -2 => new OutOfMemoryException(msg),
+            -6 => new InvalidOperationException("Corrupt patch"),   // Patch.cs:68-70, :128, :151
             _ => new InvalidOperationException(msg), // -3 CUDA, -4 no device (there is no CPU fallback), -5 internal
         };
     }
@@ -74,12 +77,22 @@ public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposa
     private IntPtr _ctx;
     internal IntPtr Handle => _ctx;   // CudaDiff.Create drives the same native context
     private readonly object _gate = new();
+    internal object Gate => _gate;    // CudaDiff.Create holds it while it reads the context-owned streams
 
     public CudaSuffixSort(int device = -1)
     {
         int dev = device;
         Native.Check(IntPtr.Zero, device < 0 ? Native.dq_cuda_create(out _ctx, null, 0)
                                              : Native.dq_cuda_create(out _ctx, &dev, 1));
+    }
+
+    /// <summary>A device GROUP: this one provider, in this one process, drives all listed GPUs (dq_cuda_create with
+    /// ndev &gt; 1). Nothing else changes for the caller: texts of at least DQ_SHARD_MIN bytes (default 128 MiB) are
+    /// sorted by all of them, SearchAll shards the scan positions, smaller inputs stay on devices[0].</summary>
+    public CudaSuffixSort(ReadOnlySpan<int> devices)
+    {
+        fixed (int* d = devices)
+            Native.Check(IntPtr.Zero, Native.dq_cuda_create(out _ctx, d, devices.Length));
     }
 
     public IMemoryOwner<int> Sort(ReadOnlySpan<byte> textBuffer)

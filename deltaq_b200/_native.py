@@ -162,7 +162,9 @@ class Context:
     and searched by all of them (the same ordinal may be listed several times: logical shards on one GPU)."""
 
     def __init__(self, device=None, lib=None):
+        import threading
         self.lib = lib or default_library()
+        self._gate = threading.Lock()   # held while context-owned result buffers are read (bsdiff_streams, greedy_emit)
         self._h = ctypes.c_void_p()
         if device is None:
             rc = self.lib.L.dq_cuda_create(ctypes.byref(self._h), None, 0)
@@ -245,14 +247,21 @@ class Context:
 
     def greedy_emit(self, old, new, pos, ln):
         out = DqDiffStreams()
-        self._check(self.lib.L.dq_cuda_greedy_emit(self._h, _addr(old), old.size, _addr(new), new.size,
-                                                   _addr(pos), _addr(ln), ctypes.byref(out)))
-        return self._streams(out)
+        with self._gate:
+            self._check(self.lib.L.dq_cuda_greedy_emit(self._h, _addr(old), old.size, _addr(new), new.size,
+                                                       _addr(pos), _addr(ln), ctypes.byref(out)))
+            return self._streams(out)
 
     def bsdiff_streams(self, old, new, copy=True):
         """copy=False returns numpy views of the context-owned buffers (valid until the next call on this
         context) -- what a C caller of dq_cuda_bsdiff_streams gets; copy=True returns bytes objects."""
         out = DqDiffStreams()
+        if copy:
+            # the buffers belong to the context: copy them out before another thread's call can overwrite them
+            with self._gate:
+                self._check(self.lib.L.dq_cuda_bsdiff_streams(self._h, _addr(old), old.size, _addr(new), new.size,
+                                                              ctypes.byref(out)))
+                return self._streams(out)
         self._check(self.lib.L.dq_cuda_bsdiff_streams(self._h, _addr(old), old.size, _addr(new), new.size,
                                                       ctypes.byref(out)))
         if not copy:

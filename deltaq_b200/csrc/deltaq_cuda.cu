@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -1091,6 +1092,8 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
     DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || new_), "bsdiff_streams: bad arguments"));
+    // the host loop looks up to 64 positions ahead in 32-bit arithmetic
+    DQ_TRY(check_args(ctx, m <= INT32_MAX - 64, "bsdiff_streams: newData longer than INT32_MAX - 64 bytes"));
     DQ_CK(ctx, cudaSetDevice(ctx->device));
     // Diff.cs:90 -- suffixSort.Sort(oldData, I[..^1]); the suffix array stays on the device.  `new` goes up on
     // the copy stream while the sort runs.
@@ -1125,7 +1128,10 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
         if (upto > m) upto = m;
         while (ready_end < upto && next < ctx->slices_used) {
             cudaError_t e_ = cudaEventSynchronize(ctx->slice_done[next]);
-            if (e_ != cudaSuccess) werr = e_;
+            if (e_ != cudaSuccess) {
+                werr = e_;
+                throw std::runtime_error("table slice did not arrive");  // never walk a table that was not filled
+            }
             ready_end = ctx->slice_end[next++];
             if (trace) fprintf(stderr, "[dq trace] slice %d landed %.3f ms\n", next - 1, since());
         }
@@ -1135,11 +1141,17 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
         int32_t v = 0;
         cudaError_t e_ = cudaMemcpyAsync(&v, ctx->s_pos.as<int32_t>() + scan, 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
         if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(ctx->copy_stream);
-        if (e_ != cudaSuccess) werr = e_;
+        if (e_ != cudaSuccess) {
+            werr = e_;
+            throw std::runtime_error("could not fetch a table entry");
+        }
         return v;
     };
     if (trace) fprintf(stderr, "[dq trace] search enqueued %.3f ms\n", since());
     bool overflow = false;
+    // nothing thrown by the host loop (allocation failures, thread creation, a table slice that never arrived) may cross
+    // the C ABI: it becomes a status
+    try {
     if (m) {
         static_assert(sizeof(dq::diffhost::MatchHead) == sizeof(dq::search::MatchHead) && sizeof(dq::diffhost::TileEntry) == sizeof(uint2),
                       "host and device views of the coded table must agree");
@@ -1171,6 +1183,18 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
         dq::diffhost::FullTable full{h_pos, h_len};
         dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, full, ctx->streams, [](int32_t) {});
         ctx->stats.table_fallbacks++;
+    }
+    } catch (const std::bad_alloc &) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = "bsdiff_streams: out of host memory";
+        return DQ_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception &ex) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = std::string("bsdiff_streams: ") + ex.what() +
+                   (werr != cudaSuccess ? std::string(" (") + cudaGetErrorString(werr) + ")" : std::string());
+        return werr != cudaSuccess ? DQ_ERR_CUDA : DQ_ERR_INTERNAL;
     }
     if (trace) fprintf(stderr, "[dq trace] host loop done %.3f ms (scan side %.3f ms, extender done %.3f ms / busy %.3f ms), %zu stops%s\n", since(), ctx->streams.scan_done_ms, ctx->streams.extender_done_ms, ctx->streams.extender_busy_ms, ctx->streams.ctrl.size() / 24, overflow ? " [full-table fallback]" : "");
     DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
@@ -1213,11 +1237,19 @@ int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8
 {
     if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || (new_ && pos_tab && len_tab)),
+    DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && m <= INT32_MAX - 64 && (n == 0 || old_) && (m == 0 || (new_ && pos_tab && len_tab)),
                       "greedy_emit: bad arguments"));
     // same threads as dq_cuda_bsdiff_streams uses (scan / extender + crew / writers), over the caller's arrays
     dq::diffhost::FullTable tab{pos_tab, len_tab};
-    dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, tab, ctx->streams, [](int32_t) {});
+    try {
+        dq::diffhost::greedy_emit_pipelined(old_, n, new_, m, tab, ctx->streams, [](int32_t) {});
+    } catch (const std::bad_alloc &) {
+        ctx->err = "greedy_emit: out of host memory";
+        return DQ_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception &ex) {
+        ctx->err = std::string("greedy_emit: ") + ex.what();
+        return DQ_ERR_INTERNAL;
+    }
     export_streams(ctx, out);
     return DQ_OK;
 }

@@ -774,10 +774,10 @@ struct PipelineShape {
             int h = 0, w = 1, part = 0, mn = 0;
             const int got = std::sscanf(e, "%d,%d,%d,%d", &h, &w, &part, &mn);
             if (got >= 4 && part > 0 && mn > 0) {
-                crew_part() = part << 10;
-                crew_min() = mn << 10;
+                crew_part() = std::min(part, 1 << 20) << 10;   // KiB values: clamped so the shifts cannot overflow
+                crew_min() = std::min(mn, 1 << 20) << 10;
             }
-            if (got >= 1) return PipelineShape{h, w};
+            if (got >= 1) return PipelineShape{std::max(0, std::min(h, 64)), std::max(1, std::min(w, 64))};
         }
         unsigned hw = std::thread::hardware_concurrency();
 #if defined(__linux__)
