@@ -1102,6 +1102,26 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     const bool trace = getenv("DQ_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    float group_search_ms = -1.f;  // >= 0: the search ran on a device group and this is its time
+    if (ctx->group && m > 0 && (uint32_t)n >= ctx->group->shard_min) {
+        // a device group and a large pair (BASELINE config #5): `old` is sorted by all GPUs, every GPU answers its share
+        // of the scan positions into this context's table (peer copies), which is then coded and consumed as below
+        ctx->group->n = 0;
+        DQ_TRY(ensure(ctx, ctx->s_pos, (size_t)m * 4));
+        DQ_TRY(ensure(ctx, ctx->s_len, (size_t)m * 4));
+        DQ_TRY(group_sort(ctx, old_, (uint32_t)n, nullptr));
+        const int32_t sort_rounds = ctx->stats.rounds;
+        const float sort_ms = ctx->stats.device_ms;
+        if (trace) fprintf(stderr, "[dq trace] sorted by the group %.3f ms\n", since());
+        DQ_TRY(group_search_common(ctx, old_, n, nullptr, new_, m, 0, m, ctx->s_pos.as<int32_t>(), ctx->s_len.as<int32_t>()));
+        const float search_ms = ctx->stats.search_ms;
+        if (trace) fprintf(stderr, "[dq trace] searched by the group %.3f ms\n", since());
+        DQ_CK(ctx, cudaSetDevice(ctx->device));
+        DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, 0, (uint32_t)m, true, true));
+        ctx->stats.rounds = sort_rounds;
+        ctx->stats.device_ms = sort_ms;
+        group_search_ms = search_ms;
+    } else {
     DQ_TRY(ensure(ctx, ctx->newtext, (size_t)m + 64));
     if (m) DQ_CK(ctx, cudaMemcpyAsync(ctx->newtext.p, new_, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
     DQ_CK(ctx, cudaMemsetAsync(ctx->newtext.as<uint8_t>() + m, 0, 64, ctx->copy_stream));
@@ -1120,6 +1140,7 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     // Diff.cs:106 for every scan position, in slices; each slice crosses PCIe in its coded form (dq_search.cuh,
     // encode_table_kernel) while later slices are still being searched and the host loop runs
     DQ_TRY(search_resident(ctx, (uint32_t)n, (uint32_t)m, 0, (uint32_t)m, true));
+    }
     // Diff.cs:100-223 on the host, consuming the table as its slices land
     int next = 0;
     int32_t ready_end = 0;
@@ -1202,6 +1223,7 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
     DQ_CK(ctx, werr);
     if (m) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_ms, ctx->ev0, ctx->ev1));
     if (m) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_index_ms, ctx->ev0, ctx->ev_index));
+    if (group_search_ms >= 0.f) ctx->stats.search_ms += group_search_ms;  // the coding above + the group's search
     if (m) {
         uint32_t heads = 0;
         DQ_CK(ctx, cudaMemcpy(&heads, ctx->d_headcount.p, 4, cudaMemcpyDeviceToHost));

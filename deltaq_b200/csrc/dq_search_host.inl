@@ -232,13 +232,16 @@ int run_ends_of_new(dq_ctx *ctx, uint32_t m, cudaStream_t stream)
 // host loop when a prefix of the coded table is usable.
 constexpr int kSlices = 8;
 
-int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count, bool coded = false)
+// table_ready (with coded): ctx->s_pos / ctx->s_len already hold the answers for [0, count) -- a device group filled
+// them from all its shards (dq_group.inl) -- and only the coding and the copies to the host run here.
+int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, uint32_t count, bool coded = false,
+                    bool table_ready = false)
 {
     ctx->stats.search_queries = (int32_t)count;
     ctx->slices_used = 0;
     if (count == 0) return DQ_OK;
     DQ_CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    DQ_TRY(build_lcp(ctx, n));
+    if (!table_ready) DQ_TRY(build_lcp(ctx, n));
     DQ_CK(ctx, cudaEventRecord(ctx->ev_index, ctx->stream));
     const uint32_t chunks = (uint32_t)div_up(count, sr::kChunk), supers = (uint32_t)div_up(count, sr::kSuper);
     DQ_TRY(ensure(ctx, ctx->s_pos, (size_t)count * 4));
@@ -284,7 +287,7 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
     // chain kernel in slices of whole super-chunks.
     const uint32_t supers_per = (uint32_t)div_up(supers, slices);
     ctx->slices_used = 0;
-    {
+    if (!table_ready) {
         // level S then level A (see search_heads_kernel)
         const uint32_t per = seeds_per_warp(ctx, n, supers);
         DQ_TRY(ensure(ctx, ctx->seedl, (size_t)std::max<uint64_t>(supers, div_up(n, sr::kSuper)) * 4));
@@ -309,7 +312,7 @@ int search_resident(dq_ctx *ctx, uint32_t n, uint32_t m, uint32_t scan_begin, ui
         // the next one fills the SMs as this one drains
         cudaStream_t st = coded ? ctx->slice_stream[sl] : ctx->stream;
         if (coded) DQ_CK(ctx, cudaStreamWaitEvent(st, ctx->heads_done, 0));
-        {
+        if (!table_ready) {
             auto k = sr::search_chain_kernel;
             DQ_LAUNCH(k, (uint32_t)div_up(ce - cb, sr::kThreads), sr::kThreads, 0, st, t, ix, scan_begin, count,
                       ctx->headp.as<uint32_t>(), ctx->headl.as<uint32_t>(), ctx->s_pos.as<int32_t>(),

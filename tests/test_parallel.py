@@ -116,6 +116,26 @@ def test_group_search_emulator(shard_everything):
         _check_search(sorter)
 
 
+def _check_streams(sorter):
+    """dq_cuda_bsdiff_streams on a device group: sort by all shards, search by all shards into shard 0's table, then the
+    coding and the host loop -- streams identical to the oracle's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from search_cases import structured_pairs
+    for name, (old, new) in structured_pairs().items():
+        got = sorter.context.bsdiff_streams(old, new)
+        ref = oracle.bsdiff_streams(old, new)
+        for k in ("ctrl", "diff", "extra"):
+            assert got[k] == ref[k], (name, k)
+        assert got["search_visits"] == ref["search_calls"], name
+
+
+def test_group_streams_emulator(shard_everything):
+    import emu
+    from deltaq_b200 import CudaSuffixSort
+    with CudaSuffixSort(device=[0, 0, 0], _lib=emu.library()) as sorter:
+        _check_streams(sorter)
+
+
 def test_small_inputs_stay_on_one_device():
     """Below DQ_SHARD_MIN a group context behaves like a single-device one (BASELINE: single-GPU-sized inputs stay
     on one GPU)."""
@@ -178,6 +198,13 @@ def test_group_search_gpu(shard_everything):
     from deltaq_b200 import CudaSuffixSort
     with CudaSuffixSort(device=_devices(3)) as sorter:
         _check_search(sorter)
+
+
+@pytest.mark.gpu
+def test_group_streams_gpu(shard_everything):
+    from deltaq_b200 import CudaSuffixSort
+    with CudaSuffixSort(device=_devices(4)) as sorter:
+        _check_streams(sorter)
 
 
 @pytest.mark.gpu
