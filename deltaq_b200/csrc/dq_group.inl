@@ -901,25 +901,42 @@ int group_search(dq_ctx *top, uint32_t n, const uint8_t *new_, uint32_t m, uint3
     const uint32_t base = count / (uint32_t)G, extra = count % (uint32_t)G;
     std::vector<uint32_t> begin(G + 1, 0);
     for (size_t i = 0; i < G; ++i) begin[i + 1] = begin[i] + base + (i < extra ? 1 : 0);
-    const int32_t launches0 = top->stats.kernel_launches;
-    for (size_t i = 0; i < G; ++i) {
+    // `new` goes up once: every shard copies its own share from the caller's buffer (its own PCIe link) and fetches
+    // the other shares from its peers (NVLink); a query may read `new` to its end, so every shard needs all of it
+    std::vector<uint32_t> nb(G + 1, 0);
+    for (size_t i = 0; i < G; ++i) nb[i + 1] = (uint32_t)((uint64_t)m * (i + 1) / G);
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
+        dq_ctx *c = g.sh[i].c;
+        c->search_seen = true;
+        DQ_TRY(ensure(c, c->newtext, (size_t)m + 64));
+        if (nb[i + 1] > nb[i])
+            DQ_CK(c, cudaMemcpyAsync(c->newtext.as<uint8_t>() + nb[i], new_ + nb[i], nb[i + 1] - nb[i], cudaMemcpyDefault, c->stream));
+        DQ_CK(c, cudaMemsetAsync(c->newtext.as<uint8_t>() + m, 0, 64, c->stream));
+        return DQ_OK;
+    }));
+    DQ_TRY(group_barrier(top));
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
+        dq_ctx *c = g.sh[i].c;
+        for (size_t j = 0; j < G; ++j)
+            if (j != i && nb[j + 1] > nb[j] && g.sh[j].c->newtext.p != c->newtext.p)
+                DQ_CK(c, cudaMemcpyAsync(c->newtext.as<uint8_t>() + nb[j], g.sh[j].c->newtext.as<uint8_t>() + nb[j],
+                                         nb[j + 1] - nb[j], cudaMemcpyDefault, c->stream));
+        return DQ_OK;
+    }));
+    DQ_TRY(group_barrier(top));
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
         Shard &s = g.sh[i];
         dq_ctx *c = s.c;
         const uint32_t cnt = begin[i + 1] - begin[i];
-        DQ_CK(top, cudaSetDevice(c->device));
-        c->search_seen = true;
-        DQ_SUB(top, c, ensure(c, c->newtext, (size_t)m + 64));
-        if (m) DQ_CK(top, cudaMemcpyAsync(c->newtext.p, new_, m, cudaMemcpyDefault, c->stream));
-        DQ_CK(top, cudaMemsetAsync(c->newtext.as<uint8_t>() + m, 0, 64, c->stream));
         c->runend_new_m = -1;
         if (i) c->stats.kernel_launches = 0;
-        DQ_SUB(top, c, search_resident(c, n, m, scan_begin + begin[i], cnt));
-        if (cnt) {
-            DQ_CK(top, cudaMemcpyAsync(pos_out + begin[i], c->s_pos.p, (size_t)cnt * 4, cudaMemcpyDefault, c->stream));
-            DQ_CK(top, cudaMemcpyAsync(len_out + begin[i], c->s_len.p, (size_t)cnt * 4, cudaMemcpyDefault, c->stream));
+        DQ_TRY(search_resident(c, n, m, scan_begin + begin[i], cnt));
+        if (cnt && (void *)(pos_out + begin[i]) != c->s_pos.p) {   // (a group's own table may be shard 0's buffer itself)
+            DQ_CK(c, cudaMemcpyAsync(pos_out + begin[i], c->s_pos.p, (size_t)cnt * 4, cudaMemcpyDefault, c->stream));
+            DQ_CK(c, cudaMemcpyAsync(len_out + begin[i], c->s_len.p, (size_t)cnt * 4, cudaMemcpyDefault, c->stream));
         }
-        if (c->err.size() && c != top) top->err = c->err;
-    }
+        return DQ_OK;
+    }));
     DQ_TRY(group_sync(top));
     float worst = 0.f, worst_index = 0.f;
     for (size_t i = 0; i < G; ++i) {
@@ -935,7 +952,6 @@ int group_search(dq_ctx *top, uint32_t n, const uint8_t *new_, uint32_t m, uint3
         if (i) top->stats.kernel_launches += s.c->stats.kernel_launches;
     }
     top->stats.search_index_ms = worst_index;
-    (void)launches0;
     top->stats.search_ms = worst;
     top->stats.search_queries = (int32_t)count;
     DQ_CK(top, cudaSetDevice(top->device));
