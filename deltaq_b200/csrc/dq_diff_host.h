@@ -789,8 +789,12 @@ struct PipelineShape {
             }
         }
 #endif
+        // Few cores (one process per GPU sharing a host: 4 cores per rank on an 8-GPU box with 32) still get helpers: the
+        // long extensions come at the end of a call, when the scan and the writers have little left to do, and idle
+        // helpers sleep (wait_step)
         if (hw >= 12) return PipelineShape{3, 2};
-        if (hw >= 6) return PipelineShape{1, 2};
+        if (hw >= 6) return PipelineShape{2, 2};
+        if (hw >= 3) return PipelineShape{2, 1};
         return PipelineShape{0, 1};
     }
 };
