@@ -26,6 +26,7 @@
 #include "dq_common.cuh"
 #include "dq_radix.cuh"
 #include "dq_suffix.cuh"
+#include "dq_segsort.cuh"
 #include "dq_search.cuh"
 #include "dq_dist.cuh"
 #include "dq_diff_host.h"
@@ -78,7 +79,7 @@ struct dq_ctx {
 
     // suffix-sort state (device)
     DevBuf text, keyA, keyB, valA, valB, isa, sa, slotA, slotB, lb, hist, auxK, auxV, partK, partV, runend, depthA, depthB,
-        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile, packed, late;
+        runtile, runend_new, runtile_new, seedp, seedl, pre3, pre3tile, packed, late, segdone, segcnt;
     uint32_t *h_count = nullptr;  // pinned
     int32_t resident_n = -1;      // text/sa/isa on the device describe an input of this length
     cudaEvent_t ev_copy = nullptr;  // early copy of the suffix array: started / landed
@@ -446,6 +447,63 @@ int build_prefix3_sorted(dq_ctx *ctx, const uint64_t *sorted_keys, uint32_t n)
     return DQ_OK;
 }
 
+// One doubling round's sort without the global passes where the groups are small (dq_segsort.cuh).  (s.kin, s.vin) hold the
+// a keys / suffixes in group order and are sorted in place; s.kout / s.vout are free.  *left = pairs that went through
+// the ordinary passes because their group did not fit a tile.
+int segmented_round_sort(dq_ctx *ctx, SortBufs &s, uint32_t a, const rx::PassPlan &rp, uint32_t *left)
+{
+    namespace sg = dq::segsort;
+    const uint32_t nblk = (uint32_t)div_up(a, sg::kBlock);
+    DQ_TRY(ensure(ctx, ctx->segdone, (size_t)a));
+    DQ_TRY(ensure(ctx, ctx->segcnt, ((size_t)nblk + 8) * 4));
+    uint8_t *done = ctx->segdone.as<uint8_t>();
+    uint32_t *counts = ctx->segcnt.as<uint32_t>();
+    uint32_t *total = counts + nblk;
+    DQ_CK(ctx, cudaMemsetAsync(done, 0, a, ctx->stream));
+    {
+        auto k = sg::tile_sort_kernel;
+        DQ_LAUNCH(k, (uint32_t)div_up(a, sg::kNominal), sg::kThreads, 0, ctx->stream, s.kin, s.vin, a, done);
+        auto kc = sg::count_left_kernel;
+        DQ_LAUNCH(kc, nblk, sg::kThreads, 0, ctx->stream, done, a, counts);
+        auto ks = sg::scan_counts_kernel;
+        DQ_LAUNCH(ks, 1, 1024, 0, ctx->stream, counts, nblk, total);
+        ctx->stats.kernel_launches += 3;
+    }
+    DQ_CK(ctx, cudaGetLastError());
+    DQ_CK(ctx, cudaMemcpyAsync(ctx->h_count + 9, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t L = ctx->h_count[9];
+    *left = L;
+    if (L == 0) return DQ_OK;
+    // the groups no tile took: compacted in order, sorted by the ordinary passes, put back where they came from
+    DQ_TRY(ensure(ctx, ctx->partV, (size_t)L * 4));
+    DQ_TRY(ensure(ctx, ctx->auxK, (size_t)L * 8));
+    DQ_TRY(ensure(ctx, ctx->auxV, (size_t)L * 4));
+    uint32_t *pos = ctx->partV.as<uint32_t>();
+    {
+        auto k = sg::compact_left_kernel;
+        DQ_LAUNCH(k, nblk, sg::kThreads, 0, ctx->stream, s.kin, s.vin, done, a, counts, s.kout, s.vout, pos);
+        ctx->stats.kernel_launches++;
+    }
+    DQ_TRY(zero_hist(ctx));
+    {
+        auto k = sx::hist_only_kernel;
+        DQ_LAUNCH(k, producer_grid(ctx, L), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream, s.kout, L, rp,
+                  ctx->hist.as<uint32_t>());
+        ctx->stats.kernel_launches++;
+    }
+    SortBufs t{s.kout, ctx->auxK.as<uint64_t>(), s.vout, ctx->auxV.as<uint32_t>()};
+    DQ_TRY(run_passes(ctx, t, L, rp, true));
+    {
+        auto k = sg::scatter_back_kernel;
+        const uint32_t g = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(div_up(L, 256), (uint64_t)ctx->sm_count * 16));
+        DQ_LAUNCH(k, g, 256, 0, ctx->stream, t.kin, t.vin, pos, L, s.kin, s.vin);
+        ctx->stats.kernel_launches++;
+    }
+    DQ_CK(ctx, cudaGetLastError());
+    return DQ_OK;
+}
+
 // host_sa_out: when not null, the caller's host array (it must be device-visible, see EarlyCopy) receives the suffix
 // array here -- overlapped with the last rounds when they are small -- and *delivered says so
 int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool *delivered = nullptr)
@@ -567,6 +625,9 @@ int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool 
         depth_nxt = ctx->depthB.as<uint32_t>();
     }
     bool first = true;
+    // DQ_SEGSORT=0 turns the in-CTA sort of small groups off; DQ_SEGSORT_MIN=a lowers the round size it starts at (tests)
+    bool seg_ok = !(getenv("DQ_SEGSORT") && atoi(getenv("DQ_SEGSORT")) == 0);
+    const uint32_t seg_min = getenv("DQ_SEGSORT_MIN") ? (uint32_t)strtoul(getenv("DQ_SEGSORT_MIN"), nullptr, 10) : (64u << 10);
     while (a > 0) {
         DQ_TRY(early_copy_maybe_start(ctx, ec, ctx->sa.as<int32_t>(), host_sa_out, n, a, n));
         // active set: sa = s.vout, rank = (uint32*)s.kout, slot = slot_cur, depth = depth_cur.  Keys go to s.kin.
@@ -574,22 +635,32 @@ int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool 
         rx::plan_add_field(rp, 0, (first && run_aware) ? 32 : bits_r2);
         rx::plan_add_field(rp, 32, bits_rank);
         DQ_TRY(mark_round(ctx, a, rp.npass));
+        // small groups are sorted inside one CTA each (dq_segsort.cuh); the key builder then needs no digit histograms
+        const bool seg = seg_ok && a >= seg_min;
+        rx::PassPlan hp = rp;
+        if (seg) hp.npass = 0;
         DQ_TRY(zero_hist(ctx));
         if (first && run_aware) {
             auto k = sx::build_keys_round1_kernel;
-            DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream, s.vout,
+            DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, hp.npass * rx::kRadix * 4, ctx->stream, s.vout,
                       reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), ctx->text.as<uint8_t>(),
-                      ctx->runend.as<uint32_t>(), n, a, s.kin, depth_cur, rp, ctx->hist.as<uint32_t>());
+                      ctx->runend.as<uint32_t>(), n, a, s.kin, depth_cur, hp, ctx->hist.as<uint32_t>());
         } else {
             auto k = sx::build_keys_kernel;
-            DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, rp.npass * rx::kRadix * 4, ctx->stream, s.vout,
-                      reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), n, a, h, depth_cur, s.kin, rp,
+            DQ_LAUNCH(k, producer_grid(ctx, a), sx::kPackThreads, hp.npass * rx::kRadix * 4, ctx->stream, s.vout,
+                      reinterpret_cast<uint32_t *>(s.kout), ctx->isa.as<uint32_t>(), n, a, h, depth_cur, s.kin, hp,
                       ctx->hist.as<uint32_t>());
         }
         st.kernel_launches++;
         // sort (s.kin, s.vout) using (s.kout, s.vin) as the alternate
         std::swap(s.vin, s.vout);
-        DQ_TRY(run_passes(ctx, s, a, rp, true));
+        if (seg) {
+            uint32_t left = 0;
+            DQ_TRY(segmented_round_sort(ctx, s, a, rp, &left));
+            if ((uint64_t)left * 2 > a) seg_ok = false;  // mostly big groups (a repetitive text): plain passes from now on
+        } else {
+            DQ_TRY(run_passes(ctx, s, a, rp, true));
+        }
         st.rounds++;
         st.active_sum += a;
         st.algorithmic_bytes += (int64_t)a * (52 + 24 * rp.npass);
@@ -770,7 +841,7 @@ int destroy_single(dq_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->text, &ctx->keyA, &ctx->keyB, &ctx->valA, &ctx->valB, &ctx->isa, &ctx->sa,
                       &ctx->slotA, &ctx->slotB, &ctx->lb, &ctx->hist, &ctx->auxK, &ctx->auxV, &ctx->partK, &ctx->partV, &ctx->runend, &ctx->depthA, &ctx->depthB,
-                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->packed, &ctx->late, &ctx->newtext, &ctx->s_pos,
+                      &ctx->runtile, &ctx->runend_new, &ctx->runtile_new, &ctx->seedp, &ctx->seedl, &ctx->pre3, &ctx->pre3tile, &ctx->packed, &ctx->late, &ctx->segdone, &ctx->segcnt, &ctx->newtext, &ctx->s_pos,
                       &ctx->s_len, &ctx->lcp, &ctx->headp, &ctx->headl, &ctx->bkt, &ctx->phi, &ctx->plcp, &ctx->d_code, &ctx->d_headcount};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
