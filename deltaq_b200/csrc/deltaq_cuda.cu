@@ -625,8 +625,12 @@ int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool 
         depth_nxt = ctx->depthB.as<uint32_t>();
     }
     bool first = true;
-    // DQ_SEGSORT=0 turns the in-CTA sort of small groups off; DQ_SEGSORT_MIN=a lowers the round size it starts at (tests)
-    bool seg_ok = !(getenv("DQ_SEGSORT") && atoi(getenv("DQ_SEGSORT")) == 0);
+    // DQ_SEGSORT=1 turns the in-CTA sort of small groups on (dq_segsort.cuh).  Off by default: on BASELINE's workloads the
+    // unresolved groups are mostly bigger than a tile (periodic records, tandem repeats, repeated paragraphs), so most
+    // pairs take the compaction + ordinary passes anyway and the round gets slower (C2 round 2: 0.67 vs 0.51 ms, C3
+    // 62.3 vs 57.0 ms, C4 slice 9.3 vs 8.7 ms; profiles/r02_segsort_ab.md).  DQ_SEGSORT_MIN=a: smallest round it takes.
+    bool seg_ok = getenv("DQ_SEGSORT") && atoi(getenv("DQ_SEGSORT")) != 0;
+    int seg_pause = 0;
     const uint32_t seg_min = getenv("DQ_SEGSORT_MIN") ? (uint32_t)strtoul(getenv("DQ_SEGSORT_MIN"), nullptr, 10) : (64u << 10);
     while (a > 0) {
         DQ_TRY(early_copy_maybe_start(ctx, ec, ctx->sa.as<int32_t>(), host_sa_out, n, a, n));
@@ -636,7 +640,10 @@ int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool 
         rx::plan_add_field(rp, 32, bits_rank);
         DQ_TRY(mark_round(ctx, a, rp.npass));
         // small groups are sorted inside one CTA each (dq_segsort.cuh); the key builder then needs no digit histograms
-        const bool seg = seg_ok && a >= seg_min;
+        // (not in the run-length round: the groups of whole equal-byte runs are as big as groups get; and not right after
+        // a round that found mostly big groups)
+        const bool seg = seg_ok && a >= seg_min && !(first && run_aware) && seg_pause == 0;
+        if (seg_pause > 0) --seg_pause;
         rx::PassPlan hp = rp;
         if (seg) hp.npass = 0;
         DQ_TRY(zero_hist(ctx));
@@ -657,7 +664,7 @@ int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool 
         if (seg) {
             uint32_t left = 0;
             DQ_TRY(segmented_round_sort(ctx, s, a, rp, &left));
-            if ((uint64_t)left * 2 > a) seg_ok = false;  // mostly big groups (a repetitive text): plain passes from now on
+            if ((uint64_t)left * 2 > a) seg_pause = 2;  // mostly big groups: plain passes for the next two rounds
         } else {
             DQ_TRY(run_passes(ctx, s, a, rp, true));
         }

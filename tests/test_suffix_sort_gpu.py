@@ -176,3 +176,15 @@ def test_early_copy_of_the_suffix_array(sorter, name, monkeypatch):
     sa = np.full(t.size + 1, -7, dtype=np.int32)       # pageable memory: the plain copy at the end
     sorter.sort(t, sa[:t.size])
     assert sa[t.size] == -7 and np.array_equal(sa[:t.size], oracle.sais(t))
+
+
+@pytest.mark.parametrize("name", ["acgt_tandem", "bin_70000", "acgt_a_tail"])
+def test_segmented_sort_of_small_groups(sorter, name, monkeypatch):
+    """DQ_SEGSORT=1 (dq_segsort.cuh): groups sorted inside one CTA, the rest by the ordinary passes -- same suffix array."""
+    from conftest import small_alphabet_texts
+    monkeypatch.setenv("DQ_SEGSORT", "1")
+    monkeypatch.setenv("DQ_SEGSORT_MIN", "1")
+    for t in (small_alphabet_texts()[name], _texts_with_repeats()["rep10pct_60k"]):
+        sa = np.empty(t.size, dtype=np.int32)
+        sorter.sort(t, sa)
+        assert np.array_equal(sa, oracle.sais(t))
