@@ -927,6 +927,9 @@ int create_single(dq_ctx **out, int dev)
     if ((e = cudaFuncSetAttribute(rx::onesweep_policy_kernel<ds::BucketPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)rx::pass_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(rx::onesweep_policy_kernel<ds::RunBucketPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rx::pass_smem_bytes())) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(rx::onesweep_policy_kernel<ds::RequestPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)rx::pass_smem_bytes())) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);

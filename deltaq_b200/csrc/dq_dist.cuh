@@ -41,6 +41,7 @@ __device__ __forceinline__ uint32_t dest_of(const Splitters &sp, uint64_t key)
 // ---- policies of the partition + exchange passes ------------------------------------------------------------
 struct BucketPolicy {
     static constexpr bool kHasVal = true;
+    static constexpr bool kDigitFromVal = false;
     Splitters sp;
     uint64_t *kout[kMaxShards];  // shard d's round-0 sort input (peer memory)
     uint32_t *vout[kMaxShards];
@@ -61,9 +62,61 @@ struct BucketPolicy {
 // slice at random (at 256 MiB of text per GPU that is the difference between DRAM-sector-bound and streaming).  The
 // pass costs the same whatever the number of digits.
 //
+// ---- key skew (SURVEY hard part H7) -------------------------------------------------------------------------------
+// Equal keys travel together, so one heavy key unbalances the buckets -- and an executable's zero padding makes the
+// key 00^8 fifteen per cent of all suffixes, all of which would then go through the run-aware rounds on ONE GPU.  For a
+// run-heavy text the buckets are therefore cut on the composite (key, run code): the code is the round-1 key of a
+// suffix inside an equal-byte run (class and run length, dq_suffix.cuh), which is its true order among the suffixes
+// with the same repeated-byte key, and 0 for every other suffix.  A shard then holds one slice of a heavy key's
+// suffixes by run length; its round-0 group of them is a refinement consistent with the final order, and the groups of
+// round 1 (same class, same run length) still never cross shards.
+struct RunSplitters {
+    uint64_t key[kMaxShards];
+    uint32_t code[kMaxShards];
+    int n;
+};
+
+__device__ __forceinline__ uint32_t run_code(const uint8_t *__restrict__ T, const uint32_t *__restrict__ run_end,
+                                             uint32_t n, uint64_t key, uint32_t pos)
+{
+    if (key != (key & 0xffull) * 0x0101010101010101ull || (uint64_t)pos + 8 > n) return 0u;  // (short suffixes sort first)
+    const uint32_t end = run_end[pos];
+    const uint32_t R = end - pos;
+    const bool below = end >= n || T[end] < (uint32_t)(key & 0xffu);
+    return below ? R : (0x80000000u | (0x7fffffffu - R));
+}
+
+struct RunBucketPolicy {
+    static constexpr bool kHasVal = true;
+    static constexpr bool kDigitFromVal = true;
+    RunSplitters sp;
+    const uint8_t *T;         // the whole text and its run ends, on this shard
+    const uint32_t *run_end;
+    uint32_t n;
+    uint64_t *kout[kMaxShards];
+    uint32_t *vout[kMaxShards];
+    int bits;
+    __device__ __forceinline__ uint32_t digit(uint64_t key, uint32_t pos) const
+    {
+        const uint32_t code = run_code(T, run_end, n, key, pos);
+        uint32_t d = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxShards - 1; ++j)
+            if (j < sp.n) d += (key > sp.key[j] || (key == sp.key[j] && code >= sp.code[j])) ? 1u : 0u;
+        return d;
+    }
+    __device__ __forceinline__ int nbits() const { return bits; }
+    __device__ __forceinline__ void store(uint32_t d, uint32_t dst, uint64_t key, uint32_t val) const
+    {
+        kout[d][dst] = key;
+        vout[d][dst] = val;
+    }
+};
+
 // active element = (rank << 32 | sa)
 struct RequestPolicy {
     static constexpr bool kHasVal = false;
+    static constexpr bool kDigitFromVal = false;
     uint64_t *kout;              // local: the active set regrouped by position owner (and sub-range)
     uint32_t *qout[kMaxShards];  // this source's region of owner d's request inbox (peer memory)
     const uint32_t *gbase;       // local exclusive digit offsets (the pass's own gbase)
@@ -91,6 +144,7 @@ struct RequestPolicy {
 // update = (new rank << 32 | position); the owner receives (new rank << 32 | position - first owned position)
 struct UpdatePolicy {
     static constexpr bool kHasVal = false;
+    static constexpr bool kDigitFromVal = false;
     uint64_t *uout[kMaxShards];  // this source's region of owner d's update inbox (peer memory)
     const uint32_t *gbase;
     int kb;
@@ -109,7 +163,8 @@ struct UpdatePolicy {
 // often share a digit, so equal digits inside a warp are merged before they touch the shared counters.
 template <typename Policy>
 __global__ void __launch_bounds__(256)
-hist_policy_kernel(const uint64_t *__restrict__ keys, uint32_t count, const Policy pol, uint32_t *__restrict__ ghist)
+hist_policy_kernel(const uint64_t *__restrict__ keys, uint32_t count, const Policy pol, uint32_t *__restrict__ ghist,
+                   const uint32_t *__restrict__ vals = nullptr)
 {
     __shared__ uint32_t sh[radix::kRadix];
     sh[threadIdx.x] = 0;
@@ -119,7 +174,7 @@ hist_policy_kernel(const uint64_t *__restrict__ keys, uint32_t count, const Poli
     for (uint64_t r = 0; r < rounds; ++r) {
         const uint64_t k = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const bool valid = k < count;
-        const uint32_t d = valid ? pol.digit(keys[k]) : 0xffffu;
+        const uint32_t d = valid ? radix::digit_of(pol, keys[k], vals ? vals[k] : 0u) : 0xffffu;
         const unsigned peers = __match_any_sync(kFullMask, d);
         if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&sh[d], (uint32_t)__popc(peers));
     }
@@ -160,6 +215,20 @@ sample_keys_kernel(const uint64_t *__restrict__ keys, uint32_t count, uint32_t n
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nsamples) return;
     out[j] = keys[(uint32_t)(((uint64_t)j * 0x9E3779B1ull + 12345u) % count)];
+}
+
+// the same samples with their run codes (RunBucketPolicy)
+__global__ void __launch_bounds__(256)
+sample_pairs_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t count,
+                    uint32_t nsamples, const uint8_t *__restrict__ T, const uint32_t *__restrict__ run_end, uint32_t n,
+                    uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_codes)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nsamples) return;
+    const uint32_t k = (uint32_t)(((uint64_t)j * 0x9E3779B1ull + 12345u) % count);
+    const uint64_t key = keys[k];
+    out_keys[j] = key;
+    out_codes[j] = run_code(T, run_end, n, key, vals[k]);
 }
 
 // owner side of the ISA fetch: for every source s, answer its requests in order, straight into the requester's

@@ -137,7 +137,7 @@ int create_group(dq_ctx *top, const int *devices, int ndev)
         DQ_CK(top, cudaSetDevice(s.c->device));
         DQ_CK(top, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
         DQ_CK(top, cudaHostAlloc((void **)&s.h_small, 256, cudaHostAllocDefault));
-        DQ_CK(top, cudaHostAlloc((void **)&s.h_samples, (size_t)kSamplesPerShard * 8, cudaHostAllocDefault));
+        DQ_CK(top, cudaHostAlloc((void **)&s.h_samples, (size_t)kSamplesPerShard * 16, cudaHostAllocDefault));  // keys, then run codes
         for (int j = 0; j < ndev; ++j) {
             if (devices[j] == devices[i]) continue;
             int can = 0;
@@ -211,7 +211,7 @@ uint32_t light_grid(const dq_ctx *c, uint64_t items)
 // the destinations' meta arrays.  Leaves gbase/use_match in c->hist as run_passes does for pass 0.
 template <typename Policy>
 int digit_counts(Group &g, Shard &s, const uint64_t *keys, uint32_t count, const Policy &pol, bool publish,
-                 bool to_requests, int sb = 0)
+                 bool to_requests, int sb = 0, const uint32_t *vals = nullptr)
 {
     dq_ctx *c = s.c;
     DQ_TRY(zero_hist(c));
@@ -220,7 +220,7 @@ int digit_counts(Group &g, Shard &s, const uint64_t *keys, uint32_t count, const
     uint32_t *use_match = gbase + rx::kMaxPasses * rx::kRadix;
     if (count) {
         auto k = ds::hist_policy_kernel<Policy>;
-        DQ_LAUNCH(k, light_grid(c, count), 256, 0, c->stream, keys, count, pol, ghist);
+        DQ_LAUNCH(k, light_grid(c, count), 256, 0, c->stream, keys, count, pol, ghist, vals);
     }
     // few digits (bucket partition): rank with MATCH; position digits spread over all 256 values: let the scan decide
     auto scan = rx::scan_hist_kernel;
@@ -309,6 +309,36 @@ int group_route_updates(dq_ctx *top, const std::vector<uint32_t> &counts)
     });
 }
 
+// every shard gets the whole text (peer copies of the slices) and computes its run ends (dq_suffix.cuh, run_*_kernel)
+int group_text_and_run_ends(dq_ctx *top, uint32_t n)
+{
+    Group &g = *top->group;
+    DQ_TRY(group_barrier(top));
+    DQ_TRY(for_shards(top, [&](size_t i) -> int {
+        dq_ctx *c = g.sh[i].c;
+        DQ_TRY(ensure(c, c->text, (size_t)n + 64));
+        DQ_CK(c, cudaMemsetAsync(c->text.as<uint8_t>() + n, 0, 64, c->stream));
+        for (Shard &s : g.sh)
+            if (s.own_cnt)
+                DQ_CK(c, cudaMemcpyAsync(c->text.as<uint8_t>() + s.own_begin, s.slice.p, s.own_cnt, cudaMemcpyDefault, c->stream));
+        DQ_TRY(ensure(c, c->runend, (size_t)n * 4));
+        const uint32_t ntiles = (uint32_t)div_up(n, sx::kRunTile);
+        DQ_TRY(ensure(c, c->runtile, (size_t)ntiles * 8));
+        uint32_t *tile_first = c->runtile.as<uint32_t>(), *next_after = tile_first + ntiles;
+        auto k1 = sx::run_tile_first_kernel;
+        DQ_LAUNCH(k1, ntiles, 256, 0, c->stream, c->text.as<uint8_t>(), n, tile_first);
+        auto k2 = sx::run_tile_scan_kernel;
+        DQ_LAUNCH(k2, 1, 1024, 0, c->stream, tile_first, ntiles, n, next_after);
+        auto k3 = sx::run_end_kernel;
+        DQ_LAUNCH(k3, ntiles, 256, 0, c->stream, c->text.as<uint8_t>(), n, next_after, c->runend.as<uint32_t>());
+        c->stats.kernel_launches += 3;
+        DQ_CK(c, cudaGetLastError());
+        return DQ_OK;
+    }));
+    g.runend_n = n;
+    return DQ_OK;
+}
+
 // Sorts the n-byte text at `text` (host memory, or device memory of any GPU of the group: the copies are
 // cudaMemcpyDefault) with all shards.  On return shard s holds SA[slot_base, slot_base+cnt) in sa_local and
 // ISA[own_begin, own_begin+own_cnt) in isa_local; sa_out (may be null) receives the whole suffix array.
@@ -381,7 +411,7 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         DQ_CK(top, cudaSetDevice(c->device));
         DQ_SUB(top, c, ensure(c, c->partK, (size_t)std::max<uint32_t>(s.own_cnt, 1) * 8));
         DQ_SUB(top, c, ensure(c, c->partV, (size_t)std::max<uint32_t>(s.own_cnt, 1) * 4));
-        DQ_SUB(top, c, ensure(c, s.samples, (size_t)kSamplesPerShard * 8));
+        DQ_SUB(top, c, ensure(c, s.samples, (size_t)kSamplesPerShard * 16));
         DQ_SUB(top, c, ensure(c, s.isa_local, (size_t)std::max<uint32_t>(s.own_cnt, 1) * 4));
         DQ_SUB(top, c, ensure(c, s.meta_req, G * sizeof(ds::RunMeta)));
         DQ_SUB(top, c, ensure(c, s.meta_upd, G * sizeof(ds::RunMeta)));
@@ -410,8 +440,46 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     }
     DQ_CK(top, cudaGetLastError());
     DQ_TRY(group_sync(top));
+    // equal-byte runs (dq_suffix.cuh): many of them => run-aware rounds, and buckets cut on (key, run code) so that the
+    // heavy repeated-byte keys spread over the shards (dq_dist.cuh, "key skew")
+    uint64_t uniform_total = 0;
+    for (Shard &s : g.sh) uniform_total += s.own_cnt ? s.h_small[32] : 0;
+    const bool run_heavy = ac.bits == 8 && uniform_total * 64 >= n && !getenv("DQ_GROUP_NO_RUNS");
+    g.runend_n = 0;
     ds::Splitters sp{};
-    {
+    ds::RunSplitters rsp{};
+    if (run_heavy) {
+        DQ_TRY(group_text_and_run_ends(top, n));
+        for (size_t i = 0; i < G; ++i) {
+            Shard &s = g.sh[i];
+            dq_ctx *c = s.c;
+            if (!sample_cnt[i]) continue;
+            DQ_CK(top, cudaSetDevice(c->device));
+            uint32_t *codes = reinterpret_cast<uint32_t *>(s.samples.as<uint64_t>() + kSamplesPerShard);
+            auto ks = ds::sample_pairs_kernel;
+            DQ_LAUNCH(ks, (uint32_t)div_up(sample_cnt[i], 256), 256, 0, c->stream, c->partK.as<uint64_t>(),
+                      c->partV.as<uint32_t>(), s.own_cnt, sample_cnt[i], c->text.as<uint8_t>(), c->runend.as<uint32_t>(), n,
+                      s.samples.as<uint64_t>(), codes);
+            c->stats.kernel_launches++;
+            DQ_CK(top, cudaMemcpyAsync(s.h_samples, s.samples.p, (size_t)kSamplesPerShard * 8 + (size_t)sample_cnt[i] * 4,
+                                       cudaMemcpyDeviceToHost, c->stream));
+        }
+        DQ_CK(top, cudaGetLastError());
+        DQ_TRY(group_sync(top));
+        std::vector<std::pair<uint64_t, uint32_t>> all;
+        all.reserve(total_samples);
+        for (size_t i = 0; i < G; ++i) {
+            const uint32_t *codes = reinterpret_cast<const uint32_t *>(g.sh[i].h_samples + kSamplesPerShard);
+            for (uint32_t j = 0; j < sample_cnt[i]; ++j) all.emplace_back(g.sh[i].h_samples[j], codes[j]);
+        }
+        std::sort(all.begin(), all.end());
+        rsp.n = (int)G - 1;
+        for (int j = 0; j < rsp.n; ++j) {
+            const auto &v = all.empty() ? std::pair<uint64_t, uint32_t>(0, 0) : all[(size_t)(j + 1) * all.size() / G];
+            rsp.key[j] = v.first;
+            rsp.code[j] = v.second;
+        }
+    } else {
         std::vector<uint64_t> all;
         all.reserve(total_samples);
         for (size_t i = 0; i < G; ++i) all.insert(all.end(), g.sh[i].h_samples, g.sh[i].h_samples + sample_cnt[i]);
@@ -425,9 +493,20 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     ds::BucketPolicy bp{};
     bp.sp = sp;
     bp.bits = bits_for(G);
+    ds::RunBucketPolicy rbp{};
+    rbp.sp = rsp;
+    rbp.n = n;
+    rbp.bits = bits_for(G);
     for (Shard &s : g.sh) {
         DQ_CK(top, cudaSetDevice(s.c->device));
-        DQ_SUB(top, s.c, digit_counts(g, s, s.c->partK.as<uint64_t>(), s.own_cnt, bp, false, false));
+        if (run_heavy) {
+            rbp.T = s.c->text.as<uint8_t>();
+            rbp.run_end = s.c->runend.as<uint32_t>();
+            DQ_SUB(top, s.c, digit_counts(g, s, s.c->partK.as<uint64_t>(), s.own_cnt, rbp, false, false, 0,
+                                         s.c->partV.as<uint32_t>()));
+        } else {
+            DQ_SUB(top, s.c, digit_counts(g, s, s.c->partK.as<uint64_t>(), s.own_cnt, bp, false, false));
+        }
         DQ_CK(top, cudaMemcpyAsync(s.h_small, s.c->hist.p, ds::kMaxShards * 4, cudaMemcpyDeviceToHost, s.c->stream));
     }
     DQ_TRY(group_sync(top));
@@ -456,8 +535,8 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
         DQ_SUB(top, c, ensure(c, s.reply, (size_t)std::max<uint32_t>(s.cnt, 1) * 4));
         DQ_SUB(top, c, ensure(c, s.inbox_req, (size_t)std::max<uint32_t>(cap, 1) * 4 * G));
         DQ_SUB(top, c, ensure(c, s.inbox_upd, (size_t)std::max<uint32_t>(cap, 1) * 8 * G));
-        bp.kout[&s - &g.sh[0]] = c->keyA.as<uint64_t>();
-        bp.vout[&s - &g.sh[0]] = c->valA.as<uint32_t>();
+        bp.kout[&s - &g.sh[0]] = rbp.kout[&s - &g.sh[0]] = c->keyA.as<uint64_t>();
+        bp.vout[&s - &g.sh[0]] = rbp.vout[&s - &g.sh[0]] = c->valA.as<uint32_t>();
     }
     // ---- round 0c: partition by bucket, scattered straight into the owners' sort inputs.  Equal keys must meet in
     // descending suffix order (dq_suffix.cuh, end-of-text rule): every slice is packed descending and the slices are
@@ -471,7 +550,13 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
             for (size_t j = i + 1; j < G; ++j) off[d] += g.sh[j].h_small[d];
         uint32_t *gbase = c->hist.as<uint32_t>() + rx::kMaxPasses * rx::kRadix;
         DQ_CK(top, cudaMemcpyAsync(gbase, off, sizeof off, cudaMemcpyHostToDevice, c->stream));
-        DQ_SUB(top, c, policy_pass(s, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), bp, s.own_cnt));
+        if (run_heavy) {
+            rbp.T = c->text.as<uint8_t>();
+            rbp.run_end = c->runend.as<uint32_t>();
+            DQ_SUB(top, c, policy_pass(s, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), rbp, s.own_cnt));
+        } else {
+            DQ_SUB(top, c, policy_pass(s, c->partK.as<uint64_t>(), c->partV.as<uint32_t>(), bp, s.own_cnt));
+        }
     }
     DQ_TRY(group_barrier(top));
     DQ_TRY(group_mark(top, "r0_partition_exchange"));
@@ -537,44 +622,20 @@ int group_sort(dq_ctx *top, const uint8_t *text, uint32_t n, int32_t *sa_out)
     DQ_TRY(group_mark(top, "r0_route_updates"));
 
     // ---- equal-byte runs (dq_suffix.cuh): a text full of them (zero padding of executables) is refined by run length
-    // in round 1 and carries a depth per group from then on, like the one-GPU path.  Every shard then needs the whole
-    // text and its run ends (peer copies of the slices + three local kernels), and the rounds read ISA through peer
-    // pointers whatever their size: only the suffixes outside runs fetch a rank, and they fetch it at their own depth.
-    uint64_t uniform_total = 0;
-    for (Shard &s : g.sh) uniform_total += s.own_cnt ? s.h_small[32] : 0;
-    const bool run_aware = ac.bits == 8 && total_active > 0 && uniform_total * 64 >= n && !getenv("DQ_GROUP_NO_RUNS");
-    g.runend_n = 0;
+    // in round 1 and carries a depth per group from then on, like the one-GPU path.  Every shard has the whole text and
+    // its run ends by now (group_text_and_run_ends), and the rounds read ISA through peer pointers whatever their size:
+    // only the suffixes outside runs fetch a rank, and they fetch it at their own depth.
+    const bool run_aware = run_heavy && total_active > 0;
     if (run_aware) {
-        DQ_TRY(group_barrier(top));
         DQ_TRY(for_shards(top, [&](size_t i) -> int {
             Shard &t = g.sh[i];
             dq_ctx *c = t.c;
-            DQ_TRY(ensure(c, c->text, (size_t)n + 64));
-            DQ_CK(c, cudaMemsetAsync(c->text.as<uint8_t>() + n, 0, 64, c->stream));
-            for (Shard &s : g.sh)
-                if (s.own_cnt)
-                    DQ_CK(c, cudaMemcpyAsync(c->text.as<uint8_t>() + s.own_begin, s.slice.p, s.own_cnt, cudaMemcpyDefault, c->stream));
-            const size_t n4 = (size_t)n * 4;
-            DQ_TRY(ensure(c, c->runend, n4));
-            const uint32_t ntiles = (uint32_t)div_up(n, sx::kRunTile);
-            DQ_TRY(ensure(c, c->runtile, (size_t)ntiles * 8));
-            uint32_t *tile_first = c->runtile.as<uint32_t>(), *next_after = tile_first + ntiles;
-            auto k1 = sx::run_tile_first_kernel;
-            DQ_LAUNCH(k1, ntiles, 256, 0, c->stream, c->text.as<uint8_t>(), n, tile_first);
-            auto k2 = sx::run_tile_scan_kernel;
-            DQ_LAUNCH(k2, 1, 1024, 0, c->stream, tile_first, ntiles, n, next_after);
-            auto k3 = sx::run_end_kernel;
-            DQ_LAUNCH(k3, ntiles, 256, 0, c->stream, c->text.as<uint8_t>(), n, next_after, c->runend.as<uint32_t>());
-            c->stats.kernel_launches += 3;
-            DQ_CK(c, cudaGetLastError());
             DQ_TRY(ensure(c, c->depthA, (size_t)std::max<uint32_t>(t.cnt, 1) * 4));
             DQ_TRY(ensure(c, c->depthB, (size_t)std::max<uint32_t>(t.cnt, 1) * 4));
             t.depth_cur = c->depthA.as<uint32_t>();
             t.depth_nxt = c->depthB.as<uint32_t>();
             return DQ_OK;
         }));
-        g.runend_n = n;
-        DQ_TRY(group_mark(top, "runs_text_and_run_ends"));
     }
     bool first_round = true;
 

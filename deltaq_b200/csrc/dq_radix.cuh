@@ -174,8 +174,19 @@ constexpr size_t pass_smem_bytes()
 // ---- what a pass sorts by and where it puts the result ------------------------------------------------------
 // A policy names the digit of a key and stores one ranked pair.  `dst` is the pair's index inside the output
 // sequence of its digit, counted from gbase[digit] (for the plain pass: the global output index).
+// digit of a pair under a policy: from the key alone, or -- kDigitFromVal -- from key and value
+template <typename Policy>
+__device__ __forceinline__ uint32_t digit_of(const Policy &pol, uint64_t key, uint32_t val)
+{
+    if constexpr (Policy::kDigitFromVal)
+        return pol.digit(key, val);
+    else
+        return pol.digit(key);
+}
+
 struct PlainPolicy {
     static constexpr bool kHasVal = true;
+    static constexpr bool kDigitFromVal = false;
     int shift;
     uint32_t mask;
     uint64_t *__restrict__ kout;
@@ -192,14 +203,14 @@ struct PlainPolicy {
 // stable rank of every item of the warp among the tile's items with the same digit; wh[] = the warp's
 // running counters, pre-loaded with (slot of the digit in the tile) + (items of earlier warps)
 template <bool FULL, bool USE_MATCH, typename Policy>
-__device__ __forceinline__ void rank_and_stage(const uint64_t (&key)[kItems], uint32_t (&rk)[kItems / 2], uint32_t *wh,
-                                               uint64_t *skeys, uint32_t wbase, uint32_t tile_count, const Policy &pol,
-                                               int nbits)
+__device__ __forceinline__ void rank_and_stage(const uint64_t (&key)[kItems], const uint32_t (&val)[kItems],
+                                               uint32_t (&rk)[kItems / 2], uint32_t *wh, uint64_t *skeys, uint32_t wbase,
+                                               uint32_t tile_count, const Policy &pol, int nbits)
 {
     const unsigned lane = lane_id();
 #pragma unroll
     for (int j = 0; j < kItems; ++j) {
-        const uint32_t dj = pol.digit(key[j]);
+        const uint32_t dj = digit_of(pol, key[j], val[j]);
         unsigned peers = match_digit<USE_MATCH>(dj, nbits);
         bool valid = true;
         if (!FULL) {
@@ -241,10 +252,20 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
         const uint32_t li = wbase + j * 32;
         key[j] = (FULL || li < tile_count) ? ld_stream(kin + tile_base + li) : ~0ull;
     }
+    // values: requested after the early counts, so that they land during the look-back and the ranking -- unless the
+    // digit depends on them
+    uint32_t val[kItems];
+    if (Policy::kDigitFromVal) {
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            const uint32_t li = wbase + j * 32;
+            val[j] = (FULL || li < tile_count) ? ld_stream(vin + tile_base + li) : 0u;
+        }
+    }
     uint32_t *wh = whist + warp * kRadix;
 #pragma unroll
     for (int j = 0; j < kItems; ++j)
-        if (FULL || wbase + j * 32 < tile_count) atomicAdd(&wh[pol.digit(key[j])], 1u);
+        if (FULL || wbase + j * 32 < tile_count) atomicAdd(&wh[digit_of(pol, key[j], val[j])], 1u);
     __syncthreads();
 
     // ---- 2. thread d: tile count of digit d, published immediately
@@ -263,11 +284,12 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     const int nbits = pol.nbits();
 
     // values are requested now and land during the look-back and the ranking
-    uint32_t val[kItems];
+    if (!Policy::kDigitFromVal) {
 #pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-        const uint32_t li = wbase + j * 32;
-        val[j] = (Policy::kHasVal && (FULL || li < tile_count)) ? ld_stream(vin + tile_base + li) : 0u;
+        for (int j = 0; j < kItems; ++j) {
+            const uint32_t li = wbase + j * 32;
+            val[j] = (Policy::kHasVal && (FULL || li < tile_count)) ? ld_stream(vin + tile_base + li) : 0u;
+        }
     }
 
     // exclusive scan of the 256 digit counts -> first slot of each digit inside the tile
@@ -323,9 +345,9 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
     // ---- 4. stable ranking; keys go straight to their slot
     uint32_t rk[kItems / 2];  // two 16-bit slots per register (slots are < kTile <= 65536)
     if (few_distinct)
-        rank_and_stage<FULL, true>(key, rk, wh, skeys, wbase, tile_count, pol, nbits);
+        rank_and_stage<FULL, true>(key, val, rk, wh, skeys, wbase, tile_count, pol, nbits);
     else
-        rank_and_stage<FULL, false>(key, rk, wh, skeys, wbase, tile_count, pol, nbits);
+        rank_and_stage<FULL, false>(key, val, rk, wh, skeys, wbase, tile_count, pol, nbits);
     // ---- 5. values through the same slots, then stream the tile out
     if (Policy::kHasVal) {
 #pragma unroll
@@ -338,8 +360,9 @@ __device__ __forceinline__ void onesweep_tile(const uint64_t *__restrict__ kin, 
         const uint32_t i = tid + j * kThreads;
         if (FULL || i < tile_count) {
             const uint64_t k = skeys[i];
-            const uint32_t dg = pol.digit(k);
-            pol.store(dg, sout[dg] + i, k, Policy::kHasVal ? svals[i] : 0u);
+            const uint32_t v = Policy::kHasVal ? svals[i] : 0u;
+            const uint32_t dg = digit_of(pol, k, v);
+            pol.store(dg, sout[dg] + i, k, v);
         }
     }
 }
