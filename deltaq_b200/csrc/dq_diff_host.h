@@ -789,12 +789,11 @@ struct PipelineShape {
             }
         }
 #endif
-        // Few cores (one process per GPU sharing a host: 4 cores per rank on an 8-GPU box with 32) still get helpers: the
-        // long extensions come at the end of a call, when the scan and the writers have little left to do, and idle
-        // helpers sleep (wait_step)
+        // Few cores (one process per GPU sharing a host: 4 cores per rank on an 8-GPU box with 32) get no helpers: with
+        // {2,1} on 4 cores the end-to-end step of eight concurrent ranks went from 13.7 to 24.1 ms (oversubscription
+        // while the scan still polls the device); measured, bench.py under torchrun, N=8
         if (hw >= 12) return PipelineShape{3, 2};
-        if (hw >= 6) return PipelineShape{2, 2};
-        if (hw >= 3) return PipelineShape{2, 1};
+        if (hw >= 6) return PipelineShape{1, 2};
         return PipelineShape{0, 1};
     }
 };
