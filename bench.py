@@ -244,6 +244,36 @@ def sort_config_record(ctx, torch, text, name, peak, reps=3):
 
 # ---- one device group over all GPUs, driven by rank 0 (N > 1) ---------------------------------------------------------
 
+def diff_create_record(ctx, old, new, reps=3):
+    """Diff.Create as a whole (Diff.cs:27-242): dq_cuda_bsdiff_patch = streams + header + the three bzip2 sections
+    produced block-parallel on the host, against the same streams compressed serially (what a BZip2OutputStream per
+    section costs with libbz2).  One record beside the headline; never inside a timed region of `value` / `e2e`."""
+    import bz2
+    try:
+        times = []
+        patch = None
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            patch = ctx.bsdiff_patch(old, new)
+            times.append(time.perf_counter() - t0)
+        streams = ctx.bsdiff_streams(old, new)
+        t0 = time.perf_counter()
+        serial = [bz2.compress(streams[k]) for k in ("ctrl", "diff", "extra")]
+        serial_s = time.perf_counter() - t0
+        cl = int.from_bytes(patch[8:16], "little")
+        dl = int.from_bytes(patch[16:24], "little")
+        same = (bz2.decompress(patch[32:32 + cl]) == streams["ctrl"] and
+                bz2.decompress(patch[32 + cl:32 + cl + dl]) == streams["diff"] and
+                bz2.decompress(patch[32 + cl + dl:]) == streams["extra"])
+        best = min(times[1:])
+        return {"call": "dq_cuda_bsdiff_patch (pageable host buffers in, BSDIFF40 file out)", "ms": best * 1e3,
+                "new_MBps": new.size / best / 1e6, "patch_bytes": len(patch),
+                "serial_bz2_ms": serial_s * 1e3, "serial_bz2_bytes": 32 + sum(len(x) for x in serial),
+                "sections_decode_to_the_streams": bool(same), "host_threads": len(os.sched_getaffinity(0))}
+    except Exception as e:   # reported, not fatal: the headline line must still print
+        return {"error": repr(e)}
+
+
 def sharded_record(devices, workers, lib=None, scale=1.0):
     """`lib`/`scale`: the CPU tests run this function on the logic emulator with tiny inputs."""
     import oracle
@@ -486,8 +516,10 @@ def main():
     peak, peak_src = measured_peak()
     extras = None
     sharded = None
+    diff_create = None
     if not args.no_extras:
         if world == 1:
+            diff_create = diff_create_record(ctx, old, new)
             # BASELINE's other single-GPU configs, device-resident sort only (bounded: a few hundred ms in all)
             extras = [sort_config_record(ctx, torch, w.c1_uniform(), "C1: 1 MiB uniform random bytes", peak, reps=5),
                       sort_config_record(ctx, torch, w.c3_repetitive(), "C3: 64 MiB repetitive text", peak, reps=2),
@@ -559,6 +591,8 @@ def main():
             "clocks": clocks,
             "cpu_baseline": cpu,
         }
+        if diff_create is not None:
+            line["diff_create"] = diff_create
         if extras is not None:
             line["other_configs"] = extras
         if sharded is not None:

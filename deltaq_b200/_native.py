@@ -52,7 +52,7 @@ EXPORTS = [
     "dq_cuda_get_pass_times", "dq_cuda_get_round_times",
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
     "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
-    "dq_cuda_patch_apply",
+    "dq_cuda_patch_apply", "dq_cuda_bz2_bound", "dq_cuda_bz2_compress", "dq_cuda_bsdiff_patch",
     "dq_cuda_radix_sort_pairs", "dq_cuda_radix_sort_pairs_device",
 ]
 
@@ -85,11 +85,16 @@ class Library:
         L.dq_cuda_bsdiff_streams.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_greedy_emit.argtypes = [vp, vp, i32, vp, i32, vp, vp, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_patch_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64]
+        L.dq_cuda_bz2_bound.argtypes = [i64]
+        L.dq_cuda_bz2_compress.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+        L.dq_cuda_bsdiff_patch.argtypes = [vp, vp, i32, vp, i32, ctypes.c_int, ctypes.POINTER(vp),
+                                           ctypes.POINTER(i64)]
         L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
         L.dq_cuda_radix_sort_pairs_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         for name in EXPORTS:
-            if name != "dq_cuda_last_error":
+            if name not in ("dq_cuda_last_error", "dq_cuda_bz2_bound"):
                 getattr(L, name).restype = ctypes.c_int
+        L.dq_cuda_bz2_bound.restype = i64
         self.L = L
 
 
@@ -125,6 +130,31 @@ def patch_apply(old, ctrl, diff, extra, new_size, lib=None):
     if rc != DQ_OK:
         raise NativeError(rc, "dq_cuda_patch_apply: bad arguments")
     return out
+
+
+def bz2_compress(sections, level=0, threads=0, lib=None, info=None):
+    """dq_cuda_bz2_compress: every section (bytes-like / uint8 arrays) as one ordinary bzip2 stream, blocks compressed
+    in parallel by one crew of host threads.  level 1..9 = bzip2's; 0 = chosen per section for the thread count.
+    Returns a list of bytes.  info (a list, optional) receives (level, blocks, serial_fallback) per section."""
+    lib = lib or default_library()
+    arrs = [np.ascontiguousarray(np.frombuffer(x, dtype=np.uint8) if not isinstance(x, np.ndarray) else x)
+            for x in sections]
+    k = len(arrs)
+    if k == 0:
+        return []
+    outs = [np.empty(int(lib.L.dq_cuda_bz2_bound(a.size)), dtype=np.uint8) for a in arrs]
+    src = (ctypes.c_void_p * k)(*[a.ctypes.data if a.size else None for a in arrs])
+    dst = (ctypes.c_void_p * k)(*[o.ctypes.data for o in outs])
+    lens = (ctypes.c_int64 * k)(*[a.size for a in arrs])
+    caps = (ctypes.c_int64 * k)(*[o.size for o in outs])
+    got = (ctypes.c_int64 * k)()
+    inf = (ctypes.c_int32 * (3 * k))()
+    rc = lib.L.dq_cuda_bz2_compress(src, lens, k, int(level), int(threads), dst, caps, got, inf)
+    if rc != DQ_OK:
+        raise NativeError(rc, "dq_cuda_bz2_compress failed (bad arguments, or libbz2 missing)")
+    if info is not None:
+        info[:] = [(inf[3 * i], inf[3 * i + 1], inf[3 * i + 2]) for i in range(k)]
+    return [outs[i][:got[i]].tobytes() for i in range(k)]
 
 
 class PinnedArray:
@@ -272,6 +302,16 @@ class Context:
             return {"ctrl": view(out.ctrl, out.ctrl_len), "diff": view(out.diff, out.diff_len),
                     "extra": view(out.extra, out.extra_len), "search_visits": out.search_visits}
         return self._streams(out)
+
+    def bsdiff_patch(self, old, new, level=0):
+        """dq_cuda_bsdiff_patch: the complete BSDIFF40 file for (old, new) as bytes -- sort, search and greedy loop as
+        bsdiff_streams, then the three bzip2 sections produced block-parallel on the host."""
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        with self._gate:   # the patch buffer belongs to the context: copy it out before another call can replace it
+            self._check(self.lib.L.dq_cuda_bsdiff_patch(self._h, _addr(old), old.size, _addr(new), new.size, int(level),
+                                                        ctypes.byref(p), ctypes.byref(n)))
+            return ctypes.string_at(p.value, n.value)
 
     @staticmethod
     def _streams(out):

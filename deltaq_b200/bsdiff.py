@@ -7,9 +7,10 @@ container (Diff.cs:54-70, :226-241, Constants.cs:5-12).  The suffix sort (Diff.c
 ``Search`` call (Diff.cs:106) run on the GPU; the greedy scan/emit loop (Diff.cs:100-223) runs on the
 host inside libdeltaq_cuda (csrc/dq_diff_host.h), consuming the bulk (pos, len) table.
 
-The three streams are compressed with Python's ``bz2`` (libbz2).  The reference uses SharpZipLib 1.4.2
-(un-vendored third party); compressed bytes are not claimed identical to it -- the uncompressed
-ctrl/diff/extra streams and the header fields are (tests/test_bsdiff_gpu.py).
+The three streams are compressed by libbz2, block-parallel on the host (csrc/dq_bz2_host.h: the bytes equal what
+serial libbz2 writes at the chosen level).  The reference uses SharpZipLib 1.4.2 (un-vendored third party);
+compressed bytes are not claimed identical to it -- the uncompressed ctrl/diff/extra streams and the header fields
+are (tests/test_bsdiff_gpu.py).
 
 ``Patch.apply`` mirrors Patch.Apply (Patch.cs:25-168); it is not on the hot path and exists for the
 reference's round-trip tests (BsDiffTests.cs:30-78).
@@ -112,6 +113,12 @@ class Diff:
         o = as_bytes_array(old_data, "oldData")
         w = as_bytes_array(new_data, "newData")
 
+        if isinstance(suffix_sort, CudaSuffixSort):
+            # one native call: streams as create_streams(), header and sections assembled in the library
+            # (dq_cuda_bsdiff_patch); the bytes and the final stream position are those of the general path below
+            output.write(suffix_sort.context.bsdiff_patch(o, w))
+            return
+
         header = bytearray(HEADER_SIZE)
         header[0:8] = write_packed_long(SIGNATURE)
         header[24:32] = write_packed_long(w.size)
@@ -119,9 +126,8 @@ class Diff:
         output.write(bytes(header))
 
         streams = create_streams(o, w, suffix_sort)
-        ctrl = bz2.compress(streams["ctrl"])
-        diff = bz2.compress(streams["diff"])
-        extra = bz2.compress(streams["extra"])
+        # Diff.cs:85-87: three bzip2 sections -- here one crew of host threads over the blocks of all three
+        ctrl, diff, extra = _native.bz2_compress([streams["ctrl"], streams["diff"], streams["extra"]])
 
         output.write(ctrl)
         header[8:16] = write_packed_long(len(ctrl))

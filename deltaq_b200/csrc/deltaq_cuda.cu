@@ -31,6 +31,7 @@
 #include "dq_dist.cuh"
 #include "dq_diff_host.h"
 #include "dq_patch_host.h"
+#include "dq_bz2_host.h"
 
 namespace {
 
@@ -108,6 +109,7 @@ struct dq_ctx {
 
     // diff streams (host)
     dq::diffhost::Streams streams;
+    std::vector<uint8_t> patch, patch_tail[2];  // dq_cuda_bsdiff_patch: the BSDIFF40 file / scratch for two sections
     PinBuf h_pos, h_len;             // full table: fallback only
     PinBuf h_code, h_heads, h_tiles; // coded table (encode_table_kernel)
     DevBuf d_code, d_headcount;
@@ -1167,11 +1169,10 @@ int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *d_old, int32_t n, c
     return search_common(ctx, d_old, n, d_I_or_null, d_new, m, scan_begin, count, d_pos_out, d_len_out, true);
 }
 
-int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
-                           dq_diff_streams *out)
+// body of dq_cuda_bsdiff_streams; the caller holds ctx->mu
+static int bsdiff_streams_locked(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
+                                 dq_diff_streams *out)
 {
-    if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(ctx->mu);
     DQ_TRY(check_args(ctx, n >= 0 && m >= 0 && (n == 0 || old_) && (m == 0 || new_), "bsdiff_streams: bad arguments"));
     // the host loop looks up to 64 positions ahead in 32-bit arithmetic
     DQ_TRY(check_args(ctx, m <= INT32_MAX - 64, "bsdiff_streams: newData longer than INT32_MAX - 64 bytes"));
@@ -1321,6 +1322,98 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
         }
     }
     export_streams(ctx, out);
+    return DQ_OK;
+}
+
+int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
+                           dq_diff_streams *out)
+{
+    if (!ctx || !out) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return bsdiff_streams_locked(ctx, old_, n, new_, m, out);
+}
+
+int64_t dq_cuda_bz2_bound(int64_t n) { return n < 0 ? -1 : dq::bz2host::bound(n); }
+
+int dq_cuda_bz2_compress(const uint8_t *const *src, const int64_t *len, int count, int level, int threads,
+                         uint8_t *const *out, const int64_t *cap, int64_t *out_len, int32_t *info)
+{
+    if (count < 0 || count > 64 || level < 0 || level > 9 || threads < 0) return DQ_ERR_INVALID_ARGUMENT;
+    if (count && (!src || !len || !out || !cap || !out_len)) return DQ_ERR_INVALID_ARGUMENT;
+    dq::bz2host::StreamJob jobs[64];
+    for (int s = 0; s < count; ++s) {
+        if (len[s] < 0 || (len[s] && !src[s]) || !out[s] || cap[s] < dq::bz2host::bound(len[s])) return DQ_ERR_INVALID_ARGUMENT;
+        jobs[s].src = src[s];
+        jobs[s].len = len[s];
+        jobs[s].out = out[s];
+        jobs[s].cap = cap[s];
+    }
+    int rc;
+    try {
+        rc = dq::bz2host::compress_streams(jobs, count, level, threads);
+    } catch (const std::bad_alloc &) {
+        return DQ_ERR_OUT_OF_MEMORY;
+    } catch (...) {
+        return DQ_ERR_INTERNAL;
+    }
+    if (rc != 0) return DQ_ERR_INTERNAL;  // libbz2 missing or failing; the buffers were checked above
+    for (int s = 0; s < count; ++s) {
+        out_len[s] = jobs[s].out_len;
+        if (info) {
+            info[3 * s] = jobs[s].level;
+            info[3 * s + 1] = jobs[s].pieces;
+            info[3 * s + 2] = jobs[s].fell_back ? 1 : 0;
+        }
+    }
+    return DQ_OK;
+}
+
+int dq_cuda_bsdiff_patch(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m, int level,
+                         const uint8_t **patch, int64_t *patch_len)
+{
+    if (!ctx || !patch || !patch_len || level < 0 || level > 9) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    dq_diff_streams st;
+    DQ_TRY(bsdiff_streams_locked(ctx, old_, n, new_, m, &st));
+    // Diff.cs:54-70, :226-241: header (signature, compressed sizes of ctrl and diff, size of newData), then the sections
+    namespace bz = dq::bz2host;
+    try {
+        const int64_t caps[3] = {bz::bound(st.ctrl_len), bz::bound(st.diff_len), bz::bound(st.extra_len)};
+        ctx->patch.resize((size_t)(32 + caps[0]));
+        ctx->patch_tail[0].resize((size_t)caps[1]);
+        ctx->patch_tail[1].resize((size_t)caps[2]);
+        bz::StreamJob jobs[3];
+        const uint8_t *srcs[3] = {st.ctrl, st.diff, st.extra};
+        const int64_t lens[3] = {st.ctrl_len, st.diff_len, st.extra_len};
+        uint8_t *outs[3] = {ctx->patch.data() + 32, ctx->patch_tail[0].data(), ctx->patch_tail[1].data()};
+        for (int s = 0; s < 3; ++s) {
+            jobs[s].src = srcs[s];
+            jobs[s].len = lens[s];
+            jobs[s].out = outs[s];
+            jobs[s].cap = caps[s];
+        }
+        const int rc = bz::compress_streams(jobs, 3, level, 0);
+        if (rc != 0) {
+            ctx->err = rc == -3 ? "bsdiff_patch: libbz2 not found" : "bsdiff_patch: libbz2 failed";
+            return DQ_ERR_INTERNAL;
+        }
+        ctx->patch.resize((size_t)(32 + jobs[0].out_len + jobs[1].out_len + jobs[2].out_len));
+        uint8_t *p = ctx->patch.data();
+        auto packed = [](uint8_t *b, int64_t y) {  // SpanExtensions.WritePackedLong (SpanExtensions.cs:7-18), y >= 0 here
+            for (int i = 0; i < 8; ++i) b[i] = (uint8_t)((uint64_t)y >> (8 * i));
+        };
+        memcpy(p, "BSDIFF40", 8);
+        packed(p + 8, jobs[0].out_len);
+        packed(p + 16, jobs[1].out_len);
+        packed(p + 24, (int64_t)m);
+        memcpy(p + 32 + jobs[0].out_len, ctx->patch_tail[0].data(), (size_t)jobs[1].out_len);
+        memcpy(p + 32 + jobs[0].out_len + jobs[1].out_len, ctx->patch_tail[1].data(), (size_t)jobs[2].out_len);
+    } catch (const std::bad_alloc &) {
+        ctx->err = "bsdiff_patch: out of host memory";
+        return DQ_ERR_OUT_OF_MEMORY;
+    }
+    *patch = ctx->patch.data();
+    *patch_len = (int64_t)ctx->patch.size();
     return DQ_OK;
 }
 

@@ -149,6 +149,25 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
 int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                         const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out);
 
+/* ---- the patch file: Diff.Create as a whole ------------------------------------------------------------
+ * Replaces the three BZip2OutputStream sections of Diff.Create (Diff.cs:14-19, :85-87, :197-207, :226-241).
+ * bzip2 blocks are independent, so every section is cut where a serial libbz2 would start its blocks, the pieces
+ * are compressed on a crew of host threads by the system's libbz2 (dlopen'ed) and stitched bit by bit into ONE
+ * ordinary stream: the bytes are identical to what serial libbz2 writes at that level, so any bzip2 reader
+ * (Patch.cs:52-93) decodes them.  level 1..9 = bzip2's block size (9 = what `bzip2 -9` and Python's bz2 write);
+ * 0 = per section, the largest level that still leaves about two blocks per thread (C2's diff section: level 1,
+ * +0.5 % bytes, 10 pieces).  threads 0 = the CPUs the process may run on.  Pure host code, no context. */
+int64_t dq_cuda_bz2_bound(int64_t n);  /* capacity a caller must offer for n input bytes */
+/* `count` (<= 64) sections by one crew.  cap[s] >= dq_cuda_bz2_bound(len[s]).  info (may be NULL): 3 ints per section
+ * = level used, blocks, 1 if the section had to be compressed serially (never observed; counted for the tests). */
+int dq_cuda_bz2_compress(const uint8_t *const *src, const int64_t *len, int count, int level, int threads,
+                         uint8_t *const *out, const int64_t *cap, int64_t *out_len, int32_t *info);
+/* dq_cuda_bsdiff_streams + the header and the three sections: *patch is a complete BSDIFF40 file (Diff.cs:54-70:
+ * "BSDIFF40", packed lengths of the ctrl and diff sections, packed size of newData; then ctrl, diff, extra), owned by
+ * the context and valid until the next call on it. */
+int dq_cuda_bsdiff_patch(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m, int level,
+                         const uint8_t **patch, int64_t *patch_len);
+
 /* ---- Patch.Apply ------------------------------------------------------------------------------------
  * Patch.ApplyInternal (Patch.cs:95-168) on the three UNCOMPRESSED streams (the caller has un-bzip2'ed them, as
  * Patch.CreatePatchStreams :52-93 does): writes exactly new_size bytes to out.  Pure host code (the add loop of

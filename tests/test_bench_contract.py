@@ -99,3 +99,20 @@ def test_sharded_record_under_a_two_rank_gloo_job():
     assert "error" not in rec, rec.get("error")
     assert rec["devices"] == [0, 0] and rec["sort_c4"]["sufcheck"] == 0
     assert rec["sort_search_256MiB"]["table_equals_one_gpu_table"] is True
+
+
+def test_diff_create_record_on_the_emulator():
+    """bench.py's `diff_create` record (dq_cuda_bsdiff_patch against serial bzip2 of the same streams), on the CPU logic
+    emulator with a small pair."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu
+    import bench
+    from deltaq_b200 import CudaSuffixSort, workloads as w
+    sorter = CudaSuffixSort(_lib=emu.library())
+    try:
+        old, new = w.c2_exe_pair(200_000, 210_000)
+        rec = bench.diff_create_record(sorter.context, old, new, reps=1)
+    finally:
+        sorter.dispose()
+    assert "error" not in rec, rec.get("error")
+    assert rec["sections_decode_to_the_streams"] is True and rec["patch_bytes"] > 32

@@ -228,3 +228,29 @@ def test_broken_provider_is_rejected(sorter, kind):
     sa = np.empty(n, np.int32)
     sorter.sort(old, sa)
     assert np.array_equal(sa, oracle.sais(old))
+
+
+def test_native_patch_file(sorter):
+    """dq_cuda_bsdiff_patch: header (Diff.cs:54-70) + three sections, each ONE ordinary bzip2 stream holding exactly the
+    bytes of dq_cuda_bsdiff_streams; Patch.apply rebuilds `new`; every level gives the same streams."""
+    import bz2
+    from deltaq_b200 import bsdiff
+    from search_cases import structured_pairs
+    pairs = list(structured_pairs().values())[:4] + [(random_bytes(70000), random_bytes(70003, seed=9))]
+    for old, new in pairs:
+        ref = bsdiff.create_streams(old, new, sorter)
+        for level in (0, 1, 9):
+            patch = sorter.context.bsdiff_patch(old, new, level=level)
+            assert patch[:8] == b"BSDIFF40"
+            cl, dl, size = (bsdiff.read_packed_long(patch[8 + 8 * i:16 + 8 * i]) for i in range(3))
+            assert size == new.size
+            assert bz2.decompress(patch[32:32 + cl]) == ref["ctrl"]
+            assert bz2.decompress(patch[32 + cl:32 + cl + dl]) == ref["diff"]
+            assert bz2.decompress(patch[32 + cl + dl:]) == ref["extra"]
+            rebuilt = io.BytesIO()
+            bsdiff.Patch.apply(old, patch, rebuilt)
+            assert rebuilt.getvalue() == new.tobytes()
+        out = io.BytesIO()
+        out.write(b"xx")                      # Diff.Create writes at the stream's current position (Diff.cs:56)
+        bsdiff.Diff.create(old, new, out, sorter)
+        assert out.getvalue()[2:] == sorter.context.bsdiff_patch(old, new) and out.tell() == len(out.getvalue())

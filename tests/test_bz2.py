@@ -1,0 +1,128 @@
+"""Block-parallel bzip2 producer (deltaq_b200/csrc/dq_bz2_host.h) against serial libbz2 (Python's bz2).
+
+The reference writes the ctrl / diff / extra sections through BZip2OutputStream (Diff.cs:14-19, :85-87); Patch.cs:52-93
+reads them back with BZip2InputStream.  The producer here must emit ONE ordinary stream per section; stronger, its bytes
+must equal what serial libbz2 writes at the same level.  Pure host code: runs without a GPU.
+"""
+import bz2
+import ctypes
+import ctypes.util
+
+import numpy as np
+import pytest
+
+from deltaq_b200 import _native
+
+
+_libbz2 = ctypes.CDLL(ctypes.util.find_library("bz2") or "libbz2.so.1.0")
+
+
+def serial(data, level):
+    """Serial libbz2, one BZ2_bzBuffToBuffCompress call -- the entry the producer uses per piece.  (Python's bz2.compress
+    feeds BZ_RUN then BZ_FINISH; it writes the same bytes except when the LAST input byte is the one that fills a
+    block, where it ends with an extra block holding that byte alone: see test_block_boundaries_every_offset.)"""
+    data = bytes(data)
+    cap = len(data) + len(data) // 100 + 600
+    dst = ctypes.create_string_buffer(cap)
+    n = ctypes.c_uint(cap)
+    rc = _libbz2.BZ2_bzBuffToBuffCompress(dst, ctypes.byref(n), data, len(data), level, 0, 0)
+    assert rc == 0
+    return dst.raw[:n.value]
+
+
+def cases():
+    rng = np.random.default_rng(11)
+    out = {}
+    out["empty"] = np.zeros(0, np.uint8)
+    out["one"] = np.array([7], np.uint8)
+    out["four_equal"] = np.full(4, 9, np.uint8)
+    out["random_250k"] = rng.integers(0, 256, 250_000, dtype=np.uint8)
+    out["random_1M"] = rng.integers(0, 256, 1_000_003, dtype=np.uint8)
+    out["zeros_3M"] = np.zeros(3_000_000, np.uint8)
+    # diff-stream like: mostly zero with islands (C2's diff section is 96 % zeros)
+    d = np.zeros(2_500_000, np.uint8)
+    idx = rng.integers(0, d.size, 120_000)
+    d[idx] = rng.integers(1, 256, idx.size, dtype=np.uint8)
+    out["diff_like"] = d
+    # runs of every length around the run-length stage's thresholds (3, 4, 5, 255, 256, 259, 510)
+    parts = []
+    for i in range(9000):
+        L = [1, 2, 3, 4, 5, 254, 255, 256, 259, 510, 511][i % 11]
+        parts.append(np.full(L, rng.integers(0, 256), np.uint8))
+    out["runs_mixed"] = np.concatenate(parts)
+    # text-like, several level-1 blocks
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(500)]
+    out["words"] = np.frombuffer(b" ".join(words[int(i)] for i in rng.integers(0, 500, 120_000)), dtype=np.uint8).copy()
+    return out
+
+
+CASES = cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("level", [1, 2, 5, 9])
+def test_bytes_equal_serial_libbz2(name, level):
+    data = CASES[name]
+    info = []
+    (z,) = _native.bz2_compress([data], level=level, threads=4, info=info)
+    assert info[0][0] == level and info[0][2] == 0, info     # no serial fallback: the split rule holds
+    assert bz2.decompress(z) == data.tobytes()
+    assert z == serial(data, level)
+
+
+def test_block_boundaries_every_offset():
+    """Inputs whose length walks across a block boundary byte by byte (level 1 closes a block at 99981 coded bytes),
+    random and run-heavy: the split must agree with libbz2 at every offset, including a run piece that overshoots the
+    limit and the length at which the last byte is the one that fills the block."""
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, 100_200, dtype=np.uint8)
+    runs = np.repeat(rng.integers(0, 256, 40_000, dtype=np.uint8), rng.integers(1, 9, 40_000))
+    # length of the runs text at which its coded size reaches the limit
+    coded, cut = 0, None
+    edges = np.flatnonzero(np.diff(runs.astype(np.int16)) != 0) + 1
+    for a, b in zip(np.concatenate([[0], edges]), np.concatenate([edges, [runs.size]])):
+        coded += (b - a) if b - a < 4 else 5
+        if coded >= 99_981:
+            cut = int(b)
+            break
+    assert cut is not None
+    differs_from_python = 0
+    for src, lens in ((base, range(99_960, 100_020)), (runs, range(cut - 30, cut + 30))):
+        sections = [src[:n] for n in lens]
+        info = []
+        got = _native.bz2_compress(sections, level=1, threads=4, info=info)
+        for n, z, inf in zip(lens, got, info):
+            assert inf[2] == 0, n
+            assert z == serial(src[:n], 1), n
+            assert bz2.decompress(z) == src[:n].tobytes()
+            differs_from_python += z != bz2.compress(src[:n].tobytes(), 1)
+    assert differs_from_python <= 2      # only the fills-the-block lengths
+
+
+def test_many_sections_one_crew_and_auto_level():
+    rng = np.random.default_rng(5)
+    ctrl = rng.integers(0, 256, 2592, dtype=np.uint8)
+    diff = CASES["diff_like"]
+    extra = CASES["random_1M"]
+    info = []
+    z = _native.bz2_compress([ctrl, diff, extra], level=0, threads=8, info=info)
+    for data, comp, inf in zip((ctrl, diff, extra), z, info):
+        assert inf[2] == 0 and 1 <= inf[0] <= 9
+        assert comp == serial(data, inf[0])
+    assert info[2][1] >= 10          # 1 MB of random bytes at the level chosen for 8 threads: about 10 blocks
+    one = _native.bz2_compress([extra], level=0, threads=1, info=info)
+    assert info[0][0] == 9 and one[0] == serial(extra, 9)   # one thread: nothing to gain from small blocks
+
+
+def test_thread_counts_agree():
+    data = CASES["words"]
+    ref = _native.bz2_compress([data], level=1, threads=1)[0]
+    for t in (2, 3, 16):
+        assert _native.bz2_compress([data], level=1, threads=t)[0] == ref
+
+
+def test_bad_arguments():
+    with pytest.raises(_native.NativeError):
+        _native.bz2_compress([b"abc"], level=10)
+    with pytest.raises(_native.NativeError):
+        _native.bz2_compress([b"abc"], level=-1)
