@@ -32,6 +32,7 @@ internal static unsafe partial class Native
     [LibraryImport(Lib)] internal static partial int dq_cuda_suffix_sort(IntPtr ctx, byte* text, int n, int* saOut);
     [LibraryImport(Lib)] internal static partial int dq_cuda_bsdiff_search(IntPtr ctx, byte* old, int n, int* iOrNull,
         byte* @new, int m, int scanBegin, int count, int* posOut, int* lenOut);
+    [LibraryImport(Lib)] internal static partial int dq_cuda_lcp(IntPtr ctx, byte* text, int n, int* iOrNull, int* lcpOut);
     [LibraryImport(Lib)] internal static partial int dq_cuda_patch_apply(byte* old, long n, byte* ctrl, long ctrlLen,
         byte* diff, long diffLen, byte* extra, long extraLen, byte* @out, long newSize);
 
@@ -123,6 +124,18 @@ public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposa
             fixed (int* p = pos) fixed (int* l = len)
                 Native.Check(_ctx, Native.dq_cuda_bsdiff_search(_ctx, o, oldData.Length, i, w, newData.Length,
                                                                 0, newData.Length, p, l));
+    }
+
+    /// <summary>LCP array of textBuffer under suffixBuffer (any suffix array of it; validated natively):
+    /// lcp[0] = 0, lcp[r] = common prefix length of suffixes suffixBuffer[r-1] and suffixBuffer[r].  An empty
+    /// suffixBuffer means "the array my last Sort of this text left on the device".</summary>
+    public void LcpArray(ReadOnlySpan<byte> textBuffer, ReadOnlySpan<int> suffixBuffer, Span<int> lcp)
+    {
+        if (lcp.Length != textBuffer.Length || (suffixBuffer.Length != 0 && suffixBuffer.Length != textBuffer.Length))
+            throw new ArgumentException("Text, suffix and LCP buffers should have the same length");
+        lock (_gate)
+            fixed (byte* t = textBuffer) fixed (int* i = suffixBuffer) fixed (int* l = lcp)
+                Native.Check(_ctx, Native.dq_cuda_lcp(_ctx, t, textBuffer.Length, suffixBuffer.Length == 0 ? null : i, l));
     }
 
     public void Dispose()

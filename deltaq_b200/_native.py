@@ -51,7 +51,7 @@ EXPORTS = [
     "dq_cuda_create", "dq_cuda_destroy", "dq_cuda_last_error", "dq_cuda_get_stats", "dq_cuda_set_timing",
     "dq_cuda_get_pass_times", "dq_cuda_get_round_times",
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
-    "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
+    "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_lcp", "dq_cuda_lcp_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
     "dq_cuda_patch_apply", "dq_cuda_bz2_bound", "dq_cuda_bz2_compress", "dq_cuda_bsdiff_patch",
     "dq_cuda_radix_sort_pairs", "dq_cuda_radix_sort_pairs_device",
 ]
@@ -82,6 +82,8 @@ class Library:
         L.dq_cuda_suffix_sort_device.argtypes = [vp, vp, i32, vp]
         L.dq_cuda_bsdiff_search.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
         L.dq_cuda_bsdiff_search_device.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
+        L.dq_cuda_lcp.argtypes = [vp, vp, i32, vp, vp]
+        L.dq_cuda_lcp_device.argtypes = [vp, vp, i32, vp, vp]
         L.dq_cuda_bsdiff_streams.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_greedy_emit.argtypes = [vp, vp, i32, vp, i32, vp, vp, ctypes.POINTER(DqDiffStreams)]
         L.dq_cuda_patch_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64]
@@ -302,6 +304,19 @@ class Context:
             return {"ctrl": view(out.ctrl, out.ctrl_len), "diff": view(out.diff, out.diff_len),
                     "extra": view(out.extra, out.extra_len), "search_visits": out.search_visits}
         return self._streams(out)
+
+    def lcp(self, text, I=None, out=None):
+        """dq_cuda_lcp: LCP array (int32, n entries, lcp[0] = 0) of `text` under the suffix array I, or under the one the
+        last suffix_sort of this context left resident (I=None)."""
+        n = text.size
+        if out is None:
+            out = np.empty(n, dtype=np.int32)
+        assert out.dtype == np.int32 and out.size == n
+        self._check(self.lib.L.dq_cuda_lcp(self._h, _addr(text), n, _addr(I) if I is not None else None, _addr(out)))
+        return out
+
+    def lcp_device(self, d_text, n, d_I, d_out):
+        self._check(self.lib.L.dq_cuda_lcp_device(self._h, d_text, n, d_I, d_out))
 
     def bsdiff_patch(self, old, new, level=0):
         """dq_cuda_bsdiff_patch: the complete BSDIFF40 file for (old, new) as bytes -- sort, search and greedy loop as

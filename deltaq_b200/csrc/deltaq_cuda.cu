@@ -1169,6 +1169,22 @@ int dq_cuda_bsdiff_search_device(dq_ctx *ctx, const uint8_t *d_old, int32_t n, c
     return search_common(ctx, d_old, n, d_I_or_null, d_new, m, scan_begin, count, d_pos_out, d_len_out, true);
 }
 
+int dq_cuda_lcp(dq_ctx *ctx, const uint8_t *text, int32_t n, const int32_t *I_or_null, int32_t *lcp_out)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!I_or_null && n > 0 && lcp_out && ctx->group && ctx->group->n == (uint32_t)n) return group_lcp(ctx, n, lcp_out);
+    return lcp_common(ctx, text, n, I_or_null, lcp_out, false);
+}
+
+int dq_cuda_lcp_device(dq_ctx *ctx, const uint8_t *d_text, int32_t n, const int32_t *d_I_or_null, int32_t *d_lcp_out)
+{
+    if (!ctx) return DQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!d_I_or_null && n > 0 && d_lcp_out && ctx->group && ctx->group->n == (uint32_t)n) return group_lcp(ctx, n, d_lcp_out);
+    return lcp_common(ctx, d_text, n, d_I_or_null, d_lcp_out, true);
+}
+
 // body of dq_cuda_bsdiff_streams; the caller holds ctx->mu
 static int bsdiff_streams_locked(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                                  dq_diff_streams *out)

@@ -1058,5 +1058,19 @@ int group_search_common(dq_ctx *top, const uint8_t *old_, int32_t n, const int32
     top->stats.search_index_ms += index_ms;
     top->stats.search_ms += index_ms;
     return DQ_OK;
-    return group_search(top, (uint32_t)n, new_, (uint32_t)m, (uint32_t)scan_begin, (uint32_t)count, pos_out, len_out);
+}
+
+// LCP array of a text the group has sorted (resident, sharded): index built by all GPUs, then one copy leaves shard 0
+int group_lcp(dq_ctx *top, int32_t n, int32_t *lcp_out)
+{
+    Group &g = *top->group;
+    DQ_TRY(group_replicate_index(top));
+    DQ_TRY(group_sync(top));
+    DQ_TRY(group_build_index(top, (uint32_t)n));
+    DQ_TRY(group_sync(top));
+    dq_ctx *c = g.sh[0].c;
+    DQ_CK(top, cudaSetDevice(c->device));
+    DQ_CK(top, cudaMemcpyAsync(lcp_out, c->lcp.p, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    DQ_CK(top, cudaStreamSynchronize(c->stream));
+    return DQ_OK;
 }

@@ -414,3 +414,24 @@ int search_common(dq_ctx *ctx, const uint8_t *old_, int32_t n, const int32_t *I,
     if (count) DQ_CK(ctx, cudaEventElapsedTime(&ctx->stats.search_index_ms, ctx->ev0, ctx->ev_index));
     return DQ_OK;
 }
+
+// dq_cuda_lcp / dq_cuda_lcp_device: the LCP array the search is anchored on, for the caller.  lcp_out[r] = length of the
+// longest common prefix of the suffixes SA[r-1] and SA[r]; lcp_out[0] = 0.
+int lcp_common(dq_ctx *ctx, const uint8_t *text, int32_t n, const int32_t *I, int32_t *lcp_out, bool device_ptrs)
+{
+    DQ_TRY(check_args(ctx, n >= 0 && (n == 0 || lcp_out) && (!I || n == 0 || text), "lcp: bad arguments"));
+    if (n == 0) return DQ_OK;
+    DQ_CK(ctx, cudaSetDevice(ctx->device));
+    if (I) {
+        ctx->stats = dq_stats{};
+        DQ_TRY(adopt_index(ctx, text, (uint32_t)n, I, device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    } else {
+        DQ_TRY(check_args(ctx, ctx->resident_n == n,
+                          "lcp: I is NULL but no suffix array of this length is resident on the device"));
+    }
+    DQ_TRY(build_lcp(ctx, (uint32_t)n));
+    DQ_CK(ctx, cudaMemcpyAsync(lcp_out, ctx->lcp.p, (size_t)n * 4,
+                               device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}

@@ -92,3 +92,15 @@ class CudaSuffixSort:
             raise ValueError("suffixes must be contiguous")
         self._ctx.suffix_sort(t, suffixes)
         return None
+
+    def lcp_array(self, text, suffixes=None):
+        """LCP array of `text` (int32, lcp[0] = 0, lcp[r] = common prefix of suffixes r-1 and r in sorted order): the
+        extension SURVEY.md 8(f) rank 4 proposes for ISuffixSort providers.  suffixes=None uses the suffix array this
+        provider's last sort(text, ...) left on the device; otherwise any suffix array of `text` (validated)."""
+        t = as_bytes_array(text)
+        I = None
+        if suffixes is not None:
+            I = np.ascontiguousarray(suffixes, dtype=np.int32)
+            if I.size != t.size:
+                raise ValueError(LENGTH_MISMATCH)
+        return self._ctx.lcp(t, I)

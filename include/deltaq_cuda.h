@@ -149,6 +149,16 @@ int dq_cuda_bsdiff_streams(dq_ctx *ctx, const uint8_t *old_, int32_t n, const ui
 int dq_cuda_greedy_emit(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m,
                         const int32_t *pos_tab, const int32_t *len_tab, dq_diff_streams *out);
 
+/* ---- LCP array ("on-device LCP array as an ISuffixSort extension") ------------------
+ * lcp_out[r] = length of the longest common prefix of the suffixes SA[r-1] and SA[r] of `text`, lcp_out[0] = 0; n
+ * entries.  This is level 0 of the index every bulk search is anchored on (built along the text, Phi/PLCP order, then
+ * permuted to rank order), so a following dq_cuda_bsdiff_search with I == NULL reuses it.  I_or_null as for
+ * dq_cuda_bsdiff_search: NULL = the suffix array the last dq_cuda_suffix_sort of this context left resident (n must
+ * match), else n (or n+1) caller-supplied entries, validated to be a permutation.  The reference has no LCP array (its
+ * Search is a binary search over I, Diff.cs:267-298); checked against Kasai's algorithm in tests/. */
+int dq_cuda_lcp(dq_ctx *ctx, const uint8_t *text, int32_t n, const int32_t *I_or_null, int32_t *lcp_out);
+int dq_cuda_lcp_device(dq_ctx *ctx, const uint8_t *d_text, int32_t n, const int32_t *d_I_or_null, int32_t *d_lcp_out);
+
 /* ---- the patch file: Diff.Create as a whole ------------------------------------------------------------
  * Replaces the three BZip2OutputStream sections of Diff.Create (Diff.cs:14-19, :85-87, :197-207, :226-241).
  * bzip2 blocks are independent, so every section is cut where a serial libbz2 would start its blocks, the pieces

@@ -44,6 +44,8 @@ def lib():
         L.oracle_sufcheck.restype = ctypes.c_int
         L.oracle_verify_sorted.argtypes = [u8p, ctypes.c_int32, i32p]
         L.oracle_verify_sorted.restype = ctypes.c_int32
+        L.oracle_lcp_kasai.argtypes = [u8p, ctypes.c_int32, i32p, i32p, i32p]
+        L.oracle_lcp_kasai.restype = None
         L.oracle_verify_pairs.argtypes = [u8p, ctypes.c_int32, i32p, ctypes.c_void_p, ctypes.c_int64]
         L.oracle_verify_pairs.restype = ctypes.c_int64
         L.oracle_sa_naive.argtypes = [u8p, ctypes.c_int32, i32p]
@@ -130,6 +132,17 @@ def verify_pairs(text, sa, idx):
     s = np.ascontiguousarray(sa, dtype=np.int32)
     ix = np.ascontiguousarray(idx, dtype=np.int64)
     return int(lib().oracle_verify_pairs(_ptr(t), t.size, _ptr(s), _ptr(ix), ix.size))
+
+
+def lcp_array(text, sa):
+    """LCP[r] = longest common prefix of suffixes sa[r-1], sa[r]; LCP[0] = 0 (definition; Kasai's evaluation order)."""
+    t = _u8(text)
+    s = np.ascontiguousarray(sa, dtype=np.int32)
+    out = np.zeros(t.size, dtype=np.int32)
+    rank = np.empty(t.size, dtype=np.int32)
+    if t.size:
+        lib().oracle_lcp_kasai(_ptr(t), t.size, _ptr(s), _ptr(rank), _ptr(out))
+    return out
 
 
 def make_I(sa):

@@ -132,3 +132,28 @@ void oracle_sa_naive(const uint8_t *T, int32_t n, int32_t *SA)
     g_n = n;
     qsort(SA, (size_t)n, sizeof(int32_t), cmp_suffix);
 }
+
+/* LCP array by definition, for the on-device LCP export (the reference has none -- this is the
+ * textbook definition, LCP[r] = longest common prefix of suffixes SA[r-1] and SA[r], LCP[0] = 0), computed with Kasai's
+ * order of evaluation (along the text, each comparison resuming one below the previous length) so that large inputs
+ * finish quickly.  rank is scratch of n entries. */
+void oracle_lcp_kasai(const uint8_t *T, int32_t n, const int32_t *SA, int32_t *rank, int32_t *LCP)
+{
+    for (int32_t r = 0; r < n; ++r)
+        rank[SA[r]] = r;
+    int32_t h = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t r = rank[i];
+        if (r == 0) {
+            LCP[0] = 0;
+            h = 0;
+            continue;
+        }
+        int32_t j = SA[r - 1];
+        while (i + h < n && j + h < n && T[i + h] == T[j + h])
+            ++h;
+        LCP[r] = h;
+        if (h > 0)
+            --h;
+    }
+}

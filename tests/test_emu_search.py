@@ -225,3 +225,39 @@ def test_native_patch_file(sorter):
         out.write(b"xx")                      # Diff.Create writes at the stream's current position (Diff.cs:56)
         bsdiff.Diff.create(old, new, out, sorter)
         assert out.getvalue()[2:] == sorter.context.bsdiff_patch(old, new) and out.tell() == len(out.getvalue())
+
+
+def _lcp_texts():
+    from conftest import adversarial_texts, small_alphabet_texts
+    out = dict(adversarial_texts())
+    out.update({k: v for k, v in small_alphabet_texts().items() if k in ("acgt_tandem", "bin_zero_tail", "one_value_5000")})
+    out["random_300k"] = random_bytes(300_000)
+    out["fuzz3"] = np.fromfile(os.path.join(GOLDEN, "assets", "fuzz3"), dtype=np.uint8)
+    out["single"] = np.array([9], np.uint8)
+    out["empty"] = np.zeros(0, np.uint8)
+    return out
+
+
+def test_lcp_array_export(sorter):
+    """dq_cuda_lcp: the LCP array under the resident suffix array and under a caller-supplied one,
+    against the definition (oracle.lcp_array); a following search reuses the index; a broken array is rejected."""
+    from deltaq_b200 import _native, bsdiff
+    for name, t in _lcp_texts().items():
+        sa = np.empty(t.size, np.int32)
+        sorter.sort(t, sa)
+        ref = oracle.lcp_array(t, sa)
+        assert np.array_equal(sorter.lcp_array(t), ref), name            # resident
+        assert np.array_equal(sorter.lcp_array(t, sa), ref), name        # adopted
+        if t.size > 100:
+            new = np.concatenate([t[50:], t[:60]])
+            pos, ln = bsdiff.search_all(t, new, sorter, I=oracle.make_I(sa))
+            lcp_again = sorter.lcp_array(t)                                # index still resident after the search
+            assert np.array_equal(lcp_again, ref), name
+            rp, rl = oracle.search_all(oracle.make_I(sa), t, new)
+            assert np.array_equal(pos, rp) and np.array_equal(ln, rl), name
+    t = random_bytes(5000)
+    with pytest.raises(_native.NativeError):
+        sorter.lcp_array(t, np.zeros(t.size, np.int32))                   # not a permutation
+    with pytest.raises(_native.NativeError):
+        sorter.sort(random_bytes(100), np.empty(100, np.int32))
+        sorter.lcp_array(t)                                               # resident array has another length

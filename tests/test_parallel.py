@@ -64,6 +64,10 @@ def _check_search(sorter):
         assert np.array_equal(pos, rp) and np.array_equal(ln, rl), name
         pos, ln = search_sharded(old, new, sorter, I=I)        # caller-supplied suffix array
         assert np.array_equal(pos, rp) and np.array_equal(ln, rl), name
+        if old.size:                                           # the LCP array of the group-sorted text (dq_cuda_lcp)
+            sa = np.empty(old.size, np.int32)
+            sorter.sort(old, sa)
+            assert np.array_equal(sorter.lcp_array(old), oracle.lcp_array(old, sa)), name
         b, c = new.size // 3, new.size // 2                    # a sub-range of scan positions
         p3 = np.empty(c, np.int32)
         l3 = np.empty(c, np.int32)
