@@ -53,6 +53,7 @@ EXPORTS = [
     "dq_cuda_host_alloc", "dq_cuda_host_free", "dq_cuda_suffix_sort", "dq_cuda_suffix_sort_device",
     "dq_cuda_bsdiff_search", "dq_cuda_bsdiff_search_device", "dq_cuda_lcp", "dq_cuda_lcp_device", "dq_cuda_bsdiff_streams", "dq_cuda_greedy_emit",
     "dq_cuda_patch_apply", "dq_cuda_bz2_bound", "dq_cuda_bz2_compress", "dq_cuda_bsdiff_patch",
+    "dq_cuda_bz2_decompress", "dq_cuda_bspatch",
     "dq_cuda_radix_sort_pairs", "dq_cuda_radix_sort_pairs_device",
 ]
 
@@ -89,6 +90,8 @@ class Library:
         L.dq_cuda_patch_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64]
         L.dq_cuda_bz2_bound.argtypes = [i64]
         L.dq_cuda_bz2_compress.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+        L.dq_cuda_bz2_decompress.argtypes = [vp, i64, ctypes.c_int, vp, i64, ctypes.POINTER(i64), vp]
+        L.dq_cuda_bspatch.argtypes = [vp, i64, vp, i64, ctypes.c_int, vp, i64, ctypes.POINTER(i64)]
         L.dq_cuda_bsdiff_patch.argtypes = [vp, vp, i32, vp, i32, ctypes.c_int, ctypes.POINTER(vp),
                                            ctypes.POINTER(i64)]
         L.dq_cuda_radix_sort_pairs.argtypes = [vp, vp, vp, i32, i32]
@@ -157,6 +160,49 @@ def bz2_compress(sections, level=0, threads=0, lib=None, info=None):
     if info is not None:
         info[:] = [(inf[3 * i], inf[3 * i + 1], inf[3 * i + 2]) for i in range(k)]
     return [outs[i][:got[i]].tobytes() for i in range(k)]
+
+
+def bz2_decompress(data, threads=0, lib=None, info=None, size_hint=0):
+    """dq_cuda_bz2_decompress: one bzip2 stream, its blocks decoded in parallel -> bytes.  info (a list, optional) receives
+    (blocks, serial_fallback).  Raises RuntimeError("Corrupt patch") for a damaged stream."""
+    lib = lib or default_library()
+    a = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+    got = ctypes.c_int64()
+    inf = (ctypes.c_int32 * 2)()
+    out = np.empty(max(int(size_hint), 0), dtype=np.uint8)
+    for _ in range(2):
+        rc = lib.L.dq_cuda_bz2_decompress(_addr(a), a.size, int(threads), _addr(out), out.size, ctypes.byref(got), inf)
+        if rc == DQ_ERR_INVALID_ARGUMENT and got.value > out.size:
+            out = np.empty(got.value, dtype=np.uint8)     # now the size is known
+            continue
+        break
+    if rc == DQ_ERR_CORRUPT_PATCH:
+        raise RuntimeError("Corrupt patch")
+    if rc != DQ_OK:
+        raise NativeError(rc, "dq_cuda_bz2_decompress failed")
+    if info is not None:
+        info[:] = [inf[0], inf[1]]
+    return out[:got.value].tobytes()
+
+
+def bspatch(old, patch, threads=0, lib=None):
+    """dq_cuda_bspatch: Patch.Apply on a BSDIFF40 file -> the new file (numpy uint8)."""
+    lib = lib or default_library()
+    o, p = (np.ascontiguousarray(np.frombuffer(x, dtype=np.uint8) if not isinstance(x, np.ndarray) else x)
+            for x in (old, patch))
+    size = ctypes.c_int64(-1)
+    rc = lib.L.dq_cuda_bspatch(_addr(o), o.size, _addr(p), p.size, int(threads), None, 0, ctypes.byref(size))
+    if rc == DQ_ERR_CORRUPT_PATCH:
+        raise RuntimeError("Corrupt patch")
+    if size.value < 0:
+        raise NativeError(rc, "dq_cuda_bspatch: bad arguments")
+    out = np.empty(size.value, dtype=np.uint8)
+    rc = lib.L.dq_cuda_bspatch(_addr(o), o.size, _addr(p), p.size, int(threads), _addr(out), out.size, ctypes.byref(size))
+    if rc == DQ_ERR_CORRUPT_PATCH:
+        raise RuntimeError("Corrupt patch")
+    if rc != DQ_OK:
+        raise NativeError(rc, "dq_cuda_bspatch failed")
+    return out
 
 
 class PinnedArray:

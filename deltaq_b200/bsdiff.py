@@ -12,8 +12,8 @@ serial libbz2 writes at the chosen level).  The reference uses SharpZipLib 1.4.2
 compressed bytes are not claimed identical to it -- the uncompressed ctrl/diff/extra streams and the header fields
 are (tests/test_bsdiff_gpu.py).
 
-``Patch.apply`` mirrors Patch.Apply (Patch.cs:25-168); it is not on the hot path and exists for the
-reference's round-trip tests (BsDiffTests.cs:30-78).
+``Patch.apply`` mirrors Patch.Apply (Patch.cs:25-168) through dq_cuda_bspatch (sections decoded block-parallel on the
+host, native add loop); it is not on the hot path and serves the reference's round-trip tests (BsDiffTests.cs:30-78).
 """
 import bz2
 import io
@@ -144,6 +144,17 @@ class Patch:
     @staticmethod
     def apply(old_data, patch, output):
         """Patch.Apply(ReadOnlyMemory<byte> input, ReadOnlyMemory<byte> diff, Stream output), Patch.cs:25-36."""
+        o = as_bytes_array(old_data, "input")
+        # header checks (:52-70), the three sections un-bzip2'ed block-parallel, the add loop (:95-168): one native call
+        out = _native.bspatch(o, np.frombuffer(bytes(patch), dtype=np.uint8))
+        output.write(out.tobytes())
+        if hasattr(output, "flush"):
+            output.flush()
+
+    @staticmethod
+    def apply_reference_order(old_data, patch, output):
+        """The same with the sections decoded by Python's bz2 (serial libbz2) and the header parsed here: an independent
+        reader of the files Diff.create writes, used by the tests."""
         o = as_bytes_array(old_data, "input")
         p = bytes(patch)
         header = p[:HEADER_SIZE]

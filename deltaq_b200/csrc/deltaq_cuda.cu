@@ -1384,6 +1384,71 @@ int dq_cuda_bz2_compress(const uint8_t *const *src, const int64_t *len, int coun
     return DQ_OK;
 }
 
+int dq_cuda_bz2_decompress(const uint8_t *src, int64_t len, int threads, uint8_t *out, int64_t cap, int64_t *out_len,
+                           int32_t *info)
+{
+    if (len < 0 || (len && !src) || threads < 0 || cap < 0 || (cap && !out) || !out_len) return DQ_ERR_INVALID_ARGUMENT;
+    dq::bz2host::DecodeJob job;
+    job.src = src;
+    job.len = len;
+    int rc;
+    try {
+        rc = dq::bz2host::decompress_streams(&job, 1, threads);
+    } catch (const std::bad_alloc &) {
+        return DQ_ERR_OUT_OF_MEMORY;
+    } catch (...) {
+        return DQ_ERR_INTERNAL;
+    }
+    if (rc == -3) return DQ_ERR_INTERNAL;
+    if (rc != 0) return DQ_ERR_CORRUPT_PATCH;
+    *out_len = (int64_t)job.out.size();
+    if (info) {
+        info[0] = job.blocks;
+        info[1] = job.fell_back ? 1 : 0;
+    }
+    if ((int64_t)job.out.size() > cap) return DQ_ERR_INVALID_ARGUMENT;  // *out_len says how much room is needed
+    if (!job.out.empty()) memcpy(out, job.out.data(), job.out.size());
+    return DQ_OK;
+}
+
+int dq_cuda_bspatch(const uint8_t *old_, int64_t n, const uint8_t *patch, int64_t patch_len, int threads, uint8_t *out,
+                    int64_t out_cap, int64_t *new_size)
+{
+    if (n < 0 || (n && !old_) || patch_len < 0 || (patch_len && !patch) || threads < 0 || out_cap < 0 || !new_size)
+        return DQ_ERR_INVALID_ARGUMENT;
+    namespace bz = dq::bz2host;
+    // Patch.cs:52-93: signature, the two section lengths and the size of the new file, all packed longs
+    if (patch_len < 32 || memcmp(patch, "BSDIFF40", 8) != 0) return DQ_ERR_CORRUPT_PATCH;
+    const int64_t ctrl_len = dq::patchhost::read_packed_long(patch + 8);
+    const int64_t diff_len = dq::patchhost::read_packed_long(patch + 16);
+    const int64_t size = dq::patchhost::read_packed_long(patch + 24);
+    if (ctrl_len < 0 || diff_len < 0 || size < 0) return DQ_ERR_CORRUPT_PATCH;
+    if (ctrl_len > patch_len - 32 || diff_len > patch_len - 32 - ctrl_len) return DQ_ERR_CORRUPT_PATCH;
+    *new_size = size;
+    if (out_cap < size || (size && !out)) return DQ_ERR_INVALID_ARGUMENT;  // *new_size says how much room is needed
+    try {
+        bz::DecodeJob jobs[3];
+        jobs[0].src = patch + 32;
+        jobs[0].len = ctrl_len;
+        jobs[1].src = patch + 32 + ctrl_len;
+        jobs[1].len = diff_len;
+        jobs[2].src = patch + 32 + ctrl_len + diff_len;
+        jobs[2].len = patch_len - 32 - ctrl_len - diff_len;
+        const int rc = bz::decompress_streams(jobs, 3, threads);
+        if (rc == -3) return DQ_ERR_INTERNAL;
+        if (rc != 0) return DQ_ERR_CORRUPT_PATCH;
+        return dq::patchhost::apply_streams(old_, n, jobs[0].out.data(), (int64_t)jobs[0].out.size(), jobs[1].out.data(),
+                                            (int64_t)jobs[1].out.size(), jobs[2].out.data(), (int64_t)jobs[2].out.size(),
+                                            out, size) == 0
+                   ? DQ_OK
+                   : DQ_ERR_CORRUPT_PATCH;
+    } catch (const std::bad_alloc &) {
+        return DQ_ERR_OUT_OF_MEMORY;
+    } catch (...) {
+        return DQ_ERR_INTERNAL;
+    }
+}
+
 int dq_cuda_bsdiff_patch(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m, int level,
                          const uint8_t **patch, int64_t *patch_len)
 {

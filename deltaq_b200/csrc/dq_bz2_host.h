@@ -437,5 +437,281 @@ inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
     return worst;
 }
 
+// ---- the reader's side: Patch.CreatePatchStreams (Patch.cs:52-93) un-bzip2's three sections serially ---------------------
+// Blocks can be decoded independently as well, once their bit offsets are known: every block starts with the 48-bit
+// magic, so the section is scanned for it at all eight bit alignments (a table on the byte that follows the first,
+// partial, byte keeps that to about one look-up per input byte), every block is wrapped into a one-block stream of its
+// own (header + the block's bits + end magic + the block's CRC) and decoded by libbz2 on the crew, and the pieces are laid
+// end to end.  The combined CRC of the block CRCs must equal the stream's.  Anything unexpected -- a magic that turns
+// out to be compressed data (2^-48 per bit), trailing bytes, several streams in a row -- sends the section to the serial
+// decoder instead.
+
+// bz_stream of libbz2 1.0.x (public, stable layout)
+struct BzStream {
+    char *next_in;
+    unsigned avail_in, total_in_lo32, total_in_hi32;
+    char *next_out;
+    unsigned avail_out, total_out_lo32, total_out_hi32;
+    void *state;
+    void *(*bzalloc)(void *, int, int);
+    void (*bzfree)(void *, void *);
+    void *opaque;
+};
+struct DecodeLib {
+    int (*init)(BzStream *, int, int) = nullptr;                                    // BZ2_bzDecompressInit
+    int (*step)(BzStream *) = nullptr;                                              // BZ2_bzDecompress
+    int (*end)(BzStream *) = nullptr;                                               // BZ2_bzDecompressEnd
+    bool ok() const { return init && step && end; }
+};
+inline const DecodeLib &libbz2_decode()
+{
+    static DecodeLib lib = [] {
+        DecodeLib d;
+        for (const char *name : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"}) {
+            if (void *h = dlopen(name, RTLD_NOW | RTLD_LOCAL)) {
+                d.init = reinterpret_cast<decltype(d.init)>(dlsym(h, "BZ2_bzDecompressInit"));
+                d.step = reinterpret_cast<decltype(d.step)>(dlsym(h, "BZ2_bzDecompress"));
+                d.end = reinterpret_cast<decltype(d.end)>(dlsym(h, "BZ2_bzDecompressEnd"));
+                if (d.ok()) break;
+            }
+        }
+        return d;
+    }();
+    return lib;
+}
+
+// growable byte buffer without the zero fill of std::vector (realloc moves large blocks by remapping, not copying)
+struct RawBuf {
+    uint8_t *p = nullptr;
+    size_t len = 0, cap = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), len(o.len), cap(o.cap) { o.p = nullptr; o.len = o.cap = 0; }
+    ~RawBuf() { free(p); }
+    void reserve(size_t want)
+    {
+        if (want <= cap) return;
+        void *q = realloc(p, want);
+        if (!q) throw std::bad_alloc();
+        p = static_cast<uint8_t *>(q);
+        cap = want;
+    }
+    void swap(RawBuf &o)
+    {
+        std::swap(p, o.p);
+        std::swap(len, o.len);
+        std::swap(cap, o.cap);
+    }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return len; }
+    bool empty() const { return len == 0; }
+};
+
+// serial decode of the first stream in [z, z+len): 0, or -2 (not a bzip2 stream / damaged)
+inline int serial_decompress(const uint8_t *z, int64_t len, RawBuf &out)
+{
+    const DecodeLib &lib = libbz2_decode();
+    if (!lib.ok()) return -2;
+    BzStream st;
+    memset(&st, 0, sizeof st);
+    if (lib.init(&st, 0, 0) != 0) return -2;
+    out.len = 0;
+    out.reserve((size_t)std::max<int64_t>(1 << 16, len * 8));
+    int64_t fed = 0;
+    int rc = 0;
+    for (;;) {
+        if (st.avail_in == 0 && fed < len) {
+            const int64_t take = std::min<int64_t>(len - fed, 1 << 30);
+            st.next_in = const_cast<char *>(reinterpret_cast<const char *>(z + fed));
+            st.avail_in = (unsigned)take;
+            fed += take;
+        }
+        if (out.len == out.cap) out.reserve(out.cap * 2);
+        const size_t room = std::min<size_t>(out.cap - out.len, 1u << 30);
+        st.next_out = reinterpret_cast<char *>(out.p + out.len);
+        st.avail_out = (unsigned)room;
+        rc = lib.step(&st);
+        out.len += room - st.avail_out;
+        if (rc != 0) break;  // 4 = BZ_STREAM_END, negative = damaged
+        if (st.avail_in == 0 && fed >= len && st.avail_out != 0) {  // input exhausted in mid-stream
+            rc = -7;                                                   // BZ_UNEXPECTED_EOF
+            break;
+        }
+    }
+    lib.end(&st);
+    return rc == 4 ? 0 : -2;
+}
+
+struct Magics {
+    uint16_t by_second_byte[256];  // bit s: block magic may start s bits into the byte before; bit 8+s: end magic
+    Magics()
+    {
+        memset(by_second_byte, 0, sizeof by_second_byte);
+        for (int s = 0; s < 8; ++s) {
+            by_second_byte[(kBlockMagic >> (32 + s)) & 0xff] |= (uint16_t)(1u << s);
+            by_second_byte[(kEndMagic >> (32 + s)) & 0xff] |= (uint16_t)(1u << (8 + s));
+        }
+    }
+};
+
+struct DecodeJob {
+    const uint8_t *src;
+    int64_t len;
+    RawBuf out;                // the decoded section
+    int blocks = 0;
+    bool fell_back = false;
+    int status = 0;            // 0, -2 damaged
+};
+
+struct DecodePiece {
+    int stream;
+    int64_t begin, end;        // bit range of the block in the section
+    RawBuf data;               // decoded
+    uint32_t crc = 0;
+    bool ok = false;
+};
+
+// bit offsets of the blocks of a single, complete stream that fills [z, z+len) exactly; false = leave it to the serial path
+inline bool find_blocks(const uint8_t *z, int64_t len, std::vector<int64_t> &blocks, int64_t &end_at)
+{
+    static const Magics magics;
+    blocks.clear();
+    if (len < 14 || z[0] != 'B' || z[1] != 'Z' || z[2] != 'h' || z[3] < '1' || z[3] > '9') return false;
+    const int64_t bits = len * 8;
+    end_at = -1;
+    for (int64_t q = 5; q < len; ++q) {  // q: the byte after the one the magic starts in
+        const uint16_t m = magics.by_second_byte[z[q]];
+        if (!m) continue;
+        for (int s = 0; s < 8; ++s) {
+            const int64_t at = (q - 1) * 8 + s;
+            if (at < 32 || at + 48 > bits) continue;
+            if ((m >> s) & 1) {
+                if (read_bits(z, at, 48) == kBlockMagic && at + 80 <= bits) blocks.push_back(at);
+            }
+            if ((m >> (8 + s)) & 1) {
+                // the end magic, its CRC and the padding must close the section exactly
+                if (read_bits(z, at, 48) == kEndMagic && (at + 80 + 7) / 8 == len) end_at = at;
+            }
+        }
+    }
+    if (end_at < 0) return false;
+    while (!blocks.empty() && blocks.back() >= end_at) blocks.pop_back();
+    if (blocks.empty()) return end_at == 32;   // an empty stream has no block
+    return blocks.front() == 32;
+}
+
+// Decode every job; threads 0 = the CPUs this process may run on.  Returns 0, -2 (some section damaged), -3 (no libbz2).
+inline int decompress_streams(DecodeJob *jobs, int count, int threads)
+{
+    const DecodeLib &lib = libbz2_decode();
+    if (!lib.ok()) return -3;
+    const int crew = threads > 0 ? std::min(threads, 256) : (int)usable_cpus();
+    std::vector<DecodePiece> pieces;
+    std::vector<size_t> first_piece(count, 0);
+    std::vector<int64_t> end_at(count, -1);
+    std::vector<int64_t> blocks;
+    for (int s = 0; s < count; ++s) {
+        DecodeJob &job = jobs[s];
+        job.out.len = 0;
+        job.blocks = 0;
+        job.status = 0;
+        job.fell_back = !find_blocks(job.src, job.len, blocks, end_at[s]);
+        first_piece[s] = pieces.size();
+        if (job.fell_back) {  // the whole section is one serial piece
+            DecodePiece pc;
+            pc.stream = s;
+            pc.begin = pc.end = -1;
+            pieces.push_back(std::move(pc));
+            continue;
+        }
+        job.blocks = (int)blocks.size();
+        for (size_t k = 0; k < blocks.size(); ++k) {
+            DecodePiece pc;
+            pc.stream = s;
+            pc.begin = blocks[k];
+            pc.end = k + 1 < blocks.size() ? blocks[k + 1] : end_at[s];
+            pieces.push_back(std::move(pc));
+        }
+    }
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+        std::vector<uint8_t> wrapped;
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= pieces.size()) return;
+            DecodePiece &pc = pieces[k];
+            const DecodeJob &job = jobs[pc.stream];
+            try {
+                if (pc.begin < 0) {
+                    pc.ok = serial_decompress(job.src, job.len, pc.data) == 0;
+                    continue;
+                }
+                pc.crc = (uint32_t)read_bits(job.src, pc.begin + 48, 32);
+                wrapped.resize((size_t)((pc.end - pc.begin + 7) / 8 + 4 + 10 + 1));
+                BitWriter w(wrapped.data(), (int64_t)wrapped.size());
+                bool fits = w.put('B', 8) && w.put('Z', 8) && w.put('h', 8) && w.put((uint64_t)job.src[3], 8) &&
+                            w.append(job.src, pc.begin, pc.end) && w.put(kEndMagic >> 24, 24) &&
+                            w.put(kEndMagic & 0xffffffu, 24) && w.put(pc.crc, 32) && w.finish();
+                if (!fits) continue;
+                // the decoded size is not known in advance (a block of zeros expands 51x): the streaming decoder grows
+                // its output as it goes
+                pc.ok = serial_decompress(wrapped.data(), w.size(), pc.data) == 0;
+            } catch (...) {
+                pc.ok = false;
+            }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        try {
+            const size_t helpers = std::min<size_t>((size_t)crew, pieces.size());
+            for (size_t t = 1; t < helpers; ++t) pool.emplace_back(work);
+        } catch (...) {
+        }
+        work();
+        for (auto &t : pool) t.join();
+    }
+    int worst = 0;
+    for (int s = 0; s < count; ++s) {
+        DecodeJob &job = jobs[s];
+        const size_t first = first_piece[s];
+        if (job.fell_back) {
+            job.status = pieces[first].ok ? 0 : -2;
+            if (pieces[first].ok) job.out.swap(pieces[first].data);
+        } else {
+            bool all_ok = true;
+            uint32_t combined = 0;
+            size_t total = 0;
+            for (int k = 0; k < job.blocks; ++k) {
+                const DecodePiece &pc = pieces[first + k];
+                all_ok = all_ok && pc.ok;
+                combined = ((combined << 1) | (combined >> 31)) ^ pc.crc;
+                total += pc.data.size();
+            }
+            if (all_ok && combined == (uint32_t)read_bits(job.src, end_at[s] + 48, 32)) {
+                if (job.blocks == 1) {
+                    job.out.swap(pieces[first].data);
+                } else {
+                    job.out.reserve(std::max<size_t>(total, 1));
+                    job.out.len = total;
+                    size_t at = 0;
+                    for (int k = 0; k < job.blocks; ++k) {
+                        const DecodePiece &pc = pieces[first + k];
+                        if (!pc.data.empty()) memcpy(job.out.p + at, pc.data.data(), pc.data.size());
+                        at += pc.data.size();
+                    }
+                }
+            } else {
+                // a candidate block was not a block, or the stream is damaged: the serial decoder decides
+                job.fell_back = true;
+                job.status = serial_decompress(job.src, job.len, job.out) == 0 ? 0 : -2;
+            }
+        }
+        worst = std::min(worst, job.status);
+    }
+    return worst;
+}
+
 }  // namespace bz2host
 }  // namespace dq

@@ -178,6 +178,21 @@ int dq_cuda_bz2_compress(const uint8_t *const *src, const int64_t *len, int coun
 int dq_cuda_bsdiff_patch(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint8_t *new_, int32_t m, int level,
                          const uint8_t **patch, int64_t *patch_len);
 
+/* ---- Patch.Apply on the patch FILE ---------------------------------------------------------------------
+ * Patch.Apply (Patch.cs:25-50) = CreatePatchStreams (:52-93: header checks, three bzip2 sections) + ApplyInternal
+ * (:95-168).  The sections are decoded block-parallel: the 48-bit block magic is located at every bit alignment,
+ * each block is decoded by the system's libbz2 on a crew of host threads as a one-block stream of its own, the
+ * combined CRC is checked against the stream's; anything unexpected falls back to the serial decoder.  Works on any
+ * BSDIFF40 file (the reference's, bsdiff 4.x's, this library's).  *new_size is set from the header as soon as the
+ * header is valid; out_cap < *new_size returns DQ_ERR_INVALID_ARGUMENT (call with out_cap 0 to ask for the size).
+ * DQ_ERR_CORRUPT_PATCH where the reference throws "Corrupt patch" and for damaged sections.  Pure host code. */
+int dq_cuda_bspatch(const uint8_t *old_, int64_t n, const uint8_t *patch, int64_t patch_len, int threads, uint8_t *out,
+                    int64_t out_cap, int64_t *new_size);
+/* One bzip2 stream, blocks decoded in parallel.  *out_len = decoded size (also when cap is too small, which returns
+ * DQ_ERR_INVALID_ARGUMENT).  info (may be NULL): blocks found, 1 if the serial decoder had to take the stream. */
+int dq_cuda_bz2_decompress(const uint8_t *src, int64_t len, int threads, uint8_t *out, int64_t cap, int64_t *out_len,
+                           int32_t *info);
+
 /* ---- Patch.Apply ------------------------------------------------------------------------------------
  * Patch.ApplyInternal (Patch.cs:95-168) on the three UNCOMPRESSED streams (the caller has un-bzip2'ed them, as
  * Patch.CreatePatchStreams :52-93 does): writes exactly new_size bytes to out.  Pure host code (the add loop of

@@ -126,3 +126,101 @@ def test_bad_arguments():
         _native.bz2_compress([b"abc"], level=10)
     with pytest.raises(_native.NativeError):
         _native.bz2_compress([b"abc"], level=-1)
+
+
+# ---- the reader's side: block-parallel decode, Patch.Apply on the file -------------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("level", [1, 9])
+def test_parallel_decode_of_serial_streams(name, level):
+    """Streams written by serial libbz2 (what a foreign bsdiff writes), decoded block by block."""
+    data = CASES[name].tobytes()
+    z = serial(data, level)
+    info = []
+    assert _native.bz2_decompress(z, threads=4, info=info) == data
+    assert info[1] == 0                                   # no serial fallback
+    assert (info[0] == 0) == (not data)                   # an empty stream has no block
+    if name == "random_1M" and level == 1:
+        assert info[0] >= 10
+
+
+def test_parallel_decode_of_the_producers_streams():
+    for name in ("diff_like", "runs_mixed", "words"):
+        data = CASES[name].tobytes()
+        (z,) = _native.bz2_compress([data], level=0, threads=8)
+        assert _native.bz2_decompress(z, threads=3) == data
+
+
+def test_decode_rejects_damage_and_handles_oddities():
+    data = CASES["words"].tobytes()
+    z = bytearray(serial(data, 1))
+    # a flipped bit inside a block: the block's CRC (or its Huffman tables) no longer fit
+    for at in (len(z) // 2, 200, len(z) - 20):
+        bad = bytearray(z)
+        bad[at] ^= 0x10
+        with pytest.raises(RuntimeError, match="Corrupt patch"):
+            _native.bz2_decompress(bytes(bad))
+    # truncated
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bz2_decompress(bytes(z[:len(z) // 2]))
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bz2_decompress(b"not a bzip2 stream at all")
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bz2_decompress(b"")
+    # trailing bytes after the stream (the reference's extra section is "the rest of the file"): the serial decoder takes
+    # it and stops at the end of the first stream, as libbz2 does
+    info = []
+    assert _native.bz2_decompress(bytes(z) + b"\0\0\0", info=info) == data and info[1] == 1
+    # the payload contains the block magic itself, byte aligned and bit shifted: candidates that are not blocks
+    magic = bytes.fromhex("314159265359")
+    rng = np.random.default_rng(8)
+    tricky = b"".join(magic + bytes(rng.integers(0, 256, 50, dtype=np.uint8)) for _ in range(3000))
+    for level in (1, 9):
+        assert _native.bz2_decompress(serial(tricky, level)) == tricky
+    # stored (incompressible) data made of the magic at every bit offset cannot appear verbatim in a bzip2 stream, but a
+    # forged "block" can: a stream followed by a second stream is not what a patch section is -- serial path, first stream
+    two = serial(b"abc" * 1000, 9) + serial(b"xyz", 9)
+    assert _native.bz2_decompress(two) == b"abc" * 1000
+
+
+def _patch_file(old, new, level=9):
+    """A BSDIFF40 file written the reference's way: oracle streams, serial bzip2 sections (Diff.cs:54-70, :226-241)."""
+    import oracle
+    st = oracle.bsdiff_streams(old, new)
+    secs = [bz2.compress(st[k], level) for k in ("ctrl", "diff", "extra")]
+    head = b"BSDIFF40" + len(secs[0]).to_bytes(8, "little") + len(secs[1]).to_bytes(8, "little") + \
+        int(new.size).to_bytes(8, "little")
+    return head + b"".join(secs)
+
+
+def test_bspatch_on_patch_files():
+    """dq_cuda_bspatch = Patch.Apply (Patch.cs:25-168) on the file: serial-bzip2 files and the producer's own, empty and
+    tiny inputs (BsPatchTests.cs:18-38), and the reference's corrupt-patch cases."""
+    from conftest import random_bytes
+    from deltaq_b200 import workloads as w
+    pairs = [(random_bytes(0), random_bytes(0)), (random_bytes(1), random_bytes(1, seed=2)),
+             (random_bytes(0), random_bytes(100)), (random_bytes(100), random_bytes(0)),
+             (random_bytes(4096), random_bytes(4099, seed=3)), w.c2_exe_pair(300_000, 330_000)]
+    for old, new in pairs:
+        for level in (1, 9):
+            patch = _patch_file(old, new, level)
+            assert _native.bspatch(old, patch).tobytes() == new.tobytes()
+    old, new = pairs[-1]
+    patch = bytearray(_patch_file(old, new))
+    for field in (0, 8, 16, 24):                       # signature; negative lengths (sign bit of a packed long)
+        bad = bytearray(patch)
+        bad[field + 7] ^= 0x80
+        with pytest.raises(RuntimeError, match="Corrupt patch"):
+            _native.bspatch(old, bytes(bad))
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bspatch(old, bytes(patch[:31]))
+    big = bytearray(patch)
+    big[8:16] = (len(patch)).to_bytes(8, "little")     # ctrl section longer than the file
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bspatch(old, bytes(big))
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bspatch(old[:1000], bytes(patch))       # wrong old file: reads past its end
+    short = bytearray(patch)
+    short[24:32] = (int(new.size) + 5).to_bytes(8, "little")   # header promises more than the streams hold
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bspatch(old, bytes(short))
