@@ -33,6 +33,30 @@ internal static unsafe partial class Native
     internal static partial int dq_cuda_bsdiff_patch(IntPtr ctx, byte* old, int n, byte* @new, int m, int level, byte** patch, long* patchLen);
 }
 
+/// <summary>Sibling of DeltaQ.BsDiff.Patch.Apply(ReadOnlyMemory&lt;byte&gt; input, ReadOnlyMemory&lt;byte&gt; diff, Stream output)
+/// (Patch.cs:25-36): header checks, the three bzip2 sections decoded block-parallel and the add loop of Patch.cs:143-144 in
+/// one native call, dq_cuda_bspatch.  Needs no device and no context.</summary>
+public static unsafe class CudaPatch
+{
+    [DllImport("deltaq_cuda")]
+    private static extern int dq_cuda_bspatch(byte* old, long n, byte* patch, long patchLen, int threads, byte* @out, long outCap, long* newSize);
+
+    public static void Apply(ReadOnlyMemory<byte> input, ReadOnlyMemory<byte> diff, Stream output)
+    {
+        if (output == null) throw new ArgumentNullException(nameof(output));
+        fixed (byte* o = input.Span) fixed (byte* p = diff.Span)
+        {
+            long size = -1;
+            int rc = dq_cuda_bspatch(o, input.Length, p, diff.Length, 0, null, 0, &size);   // the header's newSize
+            if (rc == -6 || size < 0) throw new InvalidOperationException("Corrupt patch");
+            var result = new byte[size];
+            fixed (byte* r = result)
+                Native.Check(IntPtr.Zero, dq_cuda_bspatch(o, input.Length, p, diff.Length, 0, r, size, &size));
+            output.Write(result);
+        }
+    }
+}
+
 public static unsafe class CudaDiff
 {
     private const long Signature = 0x3034464649445342;   // "BSDIFF40", Constants.cs
