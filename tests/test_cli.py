@@ -1,0 +1,57 @@
+"""`python -m deltaq_b200 bsdiff|bspatch`: the reference's command line (Commands.BsDiff.cs, Commands.BsPatch.cs) with the
+CUDA provider.  bspatch is host code and runs anywhere; bsdiff needs the GPU."""
+import bz2
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import random_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*argv):
+    return subprocess.run([sys.executable, "-m", "deltaq_b200", *argv], cwd=ROOT, capture_output=True, text=True,
+                          timeout=600)
+
+
+def _pair():
+    old = random_bytes(50_000)
+    new = np.concatenate([old[:20_000], random_bytes(300, seed=4), old[19_000:]])
+    return old, new
+
+
+def test_bspatch_cli(tmp_path):
+    old, new = _pair()
+    st = oracle.bsdiff_streams(old, new)
+    secs = [bz2.compress(st[k]) for k in ("ctrl", "diff", "extra")]
+    patch = b"BSDIFF40" + len(secs[0]).to_bytes(8, "little") + len(secs[1]).to_bytes(8, "little") + \
+        int(new.size).to_bytes(8, "little") + b"".join(secs)
+    (tmp_path / "old").write_bytes(old.tobytes())
+    (tmp_path / "delta").write_bytes(patch)
+    r = _run("bspatch", str(tmp_path / "old"), str(tmp_path / "delta"), str(tmp_path / "new"))
+    assert r.returncode == 0, r.stderr
+    assert "Applying BsDiff delta between" in r.stdout and "Finished in" in r.stdout
+    assert (tmp_path / "new").read_bytes() == new.tobytes()
+    (tmp_path / "delta").write_bytes(b"BSDIFF41" + patch[8:])
+    r = _run("bspatch", str(tmp_path / "old"), str(tmp_path / "delta"), str(tmp_path / "new2"))
+    assert r.returncode != 0 and "Failed to apply delta" in r.stderr and "Corrupt patch" in r.stderr
+
+
+@pytest.mark.gpu
+def test_bsdiff_cli_roundtrip(tmp_path):
+    old, new = _pair()
+    (tmp_path / "old").write_bytes(old.tobytes())
+    (tmp_path / "new").write_bytes(new.tobytes())
+    r = _run("bsdiff", str(tmp_path / "old"), str(tmp_path / "new"), str(tmp_path / "delta"), "-ss", "cuda")
+    assert r.returncode == 0, r.stderr
+    assert "with suffix sort CudaSuffixSort" in r.stdout and "Delta size:" in r.stdout
+    r = _run("bspatch", str(tmp_path / "old"), str(tmp_path / "delta"), str(tmp_path / "rebuilt"))
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "rebuilt").read_bytes() == new.tobytes()
+    r = _run("bsdiff", str(tmp_path / "old"), str(tmp_path / "new"), str(tmp_path / "delta"), "-ss", "sais")
+    assert r.returncode != 0
