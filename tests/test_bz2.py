@@ -224,3 +224,30 @@ def test_bspatch_on_patch_files():
     short[24:32] = (int(new.size) + 5).to_bytes(8, "little")   # header promises more than the streams hold
     with pytest.raises(RuntimeError, match="Corrupt patch"):
         _native.bspatch(old, bytes(short))
+
+
+def test_randomised_sweep_against_serial():
+    """Random mixtures of literal stretches and runs, random lengths and levels: bytes equal serial libbz2's, decode
+    (parallel and Python's) gives the input back."""
+    rng = np.random.default_rng(2024)
+    sections, levels = [], []
+    for _ in range(40):
+        parts = []
+        total = int(rng.integers(1, 400_000))
+        sigma = int(rng.choice([2, 4, 16, 256]))
+        while sum(p.size for p in parts) < total:
+            if rng.random() < 0.5:
+                parts.append(rng.integers(0, sigma, int(rng.integers(1, 5000)), dtype=np.uint8))
+            else:
+                parts.append(np.full(int(rng.choice([1, 2, 3, 4, 5, 100, 255, 256, 1000, 70_000])),
+                                     int(rng.integers(0, sigma)), np.uint8))
+        sections.append(np.concatenate(parts)[:total])
+        levels.append(int(rng.integers(1, 4)))
+    for level in (1, 2, 3):
+        pick = [s for s, lv in zip(sections, levels) if lv == level]
+        info = []
+        got = _native.bz2_compress(pick, level=level, threads=4, info=info)
+        for data, z, inf in zip(pick, got, info):
+            assert inf[2] == 0
+            assert z == serial(data, level)
+            assert _native.bz2_decompress(z, threads=4) == data.tobytes()
