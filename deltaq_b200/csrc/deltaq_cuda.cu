@@ -1315,7 +1315,7 @@ static int bsdiff_streams_locked(dq_ctx *ctx, const uint8_t *old_, int32_t n, co
                    (werr != cudaSuccess ? std::string(" (") + cudaGetErrorString(werr) + ")" : std::string());
         return werr != cudaSuccess ? DQ_ERR_CUDA : DQ_ERR_INTERNAL;
     }
-    if (trace) fprintf(stderr, "[dq trace] host loop done %.3f ms (scan side %.3f ms, extender done %.3f ms / busy %.3f ms), %zu stops%s\n", since(), ctx->streams.scan_done_ms, ctx->streams.extender_done_ms, ctx->streams.extender_busy_ms, ctx->streams.ctrl.size() / 24, overflow ? " [full-table fallback]" : "");
+    if (trace) fprintf(stderr, "[dq trace] host loop done %.3f ms (scan side %.3f ms, extender done %.3f ms / busy %.3f ms), %zu stops, %lld bytes certified equal%s\n", since(), ctx->streams.scan_done_ms, ctx->streams.extender_done_ms, ctx->streams.extender_busy_ms, ctx->streams.ctrl.size() / 24, (long long)ctx->streams.cert_bytes, overflow ? " [full-table fallback]" : "");
     DQ_CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
     DQ_CK(ctx, werr);

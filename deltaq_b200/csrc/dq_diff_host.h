@@ -19,6 +19,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 #if defined(__SSE2__)
@@ -62,6 +63,7 @@ struct Streams {
     // DQ_TRACE: when the scan side finished (relative to the start of the loop), and how long the other threads
     // spent working rather than waiting
     double scan_done_ms = 0, extender_busy_ms = 0, writer_busy_ms = 0, extender_done_ms = 0;
+    int64_t cert_errors = 0, cert_bytes = 0;  // DQ_CHECK_CERTS: certified stretches that were not equal; bytes certified
 };
 
 // bit k of the result is set iff a[k] == b[k], k in [0, 32)
@@ -459,6 +461,71 @@ template <typename Walk> inline int32_t first_best_step(Crew *crew, int32_t span
     return at;
 }
 
+// A stretch of new the scan has PROVED equal to old at the alignment of the piece it lies in: new[start .. start+len) ==
+// old[start+lastoffset .. +len).  The scan gets this for free -- it leaves its inner loop either at a match whose len bytes
+// all agree at the current alignment (Diff.cs:117, len == oldscore: no stop, the same piece goes on) or at a stop, whose
+// exact match (pos, len) starts the next piece at the alignment pos - scan -- and most of an edited file is made of such
+// stretches.  The forward extension (Diff.cs:132-145) walks them without reading them (every step is +1, so the last one
+// is the update), and their diff bytes are zeros.
+struct Cert {
+    int32_t start, len;
+};
+constexpr int32_t kCertMin = 256;  // shorter stretches are not worth a queue slot
+
+// first_best_step for the forward walk of a piece that starts at new offset `base`, with the certified stretches of that
+// piece (ascending, disjoint).  Real steps run in whole-mode Runs (chunks on this thread, waves on the crew) and combine
+// exactly as single steps do; the early exit is tested between them.
+template <typename Walk>
+inline int32_t first_best_step_certified(Crew *crew, int32_t span, int32_t base, const Cert *certs, size_t ncerts, Walk &&walk)
+{
+    const int P = crew ? crew->parts() : 1;
+    constexpr int32_t kChunk = 8 << 10;
+    int32_t cur = 0, best = 0, at = 0, done = 0;
+    size_t c = 0;
+    Run r[16];
+    auto take = [&](const Run &x, int32_t lo) {
+        if (x.best != kNoBest && cur + x.best > best) {
+            best = cur + x.best;
+            at = lo + x.first;
+        }
+        cur += x.total;
+    };
+    while (done < span) {
+        if (cur + (span - done) <= best) break;
+        while (c < ncerts && (int64_t)certs[c].start + certs[c].len - base <= done) ++c;
+        int32_t cs = span, ce = span;  // the next certified stretch in steps, clipped to what is left
+        if (c < ncerts) {
+            cs = (int32_t)std::min<int64_t>(span, std::max<int64_t>(done, (int64_t)certs[c].start - base));
+            ce = (int32_t)std::min<int64_t>(span, std::max<int64_t>(cs, (int64_t)certs[c].start + certs[c].len - base));
+        }
+        if (cs == done) {
+            if (ce > done) {  // inside it: the value rises by one per step
+                cur += ce - done;
+                done = ce;
+                if (cur > best) best = cur, at = done;
+            }
+            continue;
+        }
+        const int32_t gap = cs - done;
+        if (P == 1 || gap < crew_min()) {
+            const int32_t len = std::min(gap, kChunk);
+            take(walk(done, len, true), done);
+            done += len;
+            continue;
+        }
+        const int32_t wave = (int32_t)std::min<int64_t>(gap, (int64_t)P * crew_part());
+        const int32_t per = (int32_t)((((int64_t)wave + P - 1) / P + 31) & ~(int64_t)31);
+        crew->run([&](int part) {
+            const int32_t lo = (int32_t)std::min<int64_t>(wave, (int64_t)part * per);
+            const int32_t hi = (int32_t)std::min<int64_t>(wave, (int64_t)(part + 1) * per);
+            r[part] = lo < hi ? walk(done + lo, hi - lo, true) : Run{0, kNoBest, 0};
+        });
+        for (int part = 0; part < P; ++part) take(r[part], done + (int32_t)std::min<int64_t>(wave, (int64_t)part * per));
+        done += wave;
+    }
+    return at;
+}
+
 // Diff.cs:172-188: step i (1-based) adds (n1[i-1] == o1[i-1]) - (n2[i-1] == o2[i-1])
 template <bool kWhole>
 inline Run walk_overlap(const uint8_t *n1, const uint8_t *o1, const uint8_t *n2, const uint8_t *o2, int32_t span)
@@ -499,15 +566,17 @@ struct Piece {
 };
 
 inline Piece extend_stop(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen, int32_t scan,
-                         int32_t pos, EmitState &st, Crew *crew = nullptr)
+                         int32_t pos, EmitState &st, Crew *crew = nullptr, const Cert *certs = nullptr, size_t ncerts = 0)
 {
     int32_t &lastscan = st.lastscan, &lastpos = st.lastpos;
     // Diff.cs:132-145
     const int32_t fspan = (scan - lastscan) < (oldLen - lastpos) ? (scan - lastscan) : (oldLen - lastpos);
     const uint8_t *fo = oldData + lastpos, *fn = newData + lastscan;
-    int32_t lenf = first_best_step(crew, fspan, [&](int32_t lo, int32_t len, bool whole) {
+    auto fwalk = [&](int32_t lo, int32_t len, bool whole) {
         return whole ? walk_forward<true>(fo + lo, fn + lo, len) : walk_forward<false>(fo + lo, fn + lo, len);
-    });
+    };
+    int32_t lenf = ncerts ? first_best_step_certified(crew, fspan, lastscan, certs, ncerts, fwalk)
+                          : first_best_step(crew, fspan, fwalk);
 
     // Diff.cs:147-165
     int32_t lenb = 0;
@@ -564,9 +633,13 @@ inline void write_piece(const uint8_t *oldData, const uint8_t *newData, const Pi
 
 // ready(upto): returns once table entries [0, min(upto, newLen)) are valid (the table may still be arriving from
 // the device in slices while the loop runs)
-template <typename Table, typename Ready, typename Sink>
+struct NoCerts {
+    void operator()(int32_t, int32_t) const {}
+};
+// certified(start, len): see Cert; called only for tables whose entries are exact longest matches
+template <typename Table, typename Ready, typename Sink, typename CertSink = NoCerts>
 inline void greedy_scan(const uint8_t *oldData, int32_t oldLen, const uint8_t *newData, int32_t newLen,
-                        Table &tab, Streams &out, Ready &&ready, Sink &&sink)
+                        Table &tab, Streams &out, Ready &&ready, Sink &&sink, CertSink &&certified = CertSink{})
 {
     int32_t scan = 0, pos = 0, len = 0;
     int32_t lastoffset = 0;
@@ -714,6 +787,12 @@ inline void greedy_scan(const uint8_t *oldData, int32_t oldLen, const uint8_t *n
             if (pos == kPosUnknown) pos = tab.fetch_pos(last_read);
             sink(scan, pos);
             lastoffset = pos - scan;
+            // the match that ended the scan opens the next piece: new[scan .. scan+len) == old[pos .. pos+len)
+            if constexpr (Table::kExactMatches)
+                if (scan < newLen && len >= kCertMin) certified(scan, len);
+        } else if constexpr (Table::kExactMatches) {
+            // no stop: all len bytes of this match agree at the current alignment, the piece goes on behind it
+            if (len >= kCertMin) certified(scan, len);
         }
     }
 }
@@ -798,8 +877,9 @@ struct PipelineShape {
     }
 };
 
-// One job of a writer thread: dst[i] = n[i] - o[i] (o != nullptr, Diff.cs:197-200) or dst[i] = n[i] (extra bytes,
-// Diff.cs:202-207).  dst ranges of different jobs are disjoint.
+// One job of a writer thread: dst[i] = n[i] - o[i] (o != nullptr, Diff.cs:197-200), dst[i] = n[i] (extra bytes,
+// Diff.cs:202-207), or dst[i] = 0 (n == nullptr: a certified stretch of the piece).  dst ranges of different jobs are
+// disjoint.
 struct WriteJob {
     const uint8_t *n, *o;
     uint8_t *dst;
@@ -807,6 +887,10 @@ struct WriteJob {
 };
 inline void run_write_job(const WriteJob &j)
 {
+    if (!j.n) {  // a certified stretch: new == old there, the diff bytes are zeros
+        std::memset(j.dst, 0, (size_t)j.len);
+        return;
+    }
     if (!j.o) {
         std::memcpy(j.dst, j.n, (size_t)j.len);
         return;
@@ -834,13 +918,17 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
 {
     reset_streams(out, newLen);
     out.extra.reserve((size_t)newLen);  // like diff: disjoint ranges of new; no reallocation under the writers
-    struct Stop {
+    struct Stop {  // certified == false: a stop (scan, pos); true: a certified stretch (start, len) of the piece being scanned
         int32_t scan, pos;
+        bool certified;
     };
     constexpr int32_t kJobBytes = 256 << 10;
+    const bool check_certs = std::getenv("DQ_CHECK_CERTS") != nullptr;  // tests: compare every certified stretch
+    const bool use_certs = std::getenv("DQ_NO_CERTS") == nullptr;       // A/B: walk and subtract everything
     const int W = std::max(1, std::min(shape.writers, 4));
     const auto t_loop = std::chrono::steady_clock::now();
     out.extender_busy_ms = out.writer_busy_ms = 0;
+    out.cert_errors = out.cert_bytes = 0;
     auto stops = std::make_unique<Handoff<Stop>>();
     std::vector<std::unique_ptr<Handoff<WriteJob>>> jobs;
     for (int w = 0; w < W; ++w) jobs.push_back(std::make_unique<Handoff<WriteJob>>());
@@ -858,18 +946,42 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
         int next_writer = 0;
         auto hand_out = [&](const uint8_t *n, const uint8_t *o, uint8_t *dst, int32_t len) {
             for (int32_t k = 0; k < len; k += kJobBytes) {
-                jobs[next_writer]->push(WriteJob{n + k, o ? o + k : nullptr, dst + k, std::min(kJobBytes, len - k)});
+                jobs[next_writer]->push(WriteJob{n ? n + k : nullptr, o ? o + k : nullptr, dst + k, std::min(kJobBytes, len - k)});
                 next_writer = (next_writer + 1) % W;
             }
         };
+        std::vector<Cert> certs;  // of the piece that the next stop ends
         while (stops->pop(sp)) {
+            if (sp.certified) {
+                if (check_certs) {
+                    const int64_t o = (int64_t)sp.scan - st.lastscan + st.lastpos;
+                    if (o < 0 || o + sp.pos > oldLen || (int64_t)sp.scan + sp.pos > newLen ||
+                        std::memcmp(newData + sp.scan, oldData + o, (size_t)sp.pos) != 0)
+                        out.cert_errors++;
+                }
+                out.cert_bytes += sp.pos;
+                certs.push_back(Cert{sp.scan, sp.pos});
+                continue;
+            }
             const auto t_a = std::chrono::steady_clock::now();
-            const Piece pc = extend_stop(oldData, oldLen, newData, newLen, sp.scan, sp.pos, st, &crew);
+            const Piece pc = extend_stop(oldData, oldLen, newData, newLen, sp.scan, sp.pos, st, &crew, certs.data(), certs.size());
             out.extender_busy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
             if (pc.lenf > 0) {
-                hand_out(newData + pc.lastscan, oldData + pc.lastpos, out.diff.p.get() + diff_at, pc.lenf);
+                // diff bytes of [lastscan, lastscan + lenf): zeros over the certified stretches, new - old between them
+                uint8_t *dst = out.diff.p.get() + diff_at;
+                int32_t at = 0;  // offset into the piece
+                for (const Cert &c : certs) {
+                    const int32_t cb = (int32_t)std::min<int64_t>(pc.lenf, std::max<int64_t>(at, (int64_t)c.start - pc.lastscan));
+                    const int32_t ce = (int32_t)std::min<int64_t>(pc.lenf, std::max<int64_t>(cb, (int64_t)c.start + c.len - pc.lastscan));
+                    if (ce - cb < kCertMin) continue;
+                    if (cb > at) hand_out(newData + pc.lastscan + at, oldData + pc.lastpos + at, dst + at, cb - at);
+                    hand_out(nullptr, nullptr, dst + cb, ce - cb);
+                    at = ce;
+                }
+                if (pc.lenf > at) hand_out(newData + pc.lastscan + at, oldData + pc.lastpos + at, dst + at, pc.lenf - at);
                 diff_at += (size_t)pc.lenf;
             }
+            certs.clear();
             if (pc.extra > 0) {
                 hand_out(newData + pc.lastscan + pc.lenf, nullptr, out.extra.p.get() + extra_at, pc.extra);
                 extra_at += (size_t)pc.extra;
@@ -891,7 +1003,10 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
     };
     try {
         greedy_scan(oldData, oldLen, newData, newLen, tab, scan_side, ready,
-                    [&](int32_t scan, int32_t pos) { stops->push(Stop{scan, pos}); });
+                    [&](int32_t scan, int32_t pos) { stops->push(Stop{scan, pos, false}); },
+                    [&](int32_t start, int32_t len) {
+                        if (use_certs) stops->push(Stop{start, len, true});
+                    });
     } catch (...) {
         finish();
         throw;
@@ -900,6 +1015,7 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
     finish();
     out.visits = scan_side.visits;
     out.scan_done_ms = scan_ms;
+    if (out.cert_errors) throw std::runtime_error("greedy loop: a certified stretch of new differs from old");
 }
 
 }  // namespace diffhost

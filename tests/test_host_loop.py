@@ -46,13 +46,15 @@ def test_pair_has_stretches_long_enough_for_the_crew(pair):
     assert (ctrl[:, 0] >= (128 << 10)).sum() >= 3
 
 
-def test_streams_end_to_end_on_emulator_at_crew_sizes(pair, monkeypatch):
+@pytest.mark.parametrize("shape", ["3,2", "0,1"])
+def test_streams_end_to_end_on_emulator_at_crew_sizes(pair, monkeypatch, shape):
     # the same pair through the whole of dq_cuda_bsdiff_streams on the logic emulator: sort, search,
-    # encode_table_kernel, coded-table scan (block steps, chain walks), crew and writers
+    # encode_table_kernel, coded-table scan (block steps, chain walks, certified stretches), crew and writers
     import emu
     from deltaq_b200 import CudaSuffixSort, bsdiff
     old, new, ref = pair
-    monkeypatch.setenv("DQ_HOST_THREADS", "3,2")
+    monkeypatch.setenv("DQ_HOST_THREADS", shape)
+    monkeypatch.setenv("DQ_CHECK_CERTS", "1")
     s = CudaSuffixSort(_lib=emu.library())
     try:
         got = bsdiff.create_streams(old, new, s)
