@@ -109,7 +109,7 @@ struct dq_ctx {
 
     // diff streams (host)
     dq::diffhost::Streams streams;
-    std::vector<uint8_t> patch, patch_tail[2];  // dq_cuda_bsdiff_patch: the BSDIFF40 file / scratch for two sections
+    dq::bz2host::RawBuf patch;  // dq_cuda_bsdiff_patch: the BSDIFF40 file
     PinBuf h_pos, h_len;             // full table: fallback only
     PinBuf h_code, h_heads, h_tiles; // coded table (encode_table_kernel)
     DevBuf d_code, d_headcount;
@@ -1459,42 +1459,48 @@ int dq_cuda_bsdiff_patch(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint
     // Diff.cs:54-70, :226-241: header (signature, compressed sizes of ctrl and diff, size of newData), then the sections
     namespace bz = dq::bz2host;
     try {
-        const int64_t caps[3] = {bz::bound(st.ctrl_len), bz::bound(st.diff_len), bz::bound(st.extra_len)};
-        ctx->patch.resize((size_t)(32 + caps[0]));
-        ctx->patch_tail[0].resize((size_t)caps[1]);
-        ctx->patch_tail[1].resize((size_t)caps[2]);
         bz::StreamJob jobs[3];
         const uint8_t *srcs[3] = {st.ctrl, st.diff, st.extra};
         const int64_t lens[3] = {st.ctrl_len, st.diff_len, st.extra_len};
-        uint8_t *outs[3] = {ctx->patch.data() + 32, ctx->patch_tail[0].data(), ctx->patch_tail[1].data()};
         for (int s = 0; s < 3; ++s) {
             jobs[s].src = srcs[s];
             jobs[s].len = lens[s];
-            jobs[s].out = outs[s];
-            jobs[s].cap = caps[s];
+            jobs[s].out = nullptr;
+            jobs[s].cap = 0;
         }
-        const int rc = bz::compress_streams(jobs, 3, level, 0);
+        bz::SectionCompressor sections;
+        const int rc = sections.run(jobs, 3, level, 0);
         if (rc != 0) {
             ctx->err = rc == -3 ? "bsdiff_patch: libbz2 not found" : "bsdiff_patch: libbz2 failed";
             return DQ_ERR_INTERNAL;
         }
-        ctx->patch.resize((size_t)(32 + jobs[0].out_len + jobs[1].out_len + jobs[2].out_len));
-        uint8_t *p = ctx->patch.data();
+        // the sizes are known before a byte is stitched: the sections go straight to their places behind the header
+        const int64_t size[3] = {sections.size(0), sections.size(1), sections.size(2)};
+        ctx->patch.len = 0;
+        ctx->patch.reserve((size_t)(32 + size[0] + size[1] + size[2]));
+        uint8_t *p = ctx->patch.p;
         auto packed = [](uint8_t *b, int64_t y) {  // SpanExtensions.WritePackedLong (SpanExtensions.cs:7-18), y >= 0 here
             for (int i = 0; i < 8; ++i) b[i] = (uint8_t)((uint64_t)y >> (8 * i));
         };
         memcpy(p, "BSDIFF40", 8);
-        packed(p + 8, jobs[0].out_len);
-        packed(p + 16, jobs[1].out_len);
+        packed(p + 8, size[0]);
+        packed(p + 16, size[1]);
         packed(p + 24, (int64_t)m);
-        memcpy(p + 32 + jobs[0].out_len, ctx->patch_tail[0].data(), (size_t)jobs[1].out_len);
-        memcpy(p + 32 + jobs[0].out_len + jobs[1].out_len, ctx->patch_tail[1].data(), (size_t)jobs[2].out_len);
+        int64_t at = 32;
+        for (int s = 0; s < 3; ++s) {
+            if (!sections.write(s, p + at, size[s]) || jobs[s].out_len != size[s]) {
+                ctx->err = "bsdiff_patch: section size mismatch";
+                return DQ_ERR_INTERNAL;
+            }
+            at += size[s];
+        }
+        ctx->patch.len = (size_t)at;
     } catch (const std::bad_alloc &) {
         ctx->err = "bsdiff_patch: out of host memory";
         return DQ_ERR_OUT_OF_MEMORY;
     }
-    *patch = ctx->patch.data();
-    *patch_len = (int64_t)ctx->patch.size();
+    *patch = ctx->patch.p;
+    *patch_len = (int64_t)ctx->patch.len;
     return DQ_OK;
 }
 

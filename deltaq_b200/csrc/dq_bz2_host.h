@@ -39,6 +39,7 @@
 #include <cstring>
 #include <deque>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -211,11 +212,45 @@ private:
     int have_ = 0;
 };
 
+// growable byte buffer without the zero fill of std::vector (realloc moves large blocks by remapping, not copying)
+struct RawBuf {
+    uint8_t *p = nullptr;
+    size_t len = 0, cap = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), len(o.len), cap(o.cap) { o.p = nullptr; o.len = o.cap = 0; }
+    ~RawBuf() { free(p); }
+    void reserve(size_t want)
+    {
+        if (want <= cap) return;
+        void *q = realloc(p, want);
+        if (!q) throw std::bad_alloc();
+        p = static_cast<uint8_t *>(q);
+        cap = want;
+    }
+    void shrink()
+    {
+        if (len && len < cap) {
+            if (void *q = realloc(p, len)) p = static_cast<uint8_t *>(q), cap = len;
+        }
+    }
+    void swap(RawBuf &o)
+    {
+        std::swap(p, o.p);
+        std::swap(len, o.len);
+        std::swap(cap, o.cap);
+    }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return len; }
+    bool empty() const { return len == 0; }
+};
+
 struct Piece {
     int stream = 0;
     const uint8_t *src = nullptr;
     int64_t len = 0;
-    std::vector<uint8_t> z;       // the piece as its own bzip2 stream
+    RawBuf z;                     // the piece as its own bzip2 stream
     int64_t block_end = 0;        // bit offset of the end-of-stream magic in z
     uint32_t crc = 0;             // CRC of the one block in z
     bool ok = false;
@@ -224,18 +259,18 @@ struct Piece {
 // z is a stream of exactly one block?  Then find where the block ends.
 inline bool locate_block(Piece &pc, int level)
 {
-    const std::vector<uint8_t> &z = pc.z;
-    const int64_t bits = (int64_t)z.size() * 8;
-    if (z.size() < 4 + 10 + 10 || z[0] != 'B' || z[1] != 'Z' || z[2] != 'h' || z[3] != '0' + level) return false;
-    if (read_bits(z.data(), 32, 48) != kBlockMagic) return false;
-    pc.crc = (uint32_t)read_bits(z.data(), 80, 32);
+    const uint8_t *z = pc.z.data();
+    const int64_t bits = (int64_t)pc.z.size() * 8;
+    if (pc.z.size() < 4 + 10 + 10 || z[0] != 'B' || z[1] != 'Z' || z[2] != 'h' || z[3] != '0' + level) return false;
+    if (read_bits(z, 32, 48) != kBlockMagic) return false;
+    pc.crc = (uint32_t)read_bits(z, 80, 32);
     int found = 0;
     for (int pad = 0; pad < 8; ++pad) {
         const int64_t at = bits - pad - 80;
         if (at < 112) break;
-        if (read_bits(z.data(), at, 48) != kEndMagic) continue;
-        if ((uint32_t)read_bits(z.data(), at + 48, 32) != pc.crc) continue;  // one block: stream CRC == block CRC
-        if (pad && read_bits(z.data(), bits - pad, pad) != 0) continue;
+        if (read_bits(z, at, 48) != kEndMagic) continue;
+        if ((uint32_t)read_bits(z, at + 48, 32) != pc.crc) continue;  // one block: stream CRC == block CRC
+        if (pad && read_bits(z, bits - pad, pad) != 0) continue;
         pc.block_end = at;
         ++found;
     }
@@ -292,15 +327,33 @@ inline int64_t coded_estimate(const uint8_t *p, int64_t n)
     return (int64_t)((double)coded / (double)(kWindow * kWindows) * (double)n);
 }
 
-// Compress every job; level 1..9, or 0 = choose per stream; threads 0 = the CPUs this process may run on.
-// Returns 0, -1 (some output buffer too small), -2 (libbz2 failed), -3 (libbz2 not found).
+// run(): every job cut and compressed; level 1..9, or 0 = choose per stream; threads 0 = the CPUs this process may run
+// on.  Returns 0, -2 (libbz2 failed), -3 (libbz2 not found).  The jobs' out / cap are not used by the class: size(s) is the
+// exact length of section s and write(s, out, cap) stitches it wherever the caller wants it.
 //
 // The calling thread cuts the sections (largest first) and hands every piece to the crew the moment its end is known, so
 // the cut (about 0.5 GB/s, sequential by nature: where a block ends depends on where the one before it ended) runs
 // beside the compression instead of in front of it; then it joins the crew.
-inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
+class SectionCompressor {
+    StreamJob *jobs_ = nullptr;
+    int count_ = 0;
+    std::deque<Piece> pieces;  // in cut order; references stay valid while the cutter appends
+    std::vector<size_t> first_piece;
+    std::vector<RawBuf> serial_;  // sections that had to take the serial path
+
+public:
+    // cut and compress; afterwards size(s) is exact and write(s, ...) stitches section s
+    int run(StreamJob *jobs, int count, int level, int threads);
+    int64_t size(int s) const;
+    bool write(int s, uint8_t *out, int64_t cap);
+};
+
+inline int SectionCompressor::run(StreamJob *jobs, int count, int level, int threads)
 {
     if (!libbz2()) return -3;
+    jobs_ = jobs;
+    count_ = count;
+    pieces.clear();
     const bool trace = std::getenv("DQ_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
@@ -323,7 +376,6 @@ inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
 
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<Piece> pieces;  // in cut order; references stay valid while the cutter appends
     size_t next = 0;
     bool closed = false;
     std::atomic<int> failed{0};
@@ -338,20 +390,21 @@ inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
                 pc = &pieces[next++];
             }
             try {
-                pc->z.resize((size_t)bound(pc->len));
+                pc->z.reserve((size_t)bound(pc->len));
             } catch (...) {
                 failed.store(1);
                 continue;
             }
-            unsigned dl = (unsigned)pc->z.size();
-            const int rc = fn(reinterpret_cast<char *>(pc->z.data()), &dl,
+            unsigned dl = (unsigned)pc->z.cap;
+            const int rc = fn(reinterpret_cast<char *>(pc->z.p), &dl,
                               const_cast<char *>(reinterpret_cast<const char *>(pc->src)), (unsigned)pc->len,
                               jobs[pc->stream].level, 0, 0);
             if (rc != 0) {
                 failed.store(1);
                 continue;
             }
-            pc->z.resize(dl);
+            pc->z.len = dl;
+            pc->z.shrink();  // the bound is the size of the INPUT piece: give the rest back
             pc->ok = locate_block(*pc, jobs[pc->stream].level);
         }
     };
@@ -366,7 +419,7 @@ inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
     std::vector<int> by_size(count);
     for (int s = 0; s < count; ++s) by_size[s] = s;
     std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) { return jobs[a].len > jobs[b].len; });
-    std::vector<size_t> first_piece(count, 0);
+    first_piece.assign((size_t)count, 0);
     bool cut_failed = false;
     for (int s : by_size) {
         StreamJob &job = jobs[s];
@@ -407,33 +460,76 @@ inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
     if (failed.load() || cut_failed) return -2;
     if (trace) fprintf(stderr, "[dq trace] bz2: pieces compressed by %zu threads at %.3f ms\n", pool.size() + 1, since());
 
-    // stitch, section by section
+    // a section with a piece that did not come back as one block is compressed serially, here, so that its size is known
+    serial_.clear();
+    serial_.resize((size_t)count);
     int worst = 0;
     for (int s = 0; s < count; ++s) {
         StreamJob &job = jobs[s];
-        const size_t npc = (size_t)job.pieces, first = first_piece[s];
         bool all_ok = true;
-        for (size_t k = 0; k < npc; ++k) all_ok = all_ok && pieces[first + k].ok;
-        if (!all_ok) {
-            job.fell_back = true;
-            job.status = serial_compress(job, job.level);
-        } else {
-            BitWriter w(job.out, job.cap);
-            bool fits = w.put('B', 8) && w.put('Z', 8) && w.put('h', 8) && w.put((uint64_t)('0' + job.level), 8);
-            uint32_t combined = 0;
-            for (size_t k = 0; k < npc && fits; ++k) {
-                const Piece &pc = pieces[first + k];
-                fits = w.append(pc.z.data(), 32, pc.block_end);
-                combined = ((combined << 1) | (combined >> 31)) ^ pc.crc;
-            }
-            fits = fits && w.put(kEndMagic >> 24, 24) && w.put(kEndMagic & 0xffffffu, 24) && w.put(combined, 32) &&
-                   w.finish();
-            job.status = fits ? 0 : -1;
-            job.out_len = fits ? w.size() : 0;
-        }
+        for (int k = 0; k < job.pieces; ++k) all_ok = all_ok && pieces[first_piece[s] + (size_t)k].ok;
+        if (all_ok) continue;
+        job.fell_back = true;
+        RawBuf &z = serial_[(size_t)s];
+        z.reserve((size_t)bound(job.len));
+        StreamJob tmp = job;
+        tmp.out = z.p;
+        tmp.cap = (int64_t)z.cap;
+        job.status = serial_compress(tmp, job.level);
+        z.len = (size_t)tmp.out_len;
         worst = std::min(worst, job.status);
     }
-    if (trace) fprintf(stderr, "[dq trace] bz2: sections stitched at %.3f ms\n", since());
+    if (trace) fprintf(stderr, "[dq trace] bz2: pieces ready at %.3f ms\n", since());
+    return worst;
+}
+
+inline int64_t SectionCompressor::size(int s) const
+{
+    const StreamJob &job = jobs_[s];
+    if (job.fell_back) return (int64_t)serial_[(size_t)s].len;
+    int64_t bits = 32 + 80;  // stream header; end magic + combined CRC
+    for (int k = 0; k < job.pieces; ++k) bits += pieces[first_piece[(size_t)s] + (size_t)k].block_end - 32;
+    return (bits + 7) / 8;
+}
+
+inline bool SectionCompressor::write(int s, uint8_t *out, int64_t cap)
+{
+    StreamJob &job = jobs_[s];
+    job.out_len = 0;
+    if (cap < size(s)) {
+        job.status = -1;
+        return false;
+    }
+    if (job.fell_back) {
+        const RawBuf &z = serial_[(size_t)s];
+        if (z.len) memcpy(out, z.p, z.len);
+        job.out_len = (int64_t)z.len;
+        return true;
+    }
+    BitWriter w(out, cap);
+    bool fits = w.put('B', 8) && w.put('Z', 8) && w.put('h', 8) && w.put((uint64_t)('0' + job.level), 8);
+    uint32_t combined = 0;
+    for (int k = 0; k < job.pieces && fits; ++k) {
+        const Piece &pc = pieces[first_piece[(size_t)s] + (size_t)k];
+        fits = w.append(pc.z.data(), 32, pc.block_end);
+        combined = ((combined << 1) | (combined >> 31)) ^ pc.crc;
+    }
+    fits = fits && w.put(kEndMagic >> 24, 24) && w.put(kEndMagic & 0xffffffu, 24) && w.put(combined, 32) && w.finish();
+    job.status = fits ? 0 : -1;
+    job.out_len = fits ? w.size() : 0;
+    return fits;
+}
+
+// Compress every job into its out buffer; level 1..9, or 0 = choose per stream; threads 0 = the CPUs this process may
+// run on.  Returns 0, -1 (some output buffer too small), -2 (libbz2 failed), -3 (libbz2 not found).
+inline int compress_streams(StreamJob *jobs, int count, int level, int threads)
+{
+    SectionCompressor c;
+    const int rc = c.run(jobs, count, level, threads);
+    if (rc != 0) return rc;
+    int worst = 0;
+    for (int s = 0; s < count; ++s)
+        if (!c.write(s, jobs[s].out, jobs[s].cap)) worst = -1;
     return worst;
 }
 
@@ -479,34 +575,6 @@ inline const DecodeLib &libbz2_decode()
     }();
     return lib;
 }
-
-// growable byte buffer without the zero fill of std::vector (realloc moves large blocks by remapping, not copying)
-struct RawBuf {
-    uint8_t *p = nullptr;
-    size_t len = 0, cap = 0;
-    RawBuf() = default;
-    RawBuf(const RawBuf &) = delete;
-    RawBuf &operator=(const RawBuf &) = delete;
-    RawBuf(RawBuf &&o) noexcept : p(o.p), len(o.len), cap(o.cap) { o.p = nullptr; o.len = o.cap = 0; }
-    ~RawBuf() { free(p); }
-    void reserve(size_t want)
-    {
-        if (want <= cap) return;
-        void *q = realloc(p, want);
-        if (!q) throw std::bad_alloc();
-        p = static_cast<uint8_t *>(q);
-        cap = want;
-    }
-    void swap(RawBuf &o)
-    {
-        std::swap(p, o.p);
-        std::swap(len, o.len);
-        std::swap(cap, o.cap);
-    }
-    const uint8_t *data() const { return p; }
-    size_t size() const { return len; }
-    bool empty() const { return len == 0; }
-};
 
 // serial decode of the first stream in [z, z+len): 0, or -2 (not a bzip2 stream / damaged)
 inline int serial_decompress(const uint8_t *z, int64_t len, RawBuf &out)
