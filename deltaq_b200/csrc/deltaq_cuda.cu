@@ -1434,6 +1434,11 @@ int dq_cuda_bspatch(const uint8_t *old_, int64_t n, const uint8_t *patch, int64_
         jobs[1].len = diff_len;
         jobs[2].src = patch + 32 + ctrl_len + diff_len;
         jobs[2].len = patch_len - 32 - ctrl_len - diff_len;
+        // what a patch for `size` bytes can use: at most size diff bytes, size extra bytes and one triple per output byte
+        // (+ one); a section that decodes to more than that (plus slack) is damaged or hostile, and is not unpacked further
+        const int64_t slack = 1 << 20;
+        jobs[0].limit = size > (INT64_MAX - slack) / 24 - 1 ? INT64_MAX : 24 * (size + 1) + slack;
+        jobs[1].limit = jobs[2].limit = size + slack;
         const int rc = bz::decompress_streams(jobs, 3, threads);
         if (rc == -3) return DQ_ERR_INTERNAL;
         if (rc != 0) return DQ_ERR_CORRUPT_PATCH;

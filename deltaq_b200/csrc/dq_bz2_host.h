@@ -33,6 +33,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -332,7 +333,7 @@ inline int64_t coded_estimate(const uint8_t *p, int64_t n)
 // exact length of section s and write(s, out, cap) stitches it wherever the caller wants it.
 //
 // The calling thread cuts the sections (largest first) and hands every piece to the crew the moment its end is known, so
-// the cut (about 0.5 GB/s, sequential by nature: where a block ends depends on where the one before it ended) runs
+// the cut (1-2 GB/s, sequential by nature: where a block ends depends on where the one before it ended) runs
 // beside the compression instead of in front of it; then it joins the crew.
 class SectionCompressor {
     StreamJob *jobs_ = nullptr;
@@ -576,8 +577,8 @@ inline const DecodeLib &libbz2_decode()
     return lib;
 }
 
-// serial decode of the first stream in [z, z+len): 0, or -2 (not a bzip2 stream / damaged)
-inline int serial_decompress(const uint8_t *z, int64_t len, RawBuf &out)
+// serial decode of the first stream in [z, z+len): 0, or -2 (not a bzip2 stream / damaged / more than `limit` bytes)
+inline int serial_decompress(const uint8_t *z, int64_t len, RawBuf &out, int64_t limit = INT64_MAX)
 {
     const DecodeLib &lib = libbz2_decode();
     if (!lib.ok()) return -2;
@@ -601,6 +602,10 @@ inline int serial_decompress(const uint8_t *z, int64_t len, RawBuf &out)
         st.avail_out = (unsigned)room;
         rc = lib.step(&st);
         out.len += room - st.avail_out;
+        if ((int64_t)out.len > limit) {  // a section that decodes to more than its patch can use: not worth the memory
+            rc = -4;
+            break;
+        }
         if (rc != 0) break;  // 4 = BZ_STREAM_END, negative = damaged
         if (st.avail_in == 0 && fed >= len && st.avail_out != 0) {  // input exhausted in mid-stream
             rc = -7;                                                   // BZ_UNEXPECTED_EOF
@@ -627,6 +632,7 @@ struct DecodeJob {
     const uint8_t *src;
     int64_t len;
     RawBuf out;                // the decoded section
+    int64_t limit = INT64_MAX; // a section that decodes to more than this counts as damaged
     int blocks = 0;
     bool fell_back = false;
     int status = 0;            // 0, -2 damaged
@@ -712,7 +718,7 @@ inline int decompress_streams(DecodeJob *jobs, int count, int threads)
             const DecodeJob &job = jobs[pc.stream];
             try {
                 if (pc.begin < 0) {
-                    pc.ok = serial_decompress(job.src, job.len, pc.data) == 0;
+                    pc.ok = serial_decompress(job.src, job.len, pc.data, job.limit) == 0;
                     continue;
                 }
                 pc.crc = (uint32_t)read_bits(job.src, pc.begin + 48, 32);
@@ -724,7 +730,7 @@ inline int decompress_streams(DecodeJob *jobs, int count, int threads)
                 if (!fits) continue;
                 // the decoded size is not known in advance (a block of zeros expands 51x): the streaming decoder grows
                 // its output as it goes
-                pc.ok = serial_decompress(wrapped.data(), w.size(), pc.data) == 0;
+                pc.ok = serial_decompress(wrapped.data(), w.size(), pc.data, job.limit) == 0;
             } catch (...) {
                 pc.ok = false;
             }
@@ -757,7 +763,9 @@ inline int decompress_streams(DecodeJob *jobs, int count, int threads)
                 combined = ((combined << 1) | (combined >> 31)) ^ pc.crc;
                 total += pc.data.size();
             }
-            if (all_ok && combined == (uint32_t)read_bits(job.src, end_at[s] + 48, 32)) {
+            if (all_ok && (int64_t)total > job.limit) {
+                job.status = -2;
+            } else if (all_ok && combined == (uint32_t)read_bits(job.src, end_at[s] + 48, 32)) {
                 if (job.blocks == 1) {
                     job.out.swap(pieces[first].data);
                 } else {
@@ -773,7 +781,7 @@ inline int decompress_streams(DecodeJob *jobs, int count, int threads)
             } else {
                 // a candidate block was not a block, or the stream is damaged: the serial decoder decides
                 job.fell_back = true;
-                job.status = serial_decompress(job.src, job.len, job.out) == 0 ? 0 : -2;
+                job.status = serial_decompress(job.src, job.len, job.out, job.limit) == 0 ? 0 : -2;
             }
         }
         worst = std::min(worst, job.status);

@@ -190,7 +190,9 @@ int dq_cuda_bsdiff_patch(dq_ctx *ctx, const uint8_t *old_, int32_t n, const uint
  * combined CRC is checked against the stream's; anything unexpected falls back to the serial decoder.  Works on any
  * BSDIFF40 file (the reference's, bsdiff 4.x's, this library's).  *new_size is set from the header as soon as the
  * header is valid; out_cap < *new_size returns DQ_ERR_INVALID_ARGUMENT (call with out_cap 0 to ask for the size).
- * DQ_ERR_CORRUPT_PATCH where the reference throws "Corrupt patch" and for damaged sections.  Pure host code. */
+ * DQ_ERR_CORRUPT_PATCH where the reference throws "Corrupt patch", for damaged sections, and for a section that decodes
+ * to more than a patch for *new_size bytes can use (diff, extra: new_size; ctrl: 24 per output byte; + 1 MiB each) --
+ * the reference streams its sections and would never notice; here nothing is unpacked past that point.  Pure host code. */
 int dq_cuda_bspatch(const uint8_t *old_, int64_t n, const uint8_t *patch, int64_t patch_len, int threads, uint8_t *out,
                     int64_t out_cap, int64_t *new_size);
 /* One bzip2 stream, blocks decoded in parallel.  *out_len = decoded size (also when cap is too small, which returns

@@ -251,3 +251,18 @@ def test_randomised_sweep_against_serial():
             assert inf[2] == 0
             assert z == serial(data, level)
             assert _native.bz2_decompress(z, threads=4) == data.tobytes()
+
+
+def test_bspatch_does_not_unpack_a_bomb():
+    """A section that decodes to far more than the patch can use (here 64 MiB of zeros in 60 bytes... of diff for a
+    100-byte file) is rejected instead of being unpacked."""
+    old = np.zeros(100, np.uint8)
+    ctrl = bz2.compress((100).to_bytes(8, "little") + (0).to_bytes(8, "little") + (0).to_bytes(8, "little"))
+    bomb = bz2.compress(bytes(64 << 20))
+    extra = bz2.compress(b"")
+    head = b"BSDIFF40" + len(ctrl).to_bytes(8, "little") + len(bomb).to_bytes(8, "little") + (100).to_bytes(8, "little")
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        _native.bspatch(old, head + ctrl + bomb + extra)
+    ok = bz2.compress(bytes(100))
+    head = b"BSDIFF40" + len(ctrl).to_bytes(8, "little") + len(ok).to_bytes(8, "little") + (100).to_bytes(8, "little")
+    assert _native.bspatch(old, head + ctrl + ok + extra).tobytes() == bytes(100)
