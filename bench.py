@@ -266,7 +266,26 @@ def diff_create_record(ctx, old, new, reps=3):
                 bz2.decompress(patch[32 + cl:32 + cl + dl]) == streams["diff"] and
                 bz2.decompress(patch[32 + cl + dl:]) == streams["extra"])
         best = min(times[1:])
+        # the way back: Patch.Apply on that file, sections decoded block-parallel (dq_cuda_bspatch), against the three
+        # sections through serial libbz2 + the same native add loop
+        from deltaq_b200 import _native
+        from deltaq_b200.bsdiff import apply_streams
+        apply_times = []
+        rebuilt = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rebuilt = _native.bspatch(old, patch)
+            apply_times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        parts = [bz2.decompress(patch[32:32 + cl]), bz2.decompress(patch[32 + cl:32 + cl + dl]),
+                 bz2.decompress(patch[32 + cl + dl:])]
+        serial_new = apply_streams(old, parts[0], parts[1], parts[2], new.size)
+        serial_apply_s = time.perf_counter() - t0
+        applied = {"call": "dq_cuda_bspatch (patch file in, new file out; host code)", "ms": min(apply_times) * 1e3,
+                   "serial_bz2_decode_and_apply_ms": serial_apply_s * 1e3,
+                   "reproduces_new": bool(rebuilt.tobytes() == new.tobytes() == serial_new)}
         return {"call": "dq_cuda_bsdiff_patch (pageable host buffers in, BSDIFF40 file out)", "ms": best * 1e3,
+                "patch_apply": applied,
                 "new_MBps": new.size / best / 1e6, "patch_bytes": len(patch),
                 "serial_bz2_ms": serial_s * 1e3, "serial_bz2_bytes": 32 + sum(len(x) for x in serial),
                 "sections_decode_to_the_streams": bool(same), "host_threads": len(os.sched_getaffinity(0))}

@@ -116,3 +116,4 @@ def test_diff_create_record_on_the_emulator():
         sorter.dispose()
     assert "error" not in rec, rec.get("error")
     assert rec["sections_decode_to_the_streams"] is True and rec["patch_bytes"] > 32
+    assert rec["patch_apply"]["reproduces_new"] is True
