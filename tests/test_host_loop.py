@@ -135,3 +135,40 @@ def test_certified_stretches_on_exe_like_pairs(seed, monkeypatch):
         for k in ("ctrl", "diff", "extra"):
             assert got[k] == ref[k], (seed, no_certs, shape, k)
         assert got["search_visits"] == ref["search_calls"]
+
+
+def test_certified_stretches_with_many_small_edits(monkeypatch):
+    """Dozens of stops: point overwrites, short insertions and deletions every few KiB, so the unchanged stretches between
+    them come in every length around the 256-byte threshold of a certified stretch, and many pieces hold several."""
+    import emu
+    from deltaq_b200 import CudaSuffixSort, bsdiff
+    rng = np.random.default_rng(99)
+    old = w._exe_like(400_000, np.random.default_rng(5))
+    parts, at = [], 0
+    while at < old.size:
+        keep = int(rng.choice([40, 200, 255, 256, 257, 300, 1000, 5000, 20000]))
+        parts.append(old[at:at + keep])
+        at += keep
+        kind = rng.integers(0, 3)
+        if kind == 0:                                       # overwrite a few bytes
+            k = int(rng.integers(1, 12))
+            parts.append(rng.integers(0, 256, k, dtype=np.uint8))
+            at += k
+        elif kind == 1:                                     # insert
+            parts.append(rng.integers(0, 256, int(rng.integers(1, 600)), dtype=np.uint8))
+        else:                                               # delete
+            at += int(rng.integers(1, 600))
+    new = np.concatenate(parts)
+    ref = oracle.bsdiff_streams(old, new)
+    assert len(ref["ctrl"]) // 24 > 50
+    monkeypatch.setenv("DQ_CHECK_CERTS", "1")
+    for shape in ("0,1", "3,2,16,32"):
+        monkeypatch.setenv("DQ_HOST_THREADS", shape)
+        s = CudaSuffixSort(_lib=emu.library())
+        try:
+            got = bsdiff.create_streams(old, new, s)
+        finally:
+            s.dispose()
+        for k in ("ctrl", "diff", "extra"):
+            assert got[k] == ref[k], (shape, k)
+        assert got["search_visits"] == ref["search_calls"]
