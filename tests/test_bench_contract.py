@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
@@ -24,8 +24,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["value"] == d["value"]
 
 
-def test_committed_gpu_line_has_the_contract_keys():
-    d = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_n1.json")).read())
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r01_bench_n1.json", "r02_bench_n1.json"])
+def test_committed_gpu_line_has_the_contract_keys(name):
+    d = json.loads(open(os.path.join(ROOT, "profiles", name)).read())
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "cpu_baseline"} <= set(d)
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
