@@ -470,7 +470,8 @@ template <typename Walk> inline int32_t first_best_step(Crew *crew, int32_t span
 struct Cert {
     int32_t start, len;
 };
-constexpr int32_t kCertMin = 256;  // shorter stretches are not worth a queue slot
+constexpr int32_t kCertMin = 256;      // shorter stretches are not worth a queue slot
+constexpr int32_t kZeroJobMin = 4096;  // shorter ones are not worth a writer job of their own
 
 // first_best_step for the forward walk of a piece that starts at new offset `base`, with the certified stretches of that
 // piece (ascending, disjoint).  Real steps run in whole-mode Runs (chunks on this thread, waves on the crew) and combine
@@ -973,7 +974,7 @@ inline void greedy_emit_pipelined(const uint8_t *oldData, int32_t oldLen, const 
                 for (const Cert &c : certs) {
                     const int32_t cb = (int32_t)std::min<int64_t>(pc.lenf, std::max<int64_t>(at, (int64_t)c.start - pc.lastscan));
                     const int32_t ce = (int32_t)std::min<int64_t>(pc.lenf, std::max<int64_t>(cb, (int64_t)c.start + c.len - pc.lastscan));
-                    if (ce - cb < kCertMin) continue;
+                    if (ce - cb < kZeroJobMin) continue;  // short ones stay inside the subtraction around them
                     if (cb > at) hand_out(newData + pc.lastscan + at, oldData + pc.lastpos + at, dst + at, cb - at);
                     hand_out(nullptr, nullptr, dst + cb, ce - cb);
                     at = ce;
