@@ -61,6 +61,21 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_cores_per_rank(world):
+    """The share of the host's cores one rank keeps (main() pins to it when there are two or more per rank)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 0)
+    per = cores // max(world, 1)
+    return per if (world > 1 and per >= 2) else cores
+
+
+def workload_config(world, n, m, cores_per_rank):
+    """`config` of the JSON line: the same dict from both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "old_bytes": n, "new_bytes": m, "pairs_per_step": world,
+            "l2": "working set (>= 24 B x 16.7 M pairs per radix pass, 400 MB) exceeds the 126 MB L2; no flush",
+            "parallelism": f"{world} x independent pairs (one process and context per GPU)",
+            "host_cores_per_rank": cores_per_rank}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -151,6 +166,7 @@ def run_reference(args, rank):
         return
     import oracle
     from deltaq_b200 import workloads as w
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     oracle.build()
     old, new = w.c2_exe_pair()
     sorters = cpu_sorters()
@@ -183,7 +199,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "old_bytes": int(old.size), "new_bytes": int(new.size), "sample": sample},
+        "config": workload_config(world, int(old.size), int(new.size), host_cores_per_rank(world)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sorter": best, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -428,6 +444,7 @@ def main():
     torch.cuda.set_device(local_rank)
     host_group = None
     pinned_cores = None
+    cores_per_rank = host_cores_per_rank(world)   # before this rank pins itself
     if world > 1 and hasattr(os, "sched_setaffinity"):
         # one process per GPU: every rank's host threads (the greedy loop's scan / extender / writers, the CUDA worker
         # threads) stay on their own share of the cores, so the ranks do not preempt each other; the library sizes its
@@ -571,10 +588,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "old_bytes": n, "new_bytes": m, "pairs_per_step": world,
-                       "l2": "working set (>= 24 B x 16.7 M pairs per radix pass, 400 MB) exceeds the 126 MB L2; no flush",
-                       "parallelism": f"{world} x independent pairs (one process and context per GPU)",
-                       "host_cores_per_rank": len(pinned_cores) if pinned_cores else (os.cpu_count() or 0)},
+            "config": workload_config(world, n, m, cores_per_rank),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": dt_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": n + m,
                     # the (pos,len) table crosses PCIe coded: 1 B/position + 12 B/match head + 8 B per 1024 positions

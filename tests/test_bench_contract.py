@@ -22,6 +22,13 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["value"] == d["value"]
+    # the same `config` as the GPU arm's line (the driver compares the two arms' configs); what this run sampled is
+    # said in cpu_baseline
+    gpu = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")).read())["config"]
+    assert set(d["config"]) == set(gpu)
+    assert {k: v for k, v in d["config"].items() if k != "host_cores_per_rank"} == \
+           {k: v for k, v in gpu.items() if k != "host_cores_per_rank"}
+    assert "full C2 pair" in d["cpu_baseline"]["sample"]
 
 
 import pytest
