@@ -56,3 +56,18 @@ def structured_pairs():
     out["empty_new"] = (old[:100].copy(), np.zeros(0, np.uint8))
     out["single_old"] = (np.array([5], np.uint8), np.array([5, 5, 4, 6, 5], np.uint8))
     return out
+
+
+def tiny_old_pairs(m, seed=3):
+    """`old` of 0..9 bytes against a `new` of m bytes: the coded (pos, len) table of dq_cuda_bsdiff_streams at scale with
+    almost nothing to search in, incl. a pair (9 zero bytes against m zero bytes) in which nearly every position is a
+    match head, so the head list overflows and the full table crosses instead.  Yields (name, old, new)."""
+    rng = np.random.default_rng(seed)
+    for n_old in (0, 1, 2, 9):
+        uni = rng.integers(0, 256, m, dtype=np.uint8)
+        yield f"uniform_{n_old}", rng.integers(0, 256, n_old, dtype=np.uint8), uni
+        zeros = np.zeros(m, np.uint8)
+        yield f"zeros_{n_old}", zeros[:n_old].copy(), zeros
+        mixed = rng.integers(0, 3, m, dtype=np.uint8)
+        mixed[m // 40:m // 2] = 0
+        yield f"mixed_{n_old}", mixed[:n_old].copy(), mixed

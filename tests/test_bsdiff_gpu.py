@@ -165,7 +165,6 @@ def test_diff_create_accepts_any_isuffixsort(sorter):
 def test_coded_table_overflow_falls_back_to_full_table(monkeypatch):
     # dq_cuda_bsdiff_streams ships the table as code bytes + match heads; a head list that does not fit must give
     # the same streams through the full-table path (DQ_HEADS_CAP shrinks the list for this test)
-    pass
     from deltaq_b200 import CudaSuffixSort, bsdiff
     rng = np.random.default_rng(77)
     old = rng.integers(0, 4, 6000, dtype=np.uint8)
@@ -290,3 +289,19 @@ def test_lcp_array_export(sorter):
     with pytest.raises(_native.NativeError):
         sorter.sort(random_bytes(100), np.empty(100, np.int32))
         sorter.lcp_array(t)                                               # resident array has another length
+
+
+def test_tiny_old_against_a_large_new(sorter):
+    """`old` empty or a few bytes while the coded table is active at scale; the all-zero pair overflows the
+    head list (full-table path at 2 MiB, not only at the 6 KB of the DQ_HEADS_CAP test)."""
+    from deltaq_b200 import bsdiff
+    from search_cases import tiny_old_pairs
+    fallbacks = 0
+    for name, old, new in tiny_old_pairs(2 << 20):
+        got = bsdiff.create_streams(old, new, sorter)
+        ref = oracle.bsdiff_streams(old, new)
+        for k in ("ctrl", "diff", "extra"):
+            assert got[k] == ref[k], (name, k)
+        assert got["search_visits"] == ref["search_calls"], name
+        fallbacks += sorter.stats()["table_fallbacks"]
+    assert fallbacks >= 1
