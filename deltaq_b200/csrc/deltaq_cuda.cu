@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <memory>
 #include <thread>
 #include <utility>
@@ -508,7 +509,11 @@ int segmented_round_sort(dq_ctx *ctx, SortBufs &s, uint32_t a, const rx::PassPla
 
 // host_sa_out: when not null, the caller's host array (it must be device-visible, see EarlyCopy) receives the suffix
 // array here -- overlapped with the last rounds when they are small -- and *delivered says so
-int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool *delivered = nullptr)
+// mid: when not null, called once round 0's kernels are enqueued and before the host first waits for them (not on
+// the paths that return before that: n == 0, the one-CTA sort) -- work of the caller's that should sit behind round 0 in
+// the queues, or that blocks the host while the GPU is busy with round 0 (dq_cuda_bsdiff_streams: the upload of `new`)
+int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool *delivered = nullptr,
+                  const std::function<int()> *mid = nullptr)
 {
     if (delivered) *delivered = false;
     EarlyCopy ec{};
@@ -591,6 +596,8 @@ int sort_resident(dq_ctx *ctx, uint32_t n, int32_t *host_sa_out = nullptr, bool 
     st.rounds = 1;
     st.active_sum = n;
     st.algorithmic_bytes = (int64_t)n * (41 + 24 * plan.npass);
+
+    if (mid) DQ_TRY((*mid)());
 
     uint32_t *slot_cur = ctx->slotA.as<uint32_t>(), *slot_nxt = ctx->slotB.as<uint32_t>();
     uint32_t a = 0;
@@ -1220,16 +1227,29 @@ static int bsdiff_streams_locked(dq_ctx *ctx, const uint8_t *old_, int32_t n, co
         ctx->stats.device_ms = sort_ms;
         group_search_ms = search_ms;
     } else {
+    // `old` goes up first and alone -- the sort waits for it, nothing waits for `new` before the search -- and `new`
+    // follows on the copy stream once round 0 of the sort is enqueued: the two uploads do not share the PCIe link, and
+    // where the caller's buffer is pageable (a managed caller's `fixed` span: the copy call then holds the host until
+    // the bytes are staged) the host is held while the GPU has round 0 to work on, not in front of the sort.
     DQ_TRY(ensure(ctx, ctx->newtext, (size_t)m + 64));
-    if (m) DQ_CK(ctx, cudaMemcpyAsync(ctx->newtext.p, new_, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
-    DQ_CK(ctx, cudaMemsetAsync(ctx->newtext.as<uint8_t>() + m, 0, 64, ctx->copy_stream));
-    // run ends of `new` (used by the search when the sort finds `old` full of equal-byte runs): computed now,
-    // beside the sort, rather than in front of the search
     ctx->runend_new_m = -1;
-    if (m >= (1 << 20)) DQ_TRY(run_ends_of_new(ctx, (uint32_t)m, ctx->copy_stream));
-    DQ_CK(ctx, cudaEventRecord(ctx->slice_done[0], ctx->copy_stream));
     DQ_TRY(upload_text(ctx, ctx->text, old_, (uint32_t)n, cudaMemcpyHostToDevice));
-    DQ_TRY(sort_resident(ctx, (uint32_t)n));
+    DQ_CK(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));   // (no early copy of the suffix array on this path)
+    bool new_sent = false;
+    const std::function<int()> send_new = [&]() -> int {
+        if (new_sent) return DQ_OK;
+        new_sent = true;
+        DQ_CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+        if (m) DQ_CK(ctx, cudaMemcpyAsync(ctx->newtext.p, new_, (size_t)m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        DQ_CK(ctx, cudaMemsetAsync(ctx->newtext.as<uint8_t>() + m, 0, 64, ctx->copy_stream));
+        // run ends of `new` (used by the search when the sort finds `old` full of equal-byte runs): computed
+        // beside the sort, rather than in front of the search
+        if (m >= (1 << 20)) DQ_TRY(run_ends_of_new(ctx, (uint32_t)m, ctx->copy_stream));
+        DQ_CK(ctx, cudaEventRecord(ctx->slice_done[0], ctx->copy_stream));
+        return DQ_OK;
+    };
+    DQ_TRY(sort_resident(ctx, (uint32_t)n, nullptr, nullptr, &send_new));
+    DQ_TRY(send_new());   // the sorts that return before round 0 (n == 0, one CTA)
     ctx->resident_n = n;
     ctx->resident_rounds = ctx->stats.rounds;
     if (ctx->runend_new_m == m) ctx->stats.kernel_launches += 3;  // run_ends_of_new above (the sort resets the stats)
