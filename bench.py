@@ -234,6 +234,31 @@ def round_records(acc_rounds, steps, peak):
     return out
 
 
+def abi_sort_record(ctx, text, reps):
+    """ISuffixSort.Sort as the caller sees it (wall seconds through the C ABI): dq_cuda_suffix_sort with
+    pinned host buffers, H2D of the text and D2H of the suffix array inside.  Reported, never fatal."""
+    n = int(text.size)
+    try:
+        p_t = ctx.pinned(n, np.uint8)
+        p_sa = ctx.pinned(n, np.int32)
+        try:
+            p_t.array[:] = text
+            abi = None
+            for it in range(reps + 1):
+                t0 = time.perf_counter()
+                ctx.suffix_sort(p_t.array, p_sa.array)
+                dt = time.perf_counter() - t0
+                if it and (abi is None or dt < abi):
+                    abi = dt
+            return {"abi_ms": abi * 1e3, "input_MBps_abi": n / abi / 1e6,
+                    "abi_note": "dq_cuda_suffix_sort, pinned host text in, pinned host suffix array out (4n bytes over PCIe)"}
+        finally:
+            p_t.free()
+            p_sa.free()
+    except Exception as e:
+        return {"abi_error": repr(e)}
+
+
 def sort_config_record(ctx, torch, text, name, peak, reps=3):
     """Device-resident sort of one of BASELINE's other single-GPU configs: ms, MB/s, per-round roofline."""
     n = int(text.size)
@@ -252,10 +277,12 @@ def sort_config_record(ctx, torch, text, name, peak, reps=3):
     st = ctx.stats()
     ctx.set_timing(False)
     del d_t, d_sa
-    return {"config": name, "n": n, "device_ms": best, "input_MBps_device": n / (best * 1e-3) / 1e6,
-            "rounds": st["rounds"], "launches": st["kernel_launches"],
-            "algorithmic_GBps": st["algorithmic_bytes"] / (best * 1e-3) / 1e9,
-            "per_round": round_records(rounds, 1, peak)}
+    rec = {"config": name, "n": n, "device_ms": best, "input_MBps_device": n / (best * 1e-3) / 1e6,
+           "rounds": st["rounds"], "launches": st["kernel_launches"],
+           "algorithmic_GBps": st["algorithmic_bytes"] / (best * 1e-3) / 1e9,
+           "per_round": round_records(rounds, 1, peak)}
+    rec.update(abi_sort_record(ctx, text, reps))
+    return rec
 
 
 # ---- one device group over all GPUs, driven by rank 0 (N > 1) ---------------------------------------------------------
@@ -557,9 +584,14 @@ def main():
         if world == 1:
             diff_create = diff_create_record(ctx, old, new)
             # BASELINE's other single-GPU configs, device-resident sort only (bounded: a few hundred ms in all)
-            extras = [sort_config_record(ctx, torch, w.c1_uniform(), "C1: 1 MiB uniform random bytes", peak, reps=5),
-                      sort_config_record(ctx, torch, w.c3_repetitive(), "C3: 64 MiB repetitive text", peak, reps=2),
-                      sort_config_record(ctx, torch, w.c4_genome(64 * MIB), "C4 recipe, 64 MiB slice", peak, reps=2)]
+            extras = []
+            for make, name, reps in ((w.c1_uniform, "C1: 1 MiB uniform random bytes", 5),
+                                     (w.c3_repetitive, "C3: 64 MiB repetitive text", 2),
+                                     (lambda: w.c4_genome(64 * MIB), "C4 recipe, 64 MiB slice", 2)):
+                try:
+                    extras.append(sort_config_record(ctx, torch, make(), name, peak, reps=reps))
+                except Exception as e:   # the record reports, the bench line survives
+                    extras.append({"config": name, "error": repr(e)})
         else:
             # free this rank's GPU memory, then rank 0 drives all GPUs; the others wait on the host
             del d_old, d_new, d_sa, d_pos, d_len

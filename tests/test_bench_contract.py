@@ -63,6 +63,22 @@ def test_sharded_record_on_the_emulator(monkeypatch):
     assert rec["sort_c5"]["sampled_adjacent_pairs_out_of_order"] == 0
 
 
+def test_abi_sort_record_on_the_emulator():
+    """other_configs' ABI-level timing (dq_cuda_suffix_sort with pinned host buffers) on the emulator, tiny input."""
+    import importlib.util
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu
+    from deltaq_b200 import CudaSuffixSort
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    with CudaSuffixSort(_lib=emu.library()) as s:
+        rec = bench.abi_sort_record(s.context, np.random.default_rng(1).integers(0, 256, 20000, dtype=np.uint8), 2)
+    assert "abi_error" not in rec, rec
+    assert rec["abi_ms"] > 0 and rec["input_MBps_abi"] > 0
+
+
 def _n2_worker(rank, world, port, q):
     """What bench.py does at N > 1 after the per-rank measurements: every rank drops its own work, all meet on a HOST
     barrier (gloo: no GPU kernel spins while rank 0 uses the devices), rank 0 alone drives the device group, all meet again."""
