@@ -68,6 +68,24 @@ def host_cores_per_rank(world):
     return per if (world > 1 and per >= 2) else cores
 
 
+def cores_by_physical_core(cpus, topology=None):
+    """The logical CPUs this process may run on, ordered (package, physical core, cpu): hyper-thread siblings end up side by
+    side, so when the list is dealt out in equal runs every rank gets whole physical cores -- and the cores of one
+    package -- instead of sharing a core's two threads with another rank's spinning host loop.  Without sibling pairs in
+    the set (or without sysfs) the order is the plain one."""
+    def read(c, name):
+        with open(f"/sys/devices/system/cpu/cpu{c}/topology/{name}") as f:
+            return int(f.read().strip())
+    keyed = []
+    for c in sorted(cpus):
+        try:
+            pkg, core = topology[c] if topology is not None else (read(c, "physical_package_id"), read(c, "core_id"))
+        except Exception:
+            return sorted(cpus)
+        keyed.append((pkg, core, c))
+    return [c for _, _, c in sorted(keyed)]
+
+
 def workload_config(world, n, m, cores_per_rank):
     """`config` of the JSON line: the same dict from both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "old_bytes": n, "new_bytes": m, "pairs_per_step": world,
@@ -476,7 +494,7 @@ def main():
         # one process per GPU: every rank's host threads (the greedy loop's scan / extender / writers, the CUDA worker
         # threads) stay on their own share of the cores, so the ranks do not preempt each other; the library sizes its
         # thread crew by the CPUs the process may run on
-        cores = sorted(os.sched_getaffinity(0))
+        cores = cores_by_physical_core(os.sched_getaffinity(0))
         per = len(cores) // world
         if per >= 2:
             pinned_cores = cores[local_rank * per:(local_rank + 1) * per]

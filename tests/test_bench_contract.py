@@ -63,6 +63,22 @@ def test_sharded_record_on_the_emulator(monkeypatch):
     assert rec["sort_c5"]["sampled_adjacent_pairs_out_of_order"] == 0
 
 
+def test_rank_core_shares_hold_whole_physical_cores():
+    """bench.py deals the host's logical CPUs out to the ranks in runs of the (package, core, cpu) order: with sibling
+    threads numbered i and i + 4 on two packages, two ranks get one package each and no physical core is shared."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    topo = {0: (0, 0), 1: (0, 1), 2: (1, 0), 3: (1, 1), 4: (0, 0), 5: (0, 1), 6: (1, 0), 7: (1, 1)}
+    order = bench.cores_by_physical_core(range(8), topo)
+    assert order == [0, 4, 1, 5, 2, 6, 3, 7]
+    shares = [order[r * 4:(r + 1) * 4] for r in range(2)]
+    assert {topo[c][0] for c in shares[0]} == {0} and {topo[c][0] for c in shares[1]} == {1}
+    assert bench.cores_by_physical_core([3, 1, 2], {}) == [1, 2, 3]          # no topology: the plain order
+    assert sorted(bench.cores_by_physical_core(os.sched_getaffinity(0))) == sorted(os.sched_getaffinity(0))
+
+
 def test_abi_sort_record_on_the_emulator():
     """other_configs' ABI-level timing (dq_cuda_suffix_sort with pinned host buffers) on the emulator, tiny input."""
     import importlib.util
