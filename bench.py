@@ -155,27 +155,40 @@ def cpu_sorters():
     return out
 
 
+def stream_digests(streams):
+    """Digest of each uncompressed stream (ctrl / diff / extra): how the GPU arm's result is compared with the CPU arm's."""
+    import hashlib
+    return {k: hashlib.blake2b(bytes(streams[k]) if not isinstance(streams[k], bytes) else streams[k],
+                               digest_size=16).hexdigest() for k in ("ctrl", "diff", "extra")}
+
+
 def cpu_step_times(old, new, reps):
-    """Seconds per sorter for the sort, and for the Diff.Create loop (inline Search), best of `reps`."""
+    """Seconds per sorter for the sort, and for the Diff.Create loop (inline Search), best of `reps`; the digests of the
+    streams the loop produced; whether the reference's sorters gave the same suffix array."""
     import oracle
     sort_s = {}
     sa = None
+    agree = True
     for name, fn in cpu_sorters().items():
         best = None
         for _ in range(reps):
             t0 = time.perf_counter()
-            sa = fn(old)
+            got = fn(old)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         sort_s[name] = best
+        if sa is not None and not np.array_equal(sa, got):
+            agree = False
+        sa = got
     I = oracle.make_I(sa)
     loop = None
+    streams = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        oracle.bsdiff_streams(old, new, I)
+        streams = oracle.bsdiff_streams(old, new, I)
         dt = time.perf_counter() - t0
         loop = dt if loop is None else min(loop, dt)
-    return sort_s, loop
+    return sort_s, loop, stream_digests(streams), agree
 
 
 def run_reference(args, rank):
@@ -190,10 +203,16 @@ def run_reference(args, rank):
     sorters = cpu_sorters()
     # the faster of the reference's sorters on this input carries the arm (one untimed probe each)
     probe = {}
+    agree, first = True, None
     for name, fn in sorters.items():
         t0 = time.perf_counter()
-        fn(old)
+        got = fn(old)
         probe[name] = time.perf_counter() - t0
+        if first is None:
+            first = got
+        elif not np.array_equal(first, got):
+            agree = False
+    del first, got
     best = min(probe, key=probe.get)
     sort = sorters[best]
 
@@ -218,7 +237,8 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
         "config": workload_config(world, int(old.size), int(new.size), host_cores_per_rank(world)),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sorter": best, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sorter": best, "sorters_agree": agree,
+                         "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -228,10 +248,11 @@ def cpu_baseline_once():
     from deltaq_b200 import workloads as w
     oracle.build()
     old, new = w.c2_exe_pair()
-    sort_s, loop = cpu_step_times(old, new, 2)
+    sort_s, loop, digests, agree = cpu_step_times(old, new, 2)
     best = min(sort_s, key=sort_s.get)
     dt = sort_s[best] + loop
     return {"value": new.size / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "sorter": best,
+            "sorters_agree": agree, "stream_digests": digests,
             "sort_only_MBps": {k: old.size / v / 1e6 for k, v in sort_s.items()},
             "loop_only_MBps": new.size / loop / 1e6,
             "sample": f"the full C2 pair ({old.size} -> {new.size} bytes), best of 2 per part; oracle restatements of the "
@@ -588,6 +609,9 @@ def main():
     barrier()
     dt_pageable = time.perf_counter() - t2
 
+    # what the call returned for this pair, for the comparison with the CPU arm's streams below (untimed)
+    gpu_digests = stream_digests(ctx.bsdiff_streams(old, new, copy=True)) if rank == 0 else None
+
     # max over ranks
     if world > 1:
         tt = torch.tensor([dt, dt_e2e, dt_pageable], dtype=torch.float64, device="cuda")
@@ -674,6 +698,13 @@ def main():
             "clocks": clocks,
             "cpu_baseline": cpu,
         }
+        if cpu is not None and "stream_digests" in cpu:
+            # in-run parity at the bench's own size: the streams dq_cuda_bsdiff_streams returned for this pair against the
+            # streams of the CPU restatement of Diff.Create that was just timed on the same pair (oracle/ as the checker)
+            line["parity"] = {"streams_identical_to_cpu_baseline": gpu_digests == cpu["stream_digests"],
+                              "what": "blake2b digests of the uncompressed ctrl / diff / extra streams of the C2 pair: "
+                                      "dq_cuda_bsdiff_streams (GPU arm) vs oracle.bsdiff_streams (cpu_baseline)",
+                              "gpu": gpu_digests, "cpu": cpu["stream_digests"]}
         if diff_create is not None:
             line["diff_create"] = diff_create
         if extras is not None:

@@ -29,6 +29,7 @@ def test_reference_arm_prints_one_json_line():
     assert {k: v for k, v in d["config"].items() if k != "host_cores_per_rank"} == \
            {k: v for k, v in gpu.items() if k != "host_cores_per_rank"}
     assert "full C2 pair" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["sorters_agree"] is True      # LibDivSufSort and SA-IS restatements: the same suffix array
 
 
 import pytest
@@ -77,6 +78,29 @@ def test_rank_core_shares_hold_whole_physical_cores():
     assert {topo[c][0] for c in shares[0]} == {0} and {topo[c][0] for c in shares[1]} == {1}
     assert bench.cores_by_physical_core([3, 1, 2], {}) == [1, 2, 3]          # no topology: the plain order
     assert sorted(bench.cores_by_physical_core(os.sched_getaffinity(0))) == sorted(os.sched_getaffinity(0))
+
+
+def test_in_run_parity_digests():
+    """bench.py's `parity` record compares digests of the GPU arm's streams with the CPU baseline's: the same function on
+    the emulator's streams and the oracle's, for a small pair, must give equal digests (and differ for another pair)."""
+    import importlib.util
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu
+    import oracle
+    from deltaq_b200 import CudaSuffixSort
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(5)
+    old = rng.integers(0, 4, 30000, dtype=np.uint8)
+    new = np.concatenate([old[:9000], rng.integers(0, 256, 77, dtype=np.uint8), old[9500:]])
+    with CudaSuffixSort(_lib=emu.library()) as s:
+        gpu = bench.stream_digests(s.context.bsdiff_streams(old, new, copy=True))
+        view = bench.stream_digests(s.context.bsdiff_streams(old, new, copy=False))
+    cpu = bench.stream_digests(oracle.bsdiff_streams(old, new))
+    assert gpu == cpu == view and set(gpu) == {"ctrl", "diff", "extra"}
+    assert bench.stream_digests(oracle.bsdiff_streams(old, new[:-1])) != cpu
 
 
 def test_abi_sort_record_on_the_emulator():
