@@ -289,8 +289,12 @@ def abi_sort_record(ctx, text, reps):
                 dt = time.perf_counter() - t0
                 if it and (abi is None or dt < abi):
                     abi = dt
-            return {"abi_ms": abi * 1e3, "input_MBps_abi": n / abi / 1e6,
-                    "abi_note": "dq_cuda_suffix_sort, pinned host text in, pinned host suffix array out (4n bytes over PCIe)"}
+            import oracle
+            # the array that call delivered, under the reference's own checker (LDSSChecker.cs:23-119 restated), untimed
+            bad = int(oracle.sufcheck(np.ascontiguousarray(text), p_sa.array))
+            return {"abi_ms": abi * 1e3, "input_MBps_abi": n / abi / 1e6, "sufcheck": bad,
+                    "abi_note": "dq_cuda_suffix_sort, pinned host text in, pinned host suffix array out (4n bytes over PCIe); "
+                                "sufcheck = the reference's checker on the delivered array (0 = a correct suffix array)"}
         finally:
             p_t.free()
             p_sa.free()

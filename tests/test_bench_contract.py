@@ -116,7 +116,7 @@ def test_abi_sort_record_on_the_emulator():
     with CudaSuffixSort(_lib=emu.library()) as s:
         rec = bench.abi_sort_record(s.context, np.random.default_rng(1).integers(0, 256, 20000, dtype=np.uint8), 2)
     assert "abi_error" not in rec, rec
-    assert rec["abi_ms"] > 0 and rec["input_MBps_abi"] > 0
+    assert rec["abi_ms"] > 0 and rec["input_MBps_abi"] > 0 and rec["sufcheck"] == 0
 
 
 def _n2_worker(rank, world, port, q):
