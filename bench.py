@@ -320,9 +320,9 @@ def sort_config_record(ctx, torch, text, name, peak, reps=3):
     st = ctx.stats()
     ctx.set_timing(False)
     del d_t, d_sa
-    rec = {"config": name, "n": n, "device_ms": best, "input_MBps_device": n / (best * 1e-3) / 1e6,
+    rec = {"config": name, "n": n, "device_ms": best, "input_MBps_device": n / (best * 1e-3) / 1e6 if best else None,
            "rounds": st["rounds"], "launches": st["kernel_launches"],
-           "algorithmic_GBps": st["algorithmic_bytes"] / (best * 1e-3) / 1e9,
+           "algorithmic_GBps": st["algorithmic_bytes"] / (best * 1e-3) / 1e9 if best else None,
            "per_round": round_records(rounds, 1, peak)}
     rec.update(abi_sort_record(ctx, text, reps))
     return rec

@@ -80,6 +80,28 @@ def test_rank_core_shares_hold_whole_physical_cores():
     assert sorted(bench.cores_by_physical_core(os.sched_getaffinity(0))) == sorted(os.sched_getaffinity(0))
 
 
+def test_bench_main_runs_on_the_emulator():
+    """Every line of bench.py's GPU arm (N = 1) executed here, on the emulator with small inputs (tests/bench_on_emulator.py):
+    the line carries the contract keys, the in-run parity record holds, and no extra record reports an error."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_on_emulator.py"), "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "cpu_baseline", "parity"} <= set(d)
+    assert d["steps"] == 2 and d["warmup"] == 3 and d["n_gpus"] == 1 and d["gpu_launches"] > 0
+    assert d["parity"]["streams_identical_to_cpu_baseline"] is True
+    assert d["cpu_baseline"]["sorters_agree"] is True
+    assert d["e2e"]["h2d_bytes_per_step"] == d["config"]["old_bytes"] + d["config"]["new_bytes"]
+    assert "error" not in d["diff_create"], d["diff_create"]
+    assert d["diff_create"]["sections_decode_to_the_streams"] and d["diff_create"]["patch_apply"]["reproduces_new"]
+    assert len(d["other_configs"]) == 3
+    for rec in d["other_configs"]:
+        assert "error" not in rec and "abi_error" not in rec, rec
+        assert rec["sufcheck"] == 0 and rec["rounds"] >= 1
+
+
 def test_in_run_parity_digests():
     """bench.py's `parity` record compares digests of the GPU arm's streams with the CPU baseline's: the same function on
     the emulator's streams and the oracle's, for a small pair, must give equal digests (and differ for another pair)."""
