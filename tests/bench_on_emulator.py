@@ -5,6 +5,8 @@ the workloads are scaled down.  Prints bench.py's JSON line.  Used by tests/test
 nothing.
 
     python tests/bench_on_emulator.py [bench.py arguments]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P \
+        tests/bench_on_emulator.py --gpus 2 ...      # the N > 1 flow: gloo stands in for NCCL, logical shards for GPUs
 """
 import importlib.util
 import os
@@ -37,6 +39,19 @@ def main():
         k.pop("device", None)
         return real_empty(*a, **k)
     torch.empty = empty
+    real_tensor = torch.tensor
+
+    def tensor(*a, **k):
+        k.pop("device", None)
+        return real_tensor(*a, **k)
+    torch.tensor = tensor
+    import torch.distributed as dist
+    real_init = dist.init_process_group
+
+    def init_process_group(backend=None, **k):   # N > 1: gloo stands in for NCCL
+        k.pop("device_id", None)
+        return real_init("gloo", **k)
+    dist.init_process_group = init_process_group
 
     # the workloads, scaled down (same generators)
     c2, c3, c4, c1 = w.c2_exe_pair, w.c3_repetitive, w.c4_genome, w.c1_uniform
@@ -48,6 +63,10 @@ def main():
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
+    # N > 1: the group record on logical shards of the one emulated device, tiny inputs
+    real_sharded = bench.sharded_record
+    bench.sharded_record = lambda devices, workers, **_k: real_sharded([0] * len(devices), workers=1, lib=lib, scale=2e-5)
+    os.environ.setdefault("DQ_SHARD_MIN", "1")
     bench.main()
 
 

@@ -141,50 +141,27 @@ def test_abi_sort_record_on_the_emulator():
     assert rec["abi_ms"] > 0 and rec["input_MBps_abi"] > 0 and rec["sufcheck"] == 0
 
 
-def _n2_worker(rank, world, port, q):
-    """What bench.py does at N > 1 after the per-rank measurements: every rank drops its own work, all meet on a HOST
-    barrier (gloo: no GPU kernel spins while rank 0 uses the devices), rank 0 alone drives the device group, all meet again."""
-    import importlib.util
-    os.environ["DQ_SHARD_MIN"] = "1"
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch.distributed as dist
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    host_group = dist.new_group(backend="gloo")
-    dist.barrier(group=host_group)
-    rec = None
-    if rank == 0:
-        import emu
-        spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
-        bench = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(bench)
-        rec = bench.sharded_record([0] * world, workers=1, lib=emu.library(), scale=1e-5)
-    dist.barrier(group=host_group)
-    q.put((rank, rec))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-def test_sharded_record_under_a_two_rank_gloo_job():
-    """World size 2 over gloo on the CPU: the coordination bench.py uses under torchrun (rank 0 drives all devices through
-    one group context while the other rank waits on a host-side barrier), with the logic emulator standing in for the GPUs."""
+def test_bench_main_n2_under_torchrun_on_the_emulator():
+    """bench.py's N > 1 flow exactly as the driver launches it (torch.distributed.run, one process per rank), on the
+    emulator: every rank pins itself and diffs its own pair, the timings are reduced over the ranks, every rank drops its
+    work, all meet on a HOST barrier, rank 0 alone drives the device group (`sharded` record with its in-run checks), all
+    meet again; rank 0 prints the one line.  gloo stands in for NCCL, logical shards for the GPUs."""
     import socket
-    import torch.multiprocessing as mp
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_n2_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = dict(q.get(timeout=600) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    assert results[1] is None
-    rec = results[0]
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "bench_on_emulator.py"), "--gpus", "2", "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1                      # rank 0 alone prints
+    d = json.loads(lines[0])
+    assert BASE_KEYS | {"gpu_launches", "roofline", "cpu_baseline", "parity", "sharded"} <= set(d)
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["config"]["pairs_per_step"] == 2
+    assert d["parity"]["streams_identical_to_cpu_baseline"] is True
+    rec = d["sharded"]
     assert "error" not in rec, rec.get("error")
     assert rec["devices"] == [0, 0] and rec["sort_c4"]["sufcheck"] == 0
     assert rec["sort_search_256MiB"]["table_equals_one_gpu_table"] is True
