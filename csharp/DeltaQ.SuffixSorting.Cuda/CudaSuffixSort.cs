@@ -7,6 +7,7 @@
 // reference lacks (Diff.Search is private static, Diff.cs:267): ISuffixSearch.
 using System;
 using System.Buffers;
+using System.Collections.Generic;
 using System.Runtime.InteropServices;
 
 namespace DeltaQ.SuffixSorting.Cuda;
@@ -56,11 +57,14 @@ internal sealed unsafe class PinnedSuffixOwner : MemoryManager<int>
 {
     private IntPtr _p;
     private readonly int _length;
+    private readonly int _capacity;
+    private readonly PinnedPool? _pool;
 
-    public PinnedSuffixOwner(int length)
+    public PinnedSuffixOwner(int length, PinnedPool? pool = null)
     {
         _length = length;
-        Native.Check(IntPtr.Zero, Native.dq_cuda_host_alloc(out _p, (nuint)Math.Max(1, length) * sizeof(int)));
+        _pool = pool;
+        (_p, _capacity) = pool?.Rent(length) ?? PinnedPool.Allocate(length);
     }
 
     public override Span<int> GetSpan() => new((void*)_p, _length);
@@ -69,7 +73,62 @@ internal sealed unsafe class PinnedSuffixOwner : MemoryManager<int>
 
     protected override void Dispose(bool disposing)
     {
-        if (_p != IntPtr.Zero) { Native.dq_cuda_host_free(_p); _p = IntPtr.Zero; }
+        if (_p == IntPtr.Zero) return;
+        if (_pool is null || !_pool.Return(_p, _capacity)) Native.dq_cuda_host_free(_p);
+        _p = IntPtr.Zero;
+    }
+}
+
+/// <summary>The provider's ArrayPool: the reference rents its owners from one (MemoryOwner&lt;int&gt;.Allocate,
+/// LibDivSufSort.cs:14), so Sort(asset).Dispose() in a loop (SuffixSortingBenchmarks.cs:63-73) reuses one array. Pinning is
+/// dear -- cudaHostAlloc of a few MiB costs as much as sorting them -- so a disposed owner's buffer is kept (a few, of
+/// moderate size) for the next Sort. Same policy as deltaq_b200/suffix_sort.py.</summary>
+internal sealed unsafe class PinnedPool
+{
+    private const int Keep = 4;
+    private const long MaxBytes = 256L << 20;
+    private readonly List<(IntPtr p, int capacity)> _free = new();
+    private bool _closed;
+
+    public static (IntPtr, int) Allocate(int length)
+    {
+        int cap = Math.Max(1, length);
+        if (cap < (16 << 20)) cap = (int)System.Numerics.BitOperations.RoundUpToPowerOf2((uint)cap);
+        Native.Check(IntPtr.Zero, Native.dq_cuda_host_alloc(out var p, (nuint)cap * sizeof(int)));
+        return (p, cap);
+    }
+
+    public (IntPtr, int) Rent(int length)
+    {
+        lock (_free)
+        {
+            int best = -1;
+            for (int i = 0; i < _free.Count; i++)
+                if (_free[i].capacity >= length && _free[i].capacity <= Math.Max(2L * length, 1024) &&
+                    (best < 0 || _free[i].capacity < _free[best].capacity)) best = i;
+            if (best >= 0) { var hit = _free[best]; _free.RemoveAt(best); return hit; }
+        }
+        return Allocate(length);
+    }
+
+    public bool Return(IntPtr p, int capacity)
+    {
+        lock (_free)
+        {
+            if (_closed || (long)capacity * sizeof(int) > MaxBytes || _free.Count >= Keep) return false;
+            _free.Add((p, capacity));
+            return true;
+        }
+    }
+
+    public void Close()
+    {
+        lock (_free)
+        {
+            _closed = true;
+            foreach (var (p, _) in _free) Native.dq_cuda_host_free(p);
+            _free.Clear();
+        }
     }
 }
 
@@ -77,6 +136,7 @@ public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposa
 {
     private IntPtr _ctx;
     internal IntPtr Handle => _ctx;   // CudaDiff.Create drives the same native context
+    private readonly PinnedPool _pool = new();
     private readonly object _gate = new();
     internal object Gate => _gate;    // CudaDiff.Create holds it while it reads the context-owned streams
 
@@ -98,8 +158,9 @@ public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposa
 
     public IMemoryOwner<int> Sort(ReadOnlySpan<byte> textBuffer)
     {
-        var owner = new PinnedSuffixOwner(textBuffer.Length);
-        Sort(textBuffer, owner.GetSpan());
+        var owner = new PinnedSuffixOwner(textBuffer.Length, _pool);
+        try { Sort(textBuffer, owner.GetSpan()); }
+        catch { ((IDisposable)owner).Dispose(); throw; }
         return owner;
     }
 
@@ -140,6 +201,7 @@ public sealed unsafe class CudaSuffixSort : ISuffixSort, ISuffixSearch, IDisposa
 
     public void Dispose()
     {
+        _pool.Close();
         if (_ctx != IntPtr.Zero) { Native.dq_cuda_destroy(_ctx); _ctx = IntPtr.Zero; }
     }
 }

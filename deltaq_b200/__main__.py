@@ -4,6 +4,10 @@ section 8(f) rank 4).  Same arguments, same messages:
 
     python -m deltaq_b200 bsdiff  <oldfile> <newfile> <deltafile> [-ss cuda] [--devices 0,1,...]
     python -m deltaq_b200 bspatch <oldfile> <deltafile> <newfile>
+    python -m deltaq_b200 bench   [--sizes 0,1,...] [--reps K] [--devices 0,1,...]
+
+`bench` is the `cuda` column of the reference's suffix-sorting benchmark (bench/DeltaQ.Benchmarks/SuffixSortingBenchmarks.cs:
+`[Benchmark] public void cuda(string name, byte[] asset) => CUDA.Sort(asset).Dispose();` over its `Randoms`, :27-57).
 
 `-ss` accepts only `cuda` here (the reference's `sais` / `divsufsort` providers live in the reference; this package has
 no CPU sorter).  bspatch is host code (dq_cuda_bspatch) and needs no GPU.
@@ -82,6 +86,38 @@ def bspatch_command(args):
     return 0
 
 
+def benchmark_sizes():
+    """SuffixSortingBenchmarks.Sizes (SuffixSortingBenchmarks.cs:27-53)."""
+    return [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768] + \
+        [i * 1024 for i in range(64, 1025, 64)]
+
+
+def bench_command(args, _lib=None):
+    """One line per size: the call the reference's harness times -- Sort(asset) -> owner, Dispose() -- mean and best of
+    `reps` after one warm-up call.  Random bytes seeded like the reference's buffers (63*13*63*13; .NET's generator is
+    not reproducible here, any seeded uniform stream is the same benchmark)."""
+    from . import CudaSuffixSort
+    sizes = [int(x) for x in args.sizes.split(",")] if args.sizes else benchmark_sizes()
+    device = [int(x) for x in args.devices.split(",")] if args.devices else None
+    if device is not None and len(device) == 1:
+        device = device[0]
+    print("| Method | name | Mean | Best | MB/s (best) |")
+    print("|------- |----- |-----:|-----:|------------:|")
+    with CudaSuffixSort(device=device, _lib=_lib) as sort:
+        for size in sizes:
+            asset = np.random.default_rng(63 * 13 * 63 * 13).integers(0, 256, size, dtype=np.uint8)
+            sort.sort(asset).dispose()
+            times = []
+            for _ in range(max(1, args.reps)):
+                t0 = time.perf_counter()
+                sort.sort(asset).dispose()
+                times.append(time.perf_counter() - t0)
+            mean, best = sum(times) / len(times), min(times)
+            rate = f"{size / best / 1e6:.1f}" if size else "-"
+            print(f"| cuda | {size} | {mean * 1e6:,.1f} us | {best * 1e6:,.1f} us | {rate} |")
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="dq", description="DeltaQ binary diff and patch tool (CUDA provider)")
     sub = ap.add_subparsers(dest="command")
@@ -96,7 +132,13 @@ def main(argv=None):
     p.add_argument("oldfile", help="Original file (input)")
     p.add_argument("deltafile", help="Delta file (input)")
     p.add_argument("newfile", help="New file (output)")
+    b = sub.add_parser("bench", help="Suffix-sorting benchmark: the cuda column of SuffixSortingBenchmarks")
+    b.add_argument("--sizes", help="comma separated sizes (default: the reference's list, 0 .. 1 MiB)")
+    b.add_argument("--reps", type=int, default=10)
+    b.add_argument("--devices", help="CUDA ordinals, comma separated")
     args = ap.parse_args(argv)
+    if args.command == "bench":
+        return bench_command(args)
     if args.command == "bsdiff":
         return bsdiff_command(args)
     if args.command == "bspatch":

@@ -32,15 +32,19 @@ class SuffixArrayOwner:
     """IMemoryOwner<int> analogue: ``.memory`` is an int32 array of length n over pinned host memory;
     ``dispose()`` (or the context manager) releases it (README.md:108-110 of the reference)."""
 
-    def __init__(self, pinned, n):
+    def __init__(self, pinned, n, release=None):
         self._pinned = pinned
+        self._release = release        # hands the buffer back to the provider's pool; None: free it
         self.memory = pinned.array[:n]
 
     def dispose(self):
         if self._pinned is not None:
             self.memory = None
-            self._pinned.free()
-            self._pinned = None
+            pinned, self._pinned = self._pinned, None
+            if self._release is not None:
+                self._release(pinned)
+            else:
+                pinned.free()
 
     def __enter__(self):
         return self
@@ -53,11 +57,48 @@ class CudaSuffixSort:
     """ISuffixSort provider backed by libdeltaq_cuda.  Holds a native context (device, stream, scratch);
     disposable; one call in flight per instance.  Raises if the CUDA library or device is missing."""
 
+    # The owners Sort(text) hands out sit on pinned host memory, and pinning is dear (cudaHostAlloc of a few MiB costs as
+    # much as sorting them).  The reference rents its owners from a pool (MemoryOwner<int>.Allocate -> ArrayPool,
+    # LibDivSufSort.cs:14), so Sort(asset).Dispose() in a loop -- its benchmark, SuffixSortingBenchmarks.cs:63-73 -- reuses
+    # one array; so does this provider: a disposed owner's buffer is kept (a few, of moderate size) for the next Sort.
+    _POOL_KEEP = 4
+    _POOL_MAX_BYTES = 256 << 20
+
     def __init__(self, device=None, _lib=None):
+        import threading
         self._ctx = _native.Context(device=device, lib=_lib)
+        self._pool = []
+        self._pool_lock = threading.Lock()
+        self._closed = False
+
+    def _rent(self, n):
+        """A pinned int32 buffer of at least n entries: the smallest kept one that fits without being more than twice too
+        big, else a new one (capacities below 16 Mi entries are rounded up to a power of two, like ArrayPool's buckets)."""
+        with self._pool_lock:
+            fit = [b for b in self._pool if n <= b.array.size <= max(2 * n, 1024)]
+            if fit:
+                best = min(fit, key=lambda b: b.array.size)
+                self._pool.remove(best)
+                return best
+        cap = max(1, n)
+        if cap < (16 << 20):
+            cap = 1 << (cap - 1).bit_length()
+        return self._ctx.pinned(cap, np.int32)
+
+    def _give_back(self, pinned):
+        with self._pool_lock:
+            if not self._closed and pinned.array.nbytes <= self._POOL_MAX_BYTES and len(self._pool) < self._POOL_KEEP:
+                self._pool.append(pinned)
+                return
+        pinned.free()
 
     # -- IDisposable
     def dispose(self):
+        with self._pool_lock:
+            self._closed = True
+            pool, self._pool = self._pool, []
+        for b in pool:
+            b.free()
         self._ctx.close()
 
     close = dispose
@@ -79,9 +120,13 @@ class CudaSuffixSort:
         t = as_bytes_array(text)
         if suffixes is None:
             # overload 1: ISuffixSort.cs:18 -- allocate, sort, hand the owner to the caller
-            pinned = self._ctx.pinned(max(1, t.size), np.int32)
-            owner = SuffixArrayOwner(pinned, t.size)
-            self._ctx.suffix_sort(t, pinned.array)
+            pinned = self._rent(t.size)
+            owner = SuffixArrayOwner(pinned, t.size, release=self._give_back)
+            try:
+                self._ctx.suffix_sort(t, pinned.array)
+            except BaseException:
+                owner.dispose()
+                raise
             return owner
         # overload 2: ISuffixSort.cs:27
         if suffixes is None or not isinstance(suffixes, np.ndarray) or suffixes.dtype != np.int32:

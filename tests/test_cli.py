@@ -55,3 +55,28 @@ def test_bsdiff_cli_roundtrip(tmp_path):
     assert (tmp_path / "rebuilt").read_bytes() == new.tobytes()
     r = _run("bsdiff", str(tmp_path / "old"), str(tmp_path / "new"), str(tmp_path / "delta"), "-ss", "sais")
     assert r.returncode != 0
+
+
+def test_bench_sizes_are_the_references():
+    """SuffixSortingBenchmarks.cs:27-53: 0, the powers of two up to 32768, then 64 KiB .. 1 MiB in steps of 64 KiB."""
+    from deltaq_b200.__main__ import benchmark_sizes
+    s = benchmark_sizes()
+    assert s[:4] == [0, 1, 2, 4] and s[16] == 32768 and s[17] == 65536 and s[-1] == 1048576 and len(s) == 17 + 16
+
+
+def test_bench_command_on_the_emulator(capsys):
+    """The `cuda` column of the reference's benchmark, on the emulator with a few small sizes (the numbers mean nothing)."""
+    import argparse
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu
+    from deltaq_b200.__main__ import bench_command
+    rc = bench_command(argparse.Namespace(sizes="0,1,51,5000", reps=2, devices=None), _lib=emu.library())
+    out = capsys.readouterr().out
+    assert rc == 0 and out.count("| cuda |") == 4 and "| cuda | 5000 |" in out
+
+
+@pytest.mark.gpu
+def test_bench_cli_gpu():
+    r = _run("bench", "--sizes", "0,1,4096,65536,1048576", "--reps", "3")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("| cuda |") == 5 and "| cuda | 1048576 |" in r.stdout

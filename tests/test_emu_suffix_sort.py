@@ -127,3 +127,34 @@ def test_segmented_sort_of_small_groups(sorter, name, monkeypatch):
         sa = np.empty(t.size, dtype=np.int32)
         sorter.sort(t, sa)
         assert np.array_equal(sa, oracle.sais(t))
+
+
+def test_owners_are_rented_from_a_pool():
+    """Sort(text) -> IMemoryOwner<int>: the reference rents from ArrayPool (LibDivSufSort.cs:14), so Sort(asset).Dispose()
+    in a loop reuses one array; the provider keeps a disposed owner's pinned buffer for the next Sort.  A reused buffer is
+    dirty (the sorter must not need zeroed output: SURVEY 8(b)), owners of different sizes coexist, and an owner that
+    outlives its provider is still released."""
+    import emu
+    from deltaq_b200 import CudaSuffixSort
+    rng = np.random.default_rng(3)
+    with CudaSuffixSort(_lib=emu.library()) as s:
+        t1 = rng.integers(0, 4, 3000, dtype=np.uint8)
+        o1 = s.sort(t1)
+        addr = o1.memory.ctypes.data
+        assert o1.memory.size == t1.size and np.array_equal(o1.memory, oracle.sais(t1))
+        o1.dispose()
+        o1.dispose()                                       # idempotent
+        t2 = rng.integers(0, 256, 2500, dtype=np.uint8)    # fits the kept buffer (capacity 4096)
+        with s.sort(t2) as o2:
+            assert o2.memory.ctypes.data == addr and o2.memory.size == t2.size
+            assert np.array_equal(o2.memory, oracle.sais(t2))
+            t3 = rng.integers(0, 2, 70000, dtype=np.uint8)  # while o2 is out: another buffer
+            with s.sort(t3) as o3:
+                assert o3.memory.ctypes.data != addr and np.array_equal(o3.memory, oracle.sais(t3))
+        with s.sort(np.zeros(0, np.uint8)) as o0:
+            assert o0.memory.size == 0
+        assert 1 <= len(s._pool) <= s._POOL_KEEP
+        late = s.sort(t1)
+    assert s._pool == []
+    assert np.array_equal(late.memory, oracle.sais(t1))    # still readable after the provider is gone
+    late.dispose()                                          # freed, not pooled
