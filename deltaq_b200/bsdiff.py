@@ -117,6 +117,10 @@ class Diff:
             # one native call: streams as create_streams(), header and sections assembled in the library
             # (dq_cuda_bsdiff_patch); the bytes and the final stream position are those of the general path below
             output.write(suffix_sort.context.bsdiff_patch(o, w))
+            # the reference ends with Seek calls (Diff.cs:237-241), which push a buffering stream's bytes down: its own
+            # test reads the wrapped MemoryStream right after Create (BsPatchTests.cs:25-29)
+            if hasattr(output, "flush"):
+                output.flush()
             return
 
         header = bytearray(HEADER_SIZE)

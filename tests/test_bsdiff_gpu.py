@@ -305,3 +305,21 @@ def test_tiny_old_against_a_large_new(sorter):
         assert got["search_visits"] == ref["search_calls"], name
         fallbacks += sorter.stats()["table_fallbacks"]
     assert fallbacks >= 1
+
+
+def test_patch_and_output_are_flushed_through_buffering_streams(sorter):
+    """BsPatchTests.cs:18-38 (BsPatchFlushesOutput): Create and Apply write through buffering wrappers, and the test reads
+    the wrapped streams directly afterwards -- so both must have pushed their bytes down."""
+    import io
+    from conftest import random_bytes
+    from deltaq_b200.bsdiff import Diff, Patch
+    old, new = random_bytes(0x123, seed=21), random_bytes(0x4567, seed=22)
+    patch_ms = io.BytesIO()
+    wrapped_patch = io.BufferedRandom(patch_ms, buffer_size=1 << 20)      # (kept alive: closing it closes patch_ms)
+    Diff.create(old, new, wrapped_patch, sorter)
+    patch = patch_ms.getvalue()
+    assert patch[:8] == b"BSDIFF40"
+    rebuilt_ms = io.BytesIO()
+    wrapped_rebuilt = io.BufferedRandom(rebuilt_ms, buffer_size=1 << 20)
+    Patch.apply(old, patch, wrapped_rebuilt)
+    assert rebuilt_ms.getvalue() == new.tobytes()
