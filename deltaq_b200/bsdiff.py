@@ -147,13 +147,52 @@ class Diff:
 class Patch:
     @staticmethod
     def apply(old_data, patch, output):
-        """Patch.Apply(ReadOnlyMemory<byte> input, ReadOnlyMemory<byte> diff, Stream output), Patch.cs:25-36."""
+        """Patch.Apply, both overloads (Patch.cs:25-50):
+        (input bytes, patch bytes, output stream) -- Patch.cs:25-36;
+        (input stream, open_patch_stream(offset, length) -> stream, output stream) -- Patch.cs:44-50, where length 0 means
+        "the rest of the patch" (Patch.cs:15-17) and the streams must be readable and seekable (:60-63, :97-100)."""
+        if output is None:
+            raise TypeError("output must not be None")
+        if hasattr(output, "writable") and not output.writable():
+            raise ValueError("Output stream must be writable")          # Patch.cs:101-102
+        if callable(patch):
+            old_data, patch = Patch._read_streams(old_data, patch)
         o = as_bytes_array(old_data, "input")
         # header checks (:52-70), the three sections un-bzip2'ed block-parallel, the add loop (:95-168): one native call
         out = _native.bspatch(o, np.frombuffer(bytes(patch), dtype=np.uint8))
         output.write(out.tobytes())
         if hasattr(output, "flush"):
             output.flush()
+
+    @staticmethod
+    def _read_streams(input_stream, open_patch_stream):
+        """The stream overload's reading side: CreatePatchStreams (Patch.cs:52-93) up to the compressed sections."""
+        if input_stream is None:
+            raise TypeError("input must not be None")
+        with open_patch_stream(0, HEADER_SIZE) as hs:
+            if not hs.readable():
+                raise ValueError("Patch stream must be readable")       # ArgumentException, Patch.cs:60-61
+            if not hs.seekable():
+                raise ValueError("Patch stream must be seekable")       # Patch.cs:62-63
+            header = hs.read(HEADER_SIZE)
+        if len(header) < HEADER_SIZE or read_packed_long(header[0:8]) != SIGNATURE:
+            raise RuntimeError("Corrupt patch")                         # InvalidOperationException, Patch.cs:68-70
+        ctrl_len = read_packed_long(header[8:16])
+        diff_len = read_packed_long(header[16:24])
+        if ctrl_len < 0 or diff_len < 0 or read_packed_long(header[24:32]) < 0:
+            raise RuntimeError("Corrupt patch")                         # Patch.cs:77-78
+        parts = [bytes(header)]
+        for off, ln in ((HEADER_SIZE, ctrl_len), (HEADER_SIZE + ctrl_len, diff_len), (HEADER_SIZE + ctrl_len + diff_len, 0)):
+            with open_patch_stream(off, ln) as st:                      # Patch.cs:82-85
+                part = st.read() if ln == 0 else st.read(ln)
+            if ln and len(part) != ln:
+                raise RuntimeError("Corrupt patch")
+            parts.append(part)
+        if not input_stream.readable():
+            raise ValueError("Input stream must be readable")           # Patch.cs:97-98
+        if not input_stream.seekable():
+            raise ValueError("Input stream must be seekable")           # Patch.cs:99-100
+        return np.frombuffer(input_stream.read(), dtype=np.uint8), b"".join(parts)
 
     @staticmethod
     def apply_reference_order(old_data, patch, output):

@@ -295,3 +295,72 @@ def test_patch_and_output_are_flushed_through_buffering_streams(sorter):
     wrapped_rebuilt = io.BufferedRandom(rebuilt_ms, buffer_size=1 << 20)
     Patch.apply(old, patch, wrapped_rebuilt)
     assert rebuilt_ms.getvalue() == new.tobytes()
+
+
+@pytest.mark.parametrize("size", [0, 1, 512, 999, 1024, 4096])
+def test_roundtrip_from_streams(sorter, size):
+    """BsDiffTests.cs:57-78 (BsDiffRoundtripFromStreams): Create writes into a fixed 0x2000-byte memory stream; Apply takes
+    the old data as a stream and the patch through an open-stream callback (offset, length; length 0 = the rest -- so
+    the last section is followed by the unused tail of the buffer, which the reader must leave alone)."""
+    import io
+    from conftest import random_bytes
+    from deltaq_b200.bsdiff import Diff, Patch
+    old, new = random_bytes(size), random_bytes(size, seed=77)
+    memory = io.BytesIO(bytes(0x2000))
+    Diff.create(old, new, memory, sorter)
+    buf = memory.getvalue()
+    assert len(buf) == 0x2000
+
+    def open_patch_stream(start, length):
+        return io.BytesIO(buf[start:start + length] if length > 0 else buf[start:])
+
+    out = io.BytesIO()
+    Patch.apply(io.BytesIO(old.tobytes()), open_patch_stream, out)
+    assert out.getvalue() == new.tobytes()
+
+
+def test_apply_stream_argument_checks(sorter):
+    """Patch.cs:60-63, :97-102: unreadable / unseekable patch or input streams and an unwritable output are argument
+    errors; a bad signature or negative header fields are a corrupt patch (:68-78)."""
+    import io
+    from conftest import random_bytes
+    from deltaq_b200.bsdiff import Diff, Patch
+    old, new = random_bytes(600), random_bytes(700, seed=5)
+    ms = io.BytesIO()
+    Diff.create(old, new, ms, sorter)
+    buf = ms.getvalue()
+
+    class Pipe(io.BytesIO):
+        def seekable(self):
+            return False
+
+    class WriteOnly(io.BytesIO):
+        def readable(self):
+            return False
+
+    def opener(kind=io.BytesIO, data=buf):
+        return lambda start, length: kind(data[start:start + length] if length > 0 else data[start:])
+
+    with pytest.raises(ValueError, match="Patch stream must be seekable"):
+        Patch.apply(io.BytesIO(old.tobytes()), opener(Pipe), io.BytesIO())
+    with pytest.raises(ValueError, match="Patch stream must be readable"):
+        Patch.apply(io.BytesIO(old.tobytes()), opener(WriteOnly), io.BytesIO())
+    with pytest.raises(ValueError, match="Input stream must be seekable"):
+        Patch.apply(Pipe(old.tobytes()), opener(), io.BytesIO())
+    with pytest.raises(ValueError, match="Input stream must be readable"):
+        Patch.apply(WriteOnly(old.tobytes()), opener(), io.BytesIO())
+
+    class ReadOnly(io.BytesIO):
+        def writable(self):
+            return False
+
+    with pytest.raises(ValueError, match="Output stream must be writable"):
+        Patch.apply(io.BytesIO(old.tobytes()), opener(), ReadOnly())
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        Patch.apply(io.BytesIO(old.tobytes()), opener(data=b"BSDIFF41" + buf[8:]), io.BytesIO())
+    negative = buf[:15] + bytes([buf[15] | 0x80]) + buf[16:]          # ctrl length with the sign bit set
+    with pytest.raises(RuntimeError, match="Corrupt patch"):
+        Patch.apply(io.BytesIO(old.tobytes()), opener(data=negative), io.BytesIO())
+    out = io.BytesIO()
+    Patch.apply(io.BytesIO(old.tobytes()), opener(), out)
+    assert out.getvalue() == new.tobytes()
