@@ -5,9 +5,14 @@ section 8(f) rank 4).  Same arguments, same messages:
     python -m deltaq_b200 bsdiff  <oldfile> <newfile> <deltafile> [-ss cuda] [--devices 0,1,...]
     python -m deltaq_b200 bspatch <oldfile> <deltafile> <newfile>
     python -m deltaq_b200 bench   [--sizes 0,1,...] [--reps K] [--devices 0,1,...]
+    python -m deltaq_b200 fuzz    [file ...]          (no file: the input is read from stdin)
 
 `bench` is the `cuda` column of the reference's suffix-sorting benchmark (bench/DeltaQ.Benchmarks/SuffixSortingBenchmarks.cs:
 `[Benchmark] public void cuda(string name, byte[] asset) => CUDA.Sort(asset).Dispose();` over its `Randoms`, :27-57).
+
+`fuzz` is the reference's fuzz target (Fuzzing/Commands.Fuzz.cs:22-38, built there under `#if FUZZ`): sort the input, then
+SuffixSortingVerifier.Verify (Fuzzing/SuffixSortingVerifier.cs:7-22) -- every suffix strictly below the next -- with the CUDA
+provider in the place of GoSAIS.
 
 `-ss` accepts only `cuda` here (the reference's `sais` / `divsufsort` providers live in the reference; this package has
 no CPU sorter).  bspatch is host code (dq_cuda_bspatch) and needs no GPU.
@@ -118,6 +123,38 @@ def bench_command(args, _lib=None):
     return 0
 
 
+def suffix_less(t, a, b):
+    """t[a:] < t[b:] as Span.SequenceCompareTo orders them (first difference, else the shorter one first), without copying
+    the suffixes whole: windows that double in size."""
+    step = 64
+    while True:
+        x, y = t[a:a + step], t[b:b + step]
+        if x != y:
+            return x < y
+        if len(x) < step:       # both ran out together: only when a == b
+            return False
+        a += step
+        b += step
+        step = min(step * 2, 1 << 20)
+
+
+def verify_suffix_array(t, sa):
+    """SuffixSortingVerifier.Verify: InvalidOperationException("Input was unsorted") -> RuntimeError with (i, j)."""
+    for i in range(len(t) - 1):
+        if not suffix_less(t, int(sa[i]), int(sa[i + 1])):
+            raise RuntimeError(f"Input was unsorted (i = {i}, j = {i + 1})")
+
+
+def fuzz_command(args, _lib=None):
+    from . import CudaSuffixSort
+    inputs = [open(p, "rb").read() for p in args.files] if args.files else [sys.stdin.buffer.read()]
+    with CudaSuffixSort(_lib=_lib) as sort:
+        for data in inputs:
+            with sort.sort(np.frombuffer(data, dtype=np.uint8)) as owner:
+                verify_suffix_array(data, owner.memory)
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="dq", description="DeltaQ binary diff and patch tool (CUDA provider)")
     sub = ap.add_subparsers(dest="command")
@@ -136,7 +173,11 @@ def main(argv=None):
     b.add_argument("--sizes", help="comma separated sizes (default: the reference's list, 0 .. 1 MiB)")
     b.add_argument("--reps", type=int, default=10)
     b.add_argument("--devices", help="CUDA ordinals, comma separated")
+    f = sub.add_parser("fuzz", help="Fuzz target: sort the input with the CUDA provider and verify the suffix array")
+    f.add_argument("files", nargs="*", help="inputs (default: stdin)")
     args = ap.parse_args(argv)
+    if args.command == "fuzz":
+        return fuzz_command(args)
     if args.command == "bench":
         return bench_command(args)
     if args.command == "bsdiff":

@@ -80,3 +80,35 @@ def test_bench_cli_gpu():
     r = _run("bench", "--sizes", "0,1,4096,65536,1048576", "--reps", "3")
     assert r.returncode == 0, r.stderr
     assert r.stdout.count("| cuda |") == 5 and "| cuda | 1048576 |" in r.stdout
+
+
+def test_fuzz_target_on_the_emulator():
+    """The reference's fuzz target (Commands.Fuzz.cs) with the CUDA provider, over the reference's own fuzz corpus
+    (test/assets, copied to tests/golden/assets) on the emulator; its verifier must reject a wrong array."""
+    import argparse
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu
+    from conftest import GOLDEN, asset_names
+    from deltaq_b200.__main__ import fuzz_command, suffix_less, verify_suffix_array
+    files = [os.path.join(GOLDEN, "assets", n) for n in asset_names()]
+    assert len(files) == 13
+    assert fuzz_command(argparse.Namespace(files=files), _lib=emu.library()) == 0
+    t = b"banana"
+    verify_suffix_array(t, [5, 3, 1, 0, 4, 2])
+    with pytest.raises(RuntimeError, match="Input was unsorted"):
+        verify_suffix_array(t, [5, 1, 3, 0, 4, 2])
+    with pytest.raises(RuntimeError, match="Input was unsorted"):
+        verify_suffix_array(t, [5, 5, 3, 1, 0, 4])              # a repeated entry is not "strictly below"
+    long = bytes(1000) + b"\x01" + bytes(1000)
+    assert suffix_less(long, 0, 1) and not suffix_less(long, 1, 0)   # the longer run of zeros in front of the 1 sorts first
+    assert suffix_less(long, 1500, 1400) and not suffix_less(long, 1400, 1500)   # all zeros: the shorter suffix first
+
+
+@pytest.mark.gpu
+def test_fuzz_cli_gpu():
+    from conftest import GOLDEN, asset_names
+    r = _run("fuzz", *[os.path.join(GOLDEN, "assets", n) for n in asset_names()])
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([sys.executable, "-m", "deltaq_b200", "fuzz"], cwd=ROOT, input=b"mississippi", capture_output=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
